@@ -1,0 +1,483 @@
+"""aho_corasick_b200 -- host-side mirror of the reference's search API over libacb200.so.
+
+The names, argument meaning and error behaviour follow BurntSushi/aho-corasick 1.1.3
+(`AhoCorasick`, `AhoCorasickBuilder`, `MatchKind`, `StartKind`, `AhoCorasickKind`, `Match`,
+`find_iter`, `find_overlapping_iter`, `try_*`; src/ahocorasick.rs, src/lib.rs:239-251), so the
+parity tests read like the reference's own.  Everything that touches a haystack goes through the
+C ABI (include/acb200.h) into hand-written sm_100a kernels; there is no CPU search path here.
+Python is test/bench glue only: the product is the shared library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libacb200.so"
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def _load():
+    if not _LIB_PATH.exists():
+        raise NativeLibraryMissing(
+            f"{_LIB_PATH} is missing: build it with `python aho-corasick_b200/build.py` "
+            "(nvcc, sm_100a). There is no fallback implementation.")
+    return C.CDLL(str(_LIB_PATH))
+
+
+_lib = _load()
+
+
+class MatchKind(enum.IntEnum):  # src/util/search.rs:1052
+    Standard = 0
+    LeftmostFirst = 1
+    LeftmostLongest = 2
+
+
+class StartKind(enum.IntEnum):  # src/util/search.rs:1133
+    Unanchored = 0
+    Anchored = 1
+    Both = 2
+
+
+class AhoCorasickKind(enum.IntEnum):  # src/ahocorasick.rs:2624
+    NoncontiguousNFA = 1
+    ContiguousNFA = 2
+    DFA = 3
+
+
+class Anchored(enum.IntEnum):  # src/util/search.rs:784
+    No = 0
+    Yes = 1
+
+
+class Engine(enum.IntEnum):
+    Auto = 0
+    Walk = 1
+    Prefilter = 2
+    Sequential = 3
+
+
+E_OVERFLOW = -21
+
+
+class BuildError(Exception):  # src/util/error.rs:23-49
+    def __init__(self, code):
+        super().__init__(_lib.acg_strerror(code).decode())
+        self.code = code
+
+
+class MatchError(Exception):  # src/util/error.rs:140-223
+    def __init__(self, code):
+        super().__init__(_lib.acg_strerror(code).decode())
+        self.code = code
+
+    @property
+    def kind(self):
+        return {-10: "InvalidInputAnchored", -11: "InvalidInputUnanchored", -12: "UnsupportedStream",
+                -13: "UnsupportedOverlapping", -14: "UnsupportedEmpty"}.get(self.code, "Boundary")
+
+
+class DeviceError(RuntimeError):
+    def __init__(self, code):
+        super().__init__(_lib.acg_strerror(code).decode())
+        self.code = code
+
+
+class _BuildOpts(C.Structure):
+    _fields_ = [("match_kind", C.c_int32), ("start_kind", C.c_int32),
+                ("ascii_case_insensitive", C.c_int32), ("byte_classes", C.c_int32),
+                ("prefilter", C.c_int32), ("kind", C.c_int32), ("dense_depth", C.c_int64)]
+
+
+class _Desc(C.Structure):
+    _fields_ = [("trans", C.POINTER(C.c_uint32)), ("trans_len", C.c_uint64),
+                ("stride2", C.c_uint32), ("alphabet_len", C.c_uint32),
+                ("byte_classes", C.c_uint8 * 256),
+                ("max_special_id", C.c_uint32), ("max_match_id", C.c_uint32),
+                ("start_unanchored_id", C.c_uint32), ("start_anchored_id", C.c_uint32),
+                ("match_offsets", C.POINTER(C.c_uint32)), ("match_pids", C.POINTER(C.c_uint32)),
+                ("pattern_lens", C.POINTER(C.c_uint32)), ("n_patterns", C.c_uint32),
+                ("match_kind", C.c_uint32), ("start_kind", C.c_uint32), ("prefilter_kind", C.c_uint32),
+                ("min_pattern_len", C.c_uint64), ("max_pattern_len", C.c_uint64)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("engine", C.c_int32), ("launches", C.c_int32), ("candidates", C.c_uint64),
+                ("raw_matches", C.c_uint64), ("scan_ms", C.c_float), ("order_ms", C.c_float),
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+
+
+MATCH_DTYPE = np.dtype([("pid", "<u4"), ("_pad", "<u4"), ("start", "<u8"), ("end", "<u8")])
+
+_vp, _u64, _i = C.c_void_p, C.c_uint64, C.c_int
+_lib.acg_strerror.restype = C.c_char_p
+_lib.acg_strerror.argtypes = [_i]
+_lib.acg_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_BuildOpts), C.POINTER(_vp)]
+_lib.acg_build_host.argtypes = _lib.acg_build.argtypes
+_lib.acg_dfa_create.argtypes = [C.POINTER(_Desc), C.POINTER(_vp)]
+_lib.acg_dfa_free.argtypes = [_vp]
+_lib.acg_dfa_free.restype = None
+_lib.acg_dfa_table.argtypes = [_vp, C.POINTER(_Desc)]
+for _f in ("acg_dfa_state_len", "acg_patterns_len", "acg_min_pattern_len", "acg_max_pattern_len",
+           "acg_memory_usage"):
+    getattr(_lib, _f).argtypes = [_vp]
+    getattr(_lib, _f).restype = _u64
+for _f in ("acg_kind", "acg_match_kind", "acg_start_kind", "acg_prefilter_kind", "acg_last_engine"):
+    getattr(_lib, _f).argtypes = [_vp]
+_lib.acg_packed_variant.argtypes = [_vp, C.POINTER(_i), C.POINTER(_i)]
+_lib.acg_set_engine.argtypes = [_vp, _i]
+_lib.acg_last_stats.argtypes = [_vp, C.POINTER(_Stats)]
+_lib.acg_find_overlapping.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _vp, _u64, C.POINTER(_u64)]
+_lib.acg_find_iter.argtypes = _lib.acg_find_overlapping.argtypes
+_lib.acg_find.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _i, _vp, C.POINTER(_i)]
+_lib.acg_find_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_u64),
+                                          C.POINTER(C.c_float)]
+_lib.acg_find_iter_dev.argtypes = _lib.acg_find_overlapping_dev.argtypes
+_lib.acg_count_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64),
+                                           C.POINTER(C.c_float)]
+_lib.acg_device_count.argtypes = []
+
+
+def device_count() -> int:
+    return _lib.acg_device_count()
+
+
+class Match:
+    """`Match`, src/util/search.rs:825-830."""
+    __slots__ = ("_pid", "_start", "_end")
+
+    def __init__(self, pid, start, end):
+        self._pid, self._start, self._end = int(pid), int(start), int(end)
+
+    def pattern(self):
+        return self._pid
+
+    def start(self):
+        return self._start
+
+    def end(self):
+        return self._end
+
+    def span(self):
+        return (self._start, self._end)
+
+    def is_empty(self):
+        return self._start == self._end
+
+    def as_tuple(self):
+        return (self._pid, self._start, self._end)
+
+    def __eq__(self, o):
+        return isinstance(o, Match) and self.as_tuple() == o.as_tuple()
+
+    def __repr__(self):
+        return f"Match(pattern={self._pid}, span={self._start}..{self._end})"
+
+
+def _hay_ptr(hay):
+    """(keepalive, address, length) of a bytes-like / contiguous uint8 ndarray haystack."""
+    if isinstance(hay, np.ndarray):
+        if hay.dtype != np.uint8 or not hay.flags["C_CONTIGUOUS"]:
+            raise TypeError("haystack ndarray must be contiguous uint8")
+        return hay, hay.ctypes.data, hay.size
+    if isinstance(hay, str):
+        hay = hay.encode()
+    arr = np.frombuffer(bytes(hay) if not isinstance(hay, (bytes, bytearray, memoryview)) else hay, dtype=np.uint8)
+    return arr, arr.ctypes.data if arr.size else 0, arr.size
+
+
+def _span(span, n):
+    if span is None:
+        return 0, n
+    return int(span[0]), int(span[1])
+
+
+class AhoCorasickBuilder:
+    """`AhoCorasickBuilder`, src/ahocorasick.rs:2135-2617 (same knobs, same defaults)."""
+
+    def __init__(self):
+        self._o = dict(match_kind=MatchKind.Standard, start_kind=StartKind.Unanchored,
+                       ascii_case_insensitive=False, byte_classes=True, prefilter=True, kind=None,
+                       dense_depth=3)
+        self._host_only = False
+
+    def match_kind(self, kind):
+        self._o["match_kind"] = MatchKind(kind)
+        return self
+
+    def start_kind(self, kind):
+        self._o["start_kind"] = StartKind(kind)
+        return self
+
+    def ascii_case_insensitive(self, yes):
+        self._o["ascii_case_insensitive"] = bool(yes)
+        return self
+
+    def kind(self, kind):
+        self._o["kind"] = None if kind is None else AhoCorasickKind(kind)
+        return self
+
+    def prefilter(self, yes):
+        self._o["prefilter"] = bool(yes)
+        return self
+
+    def dense_depth(self, depth):
+        self._o["dense_depth"] = int(depth)
+        return self
+
+    def byte_classes(self, yes):
+        self._o["byte_classes"] = bool(yes)
+        return self
+
+    def host_only(self, yes=True):
+        """Build the tables without touching CUDA (table-parity checks on CPU-only machines)."""
+        self._host_only = bool(yes)
+        return self
+
+    def build(self, patterns):
+        pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
+        n = len(pats)
+        arr = (C.c_char_p * max(n, 1))()
+        keep = []
+        for i, p in enumerate(pats):
+            b = C.create_string_buffer(p, max(len(p), 1))
+            keep.append(b)
+            arr[i] = C.cast(b, C.c_char_p)
+        lens = (_u64 * max(n, 1))(*[len(p) for p in pats])
+        o = self._o
+        opts = _BuildOpts(int(o["match_kind"]), int(o["start_kind"]), int(o["ascii_case_insensitive"]),
+                          int(o["byte_classes"]), int(o["prefilter"]), int(o["kind"] or 0), o["dense_depth"])
+        h = _vp()
+        fn = _lib.acg_build_host if self._host_only else _lib.acg_build
+        rc = fn(arr, lens, n, C.byref(opts), C.byref(h))
+        if rc in (-1, -2, -3):
+            raise BuildError(rc)
+        if rc:
+            raise DeviceError(rc)
+        return AhoCorasick(h)
+
+
+class AhoCorasick:
+    """`AhoCorasick`, src/ahocorasick.rs:177-2082 (search surface only; replace/stream are out of scope)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.acg_dfa_free(h)
+            self._h = None
+
+    @staticmethod
+    def new(patterns):  # src/ahocorasick.rs:243
+        return AhoCorasickBuilder().build(patterns)
+
+    @staticmethod
+    def builder():  # src/ahocorasick.rs:268
+        return AhoCorasickBuilder()
+
+    @staticmethod
+    def from_dfa_tables(t: dict):
+        """Adopt a DFA built elsewhere (what a Rust -sys shim does): acg_dfa_create."""
+        d = _Desc()
+        keep = {}
+
+        def arr(name, dtype=np.uint32):
+            a = np.ascontiguousarray(t[name], dtype=dtype)
+            keep[name] = a
+            return a.ctypes.data_as(C.POINTER(C.c_uint32))
+        d.trans = arr("trans")
+        d.trans_len = keep["trans"].size
+        d.stride2, d.alphabet_len = int(t["stride2"]), int(t["alphabet_len"])
+        bc = np.ascontiguousarray(t["byte_classes"], dtype=np.uint8)
+        C.memmove(d.byte_classes, bc.ctypes.data, 256)
+        for k in ("max_special_id", "max_match_id", "start_unanchored_id", "start_anchored_id"):
+            setattr(d, k, int(t[k]))
+        d.match_offsets = arr("match_offsets")
+        d.match_pids = arr("match_pids")
+        d.pattern_lens = arr("pattern_lens")
+        d.n_patterns = keep["pattern_lens"].size
+        d.match_kind = int(t["match_kind"])
+        d.start_kind = int(t.get("start_kind", 0))
+        d.prefilter_kind = int(t.get("prefilter_kind", 0))
+        d.min_pattern_len, d.max_pattern_len = int(t["min_pattern_len"]), int(t["max_pattern_len"])
+        h = _vp()
+        rc = _lib.acg_dfa_create(C.byref(d), C.byref(h))
+        if rc:
+            raise DeviceError(rc)
+        return AhoCorasick(h)
+
+    # ---- getters (src/ahocorasick.rs:1867-2021) ----
+    def kind(self):
+        return AhoCorasickKind(_lib.acg_kind(self._h))
+
+    def start_kind(self):
+        return StartKind(_lib.acg_start_kind(self._h))
+
+    def match_kind(self):
+        return MatchKind(_lib.acg_match_kind(self._h))
+
+    def min_pattern_len(self):
+        return _lib.acg_min_pattern_len(self._h)
+
+    def max_pattern_len(self):
+        return _lib.acg_max_pattern_len(self._h)
+
+    def patterns_len(self):
+        return _lib.acg_patterns_len(self._h)
+
+    def memory_usage(self):
+        return _lib.acg_memory_usage(self._h)
+
+    def prefilter_kind(self):
+        return _lib.acg_prefilter_kind(self._h)
+
+    def packed_variant(self):
+        fat, ml = _i(), _i()
+        if not _lib.acg_packed_variant(self._h, C.byref(fat), C.byref(ml)):
+            return None
+        return {"fat": bool(fat.value), "mask_len": ml.value}
+
+    def state_len(self):
+        return _lib.acg_dfa_state_len(self._h)
+
+    def tables(self) -> dict:
+        d = _Desc()
+        _lib.acg_dfa_table(self._h, C.byref(d))
+        nms = (d.max_match_id >> d.stride2) - 1
+
+        def arr(ptr, n):
+            return np.ctypeslib.as_array(ptr, (n,)).copy() if n and ptr else np.zeros(0, np.uint32)
+        offs = arr(d.match_offsets, nms + 1)
+        tot = int(offs[-1])
+        return {
+            "trans": arr(d.trans, d.trans_len),
+            "stride2": d.stride2, "alphabet_len": d.alphabet_len,
+            "byte_classes": np.frombuffer(bytes(d.byte_classes), dtype=np.uint8).copy(),
+            "max_special_id": d.max_special_id, "max_match_id": d.max_match_id,
+            "start_unanchored_id": d.start_unanchored_id, "start_anchored_id": d.start_anchored_id,
+            "match_offsets": offs,
+            "match_pids": arr(d.match_pids, tot),
+            "pattern_lens": arr(d.pattern_lens, d.n_patterns),
+            "match_kind": d.match_kind, "start_kind": d.start_kind, "prefilter_kind": d.prefilter_kind,
+            "min_pattern_len": d.min_pattern_len, "max_pattern_len": d.max_pattern_len,
+            "state_len": _lib.acg_dfa_state_len(self._h),
+        }
+
+    # ---- engine control / stats (device-side knobs that do not exist in the reference) ----
+    def set_engine(self, engine):
+        rc = _lib.acg_set_engine(self._h, int(engine))
+        if rc:
+            raise DeviceError(rc)
+        return self
+
+    def last_stats(self) -> dict:
+        s = _Stats()
+        _lib.acg_last_stats(self._h, C.byref(s))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    # ---- searches ----
+    @staticmethod
+    def _raise(rc):
+        if -14 <= rc <= -10:
+            raise MatchError(rc)
+        if rc == -20:
+            raise ValueError("invalid span for haystack")  # the reference panics (search.rs:332-343)
+        raise DeviceError(rc)
+
+    def _collect(self, fn, hay, span, anchored):
+        keep, ptr, n = _hay_ptr(hay)
+        s, e = _span(span, n)
+        cap = 4096
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            cnt = _u64()
+            rc = fn(self._h, ptr, n, s, e, int(anchored), out.ctypes.data, cap, C.byref(cnt))
+            if rc == E_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            if rc:
+                self._raise(rc)
+            return out[: cnt.value]
+
+    def try_find_iter_np(self, hay, span=None, anchored=Anchored.No):
+        return self._collect(_lib.acg_find_iter, hay, span, anchored)
+
+    def try_find_overlapping_iter_np(self, hay, span=None, anchored=Anchored.No):
+        return self._collect(_lib.acg_find_overlapping, hay, span, anchored)
+
+    def try_find_iter(self, hay, span=None, anchored=Anchored.No):  # src/ahocorasick.rs:1275
+        r = self.try_find_iter_np(hay, span, anchored)
+        return [Match(a, b, c) for a, b, c in zip(r["pid"], r["start"], r["end"])]
+
+    def try_find_overlapping_iter(self, hay, span=None, anchored=Anchored.No):  # :1350
+        r = self.try_find_overlapping_iter_np(hay, span, anchored)
+        return [Match(a, b, c) for a, b, c in zip(r["pid"], r["start"], r["end"])]
+
+    find_iter = try_find_iter  # :562 (the infallible versions panic where these raise)
+    find_overlapping_iter = try_find_overlapping_iter  # :609
+
+    def try_find(self, hay, span=None, anchored=Anchored.No, earliest=False):  # :1021
+        keep, ptr, n = _hay_ptr(hay)
+        s, e = _span(span, n)
+        out = np.zeros(1, MATCH_DTYPE)
+        found = _i()
+        rc = _lib.acg_find(self._h, ptr, n, s, e, int(anchored), int(earliest), out.ctypes.data, C.byref(found))
+        if rc:
+            self._raise(rc)
+        if not found.value:
+            return None
+        return Match(out["pid"][0], out["start"][0], out["end"][0])
+
+    find = try_find  # :404
+
+    def is_match(self, hay, span=None):  # :311
+        return self.try_find(hay, span, earliest=True) is not None
+
+    # ---- device-resident haystack (torch tensor / raw pointer), for the roofline measurement ----
+    def find_overlapping_iter_dev_np(self, dev_ptr, hay_len, span=None):
+        s, e = _span(span, hay_len)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            cnt, ms = _u64(), C.c_float()
+            rc = _lib.acg_find_overlapping_dev(self._h, dev_ptr, hay_len, s, e, out.ctypes.data, cap,
+                                               C.byref(cnt), C.byref(ms))
+            if rc == E_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            if rc:
+                self._raise(rc)
+            return out[: cnt.value], ms.value
+
+    def find_iter_dev_np(self, dev_ptr, hay_len, span=None):
+        s, e = _span(span, hay_len)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            cnt, ms = _u64(), C.c_float()
+            rc = _lib.acg_find_iter_dev(self._h, dev_ptr, hay_len, s, e, out.ctypes.data, cap,
+                                        C.byref(cnt), C.byref(ms))
+            if rc == E_OVERFLOW:
+                cap = int(cnt.value)
+                continue
+            if rc:
+                self._raise(rc)
+            return out[: cnt.value], ms.value
+
+    def count_overlapping_dev(self, dev_ptr, hay_len, span=None):
+        s, e = _span(span, hay_len)
+        cnt, fnv, ms = _u64(), _u64(), C.c_float()
+        rc = _lib.acg_count_overlapping_dev(self._h, dev_ptr, hay_len, s, e, C.byref(cnt), C.byref(fnv),
+                                            C.byref(ms))
+        if rc:
+            self._raise(rc)
+        return cnt.value, fnv.value, ms.value

@@ -1,0 +1,744 @@
+// acb_api.cu -- the extern "C" boundary (include/acb200.h): handle management,
+// input validation with the reference's error behaviour, device orchestration.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/acb200.h"
+#include "acb_build.hpp"
+#include "acb_device.cuh"
+
+using acb::DfaDev;
+using acb::HostDfa;
+
+namespace {
+
+#define CK(expr)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (expr);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      std::fprintf(stderr, "acb200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), \
+                   __FILE__, __LINE__, cudaGetErrorString(e_));                        \
+      return ACG_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+struct Workspace {
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  uint64_t cap = 0;  // tuple capacity
+  uint64_t* d_keys[2] = {nullptr, nullptr};
+  uint32_t* d_pids[2] = {nullptr, nullptr};
+  unsigned long long* d_counter = nullptr;
+  unsigned long long* h_counter = nullptr;  // pinned
+  void* d_temp = nullptr;
+  size_t temp_bytes = 0;
+  uint64_t* h_keys = nullptr;  // pinned staging
+  uint32_t* h_pids = nullptr;
+  uint64_t h_cap = 0;
+  uint8_t* d_hay = nullptr;  // staging of host haystacks
+  uint64_t d_hay_cap = 0;
+  uint64_t* d_seq = nullptr;  // sequential engine output [cap*3]
+  uint64_t seq_cap = 0;
+  uint64_t* h_seq = nullptr;
+  uint64_t h_seq_cap = 0;
+};
+
+}  // namespace
+
+struct acg_dfa {
+  HostDfa h;
+  std::vector<uint8_t> depth8;
+  bool has_empty = false;
+  uint32_t max_list_len = 0;
+  bool on_device = false;
+  int device = -1;
+  uint32_t* d_trans = nullptr;
+  uint8_t* d_classes = nullptr;
+  uint32_t* d_moff = nullptr;
+  uint32_t* d_mpids = nullptr;
+  uint32_t* d_plens = nullptr;
+  uint8_t* d_depth8 = nullptr;
+  DfaDev dev{};
+  int engine_override = ACG_ENGINE_AUTO;
+  mutable std::mutex mu;
+  mutable Workspace ws;
+  mutable acg_stats stats{};
+};
+
+namespace {
+
+void derive_metadata(acg_dfa* a) {
+  HostDfa& h = a->h;
+  a->has_empty = h.min_pattern_len == 0 && !h.pattern_lens.empty();
+  a->max_list_len = 0;
+  for (size_t i = 0; i + 1 < h.match_offsets.size(); ++i)
+    a->max_list_len = std::max(a->max_list_len, h.match_offsets[i + 1] - h.match_offsets[i]);
+  // trie depth of every row = BFS distance from the start row (each transition
+  // deepens the longest-suffix state by at most one byte).
+  const uint32_t s2 = h.stride2;
+  const size_t rows = size_t(h.state_len);
+  a->depth8.assign(rows, 255);
+  std::vector<uint32_t> q;
+  auto seed = [&](uint32_t sid) {
+    if (sid == 0) return;
+    a->depth8[sid >> s2] = 0;
+    q.push_back(sid >> s2);
+  };
+  seed(h.start_unanchored_id);
+  std::vector<uint32_t> dist(rows, UINT32_MAX);
+  if (h.start_unanchored_id) dist[h.start_unanchored_id >> s2] = 0;
+  for (size_t qi = 0; qi < q.size(); ++qi) {
+    const uint32_t r = q[qi];
+    const uint32_t* row = h.trans.data() + (size_t(r) << s2);
+    for (uint32_t c = 0; c < h.alphabet_len; ++c) {
+      const uint32_t nr = row[c] >> s2;
+      if (nr == 0 || dist[nr] != UINT32_MAX) continue;
+      dist[nr] = dist[r] + 1;
+      a->depth8[nr] = uint8_t(std::min<uint32_t>(dist[nr], 255));
+      q.push_back(nr);
+    }
+  }
+}
+
+int upload(acg_dfa* a) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return ACG_E_NO_DEVICE;
+  }
+  CK(cudaGetDevice(&a->device));
+  HostDfa& h = a->h;
+  auto up = [&](auto** dptr, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+    return e;
+  };
+  CK(up(&a->d_trans, h.trans.data(), h.trans.size() * 4));
+  CK(up(&a->d_classes, h.classes, 256));
+  CK(up(&a->d_moff, h.match_offsets.data(), h.match_offsets.size() * 4));
+  CK(up(&a->d_mpids, h.match_pids.data(), h.match_pids.size() * 4));
+  CK(up(&a->d_plens, h.pattern_lens.data(), h.pattern_lens.size() * 4));
+  CK(up(&a->d_depth8, a->depth8.data(), a->depth8.size()));
+  DfaDev& d = a->dev;
+  d.trans = a->d_trans;
+  d.classes = a->d_classes;
+  d.match_offsets = a->d_moff;
+  d.match_pids = a->d_mpids;
+  d.pattern_lens = a->d_plens;
+  d.depth8 = a->d_depth8;
+  d.stride2 = h.stride2;
+  d.max_match_id = h.max_match_id;
+  d.start_unanchored_id = h.start_unanchored_id;
+  d.start_anchored_id = h.start_anchored_id;
+  d.max_pattern_len = uint32_t(std::min<uint64_t>(h.max_pattern_len, UINT32_MAX));
+  d.min_pattern_len = uint32_t(std::min<uint64_t>(h.min_pattern_len, UINT32_MAX));
+  Workspace& w = a->ws;
+  CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&w.ev0));
+  CK(cudaEventCreate(&w.ev1));
+  CK(cudaEventCreate(&w.ev2));
+  CK(cudaEventCreate(&w.ev3));
+  CK(cudaMalloc(&w.d_counter, 64));
+  CK(cudaMallocHost(&w.h_counter, 64));
+  a->on_device = true;
+  return ACG_OK;
+}
+
+int ensure_tuple_cap(Workspace& w, uint64_t cap) {
+  if (cap <= w.cap) return ACG_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (w.d_keys[i]) cudaFree(w.d_keys[i]);
+    if (w.d_pids[i]) cudaFree(w.d_pids[i]);
+    w.d_keys[i] = nullptr;
+    w.d_pids[i] = nullptr;
+  }
+  if (w.d_temp) { cudaFree(w.d_temp); w.d_temp = nullptr; }
+  w.cap = 0;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&w.d_keys[i], cap * 8));
+    CK(cudaMalloc(&w.d_pids[i], cap * 4));
+  }
+  size_t tb = 0;
+  CK(acb::sort_pairs(nullptr, tb, w.d_keys[0], w.d_keys[1], w.d_pids[0], w.d_pids[1], cap, 64, w.stream));
+  CK(cudaMalloc(&w.d_temp, std::max<size_t>(tb, 16)));
+  w.temp_bytes = tb;
+  w.cap = cap;
+  return ACG_OK;
+}
+
+int ensure_host_staging(Workspace& w, uint64_t n) {
+  if (n <= w.h_cap) return ACG_OK;
+  if (w.h_keys) cudaFreeHost(w.h_keys);
+  if (w.h_pids) cudaFreeHost(w.h_pids);
+  w.h_keys = nullptr;
+  w.h_pids = nullptr;
+  w.h_cap = 0;
+  const uint64_t cap = std::max<uint64_t>(n, 1 << 16);
+  CK(cudaMallocHost(&w.h_keys, cap * 8));
+  CK(cudaMallocHost(&w.h_pids, cap * 4));
+  w.h_cap = cap;
+  return ACG_OK;
+}
+
+int ensure_hay(Workspace& w, uint64_t bytes) {
+  if (bytes <= w.d_hay_cap) return ACG_OK;
+  if (w.d_hay) cudaFree(w.d_hay);
+  w.d_hay = nullptr;
+  w.d_hay_cap = 0;
+  const uint64_t cap = ((bytes + (1ull << 20)) >> 20) << 20;
+  CK(cudaMalloc(&w.d_hay, cap));
+  w.d_hay_cap = cap;
+  return ACG_OK;
+}
+
+int ensure_seq(Workspace& w, uint64_t cap) {
+  if (cap > w.seq_cap) {
+    if (w.d_seq) cudaFree(w.d_seq);
+    w.d_seq = nullptr;
+    w.seq_cap = 0;
+    CK(cudaMalloc(&w.d_seq, cap * 24));
+    w.seq_cap = cap;
+  }
+  if (cap > w.h_seq_cap) {
+    if (w.h_seq) cudaFreeHost(w.h_seq);
+    w.h_seq = nullptr;
+    w.h_seq_cap = 0;
+    CK(cudaMallocHost(&w.h_seq, cap * 24));
+    w.h_seq_cap = cap;
+  }
+  return ACG_OK;
+}
+
+// enforce_anchored_consistency, src/ahocorasick.rs:2778-2789
+int check_anchored(int have, int want_anchored) {
+  if (have == ACG_START_BOTH) return ACG_OK;
+  if (have == ACG_START_UNANCHORED) return want_anchored ? ACG_E_INVALID_INPUT_ANCHORED : ACG_OK;
+  return want_anchored ? ACG_OK : ACG_E_INVALID_INPUT_UNANCHORED;
+}
+// Input::set_span, src/util/search.rs:332-343 (the reference panics; we return a code)
+bool span_ok(uint64_t hay_len, uint64_t s, uint64_t e) { return e <= hay_len && s <= e + 1; }
+// DFA::start_state, src/dfa.rs:192-215
+int check_start(const HostDfa& h, int anchored) {
+  if (anchored) return h.start_anchored_id == 0 ? ACG_E_INVALID_INPUT_ANCHORED : ACG_OK;
+  return h.start_unanchored_id == 0 ? ACG_E_INVALID_INPUT_UNANCHORED : ACG_OK;
+}
+
+int bits_for(uint64_t v) {
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
+}
+
+struct TupleResult {
+  uint64_t n = 0;
+  int sorted_buf = 0;
+};
+
+// K1 + K4 on a device-resident haystack; leaves `n` ordered tuples in
+// ws.d_keys[sorted_buf] / ws.d_pids[sorted_buf].
+int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start,
+                         uint64_t span_end, TupleResult* res) {
+  Workspace& w = a->ws;
+  const uint64_t n_bytes = span_end - span_start;
+  if (a->max_list_len >= (1u << acb::kTieBits)) return ACG_E_INVALID_ARG;
+  if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
+  const uint64_t target_lanes = uint64_t(dev_sms) * 2048;
+  uint64_t seg_len = (n_bytes + target_lanes - 1) / std::max<uint64_t>(target_lanes, 1);
+  seg_len = std::max<uint64_t>(seg_len, 256);
+  seg_len = (seg_len + 15) & ~15ull;
+  // shard starts are placed so that (d_hay + span_start + k*seg_len) keeps the 16-byte
+  // phase of the first shard; the kernel handles the unaligned head per lane.
+  const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
+  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 64));
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    int rc = ensure_tuple_cap(w, cap);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(w.d_counter, 0, 8, w.stream));
+    acb::WalkLaunch p;
+    p.hay = d_hay;
+    p.span_start = span_start;
+    p.span_end = span_end;
+    p.seg_len = seg_len;
+    p.n_segs = n_segs;
+    p.keys = w.d_keys[0];
+    p.pids = w.d_pids[0];
+    p.counter = w.d_counter;
+    p.cap = w.cap;
+    CK(cudaEventRecord(w.ev0, w.stream));
+    CK(acb::launch_walk_overlapping(a->dev, p, w.stream));
+    CK(cudaEventRecord(w.ev1, w.stream));
+    CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    a->stats.launches += 1;
+    const uint64_t want = *w.h_counter;
+    if (want > w.cap) { cap = want + want / 8 + 1024; continue; }  // overflow: grow and rescan
+    res->n = want;
+    a->stats.raw_matches = want;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, w.ev0, w.ev1);
+    a->stats.scan_ms = ms;
+    if (want > 1) {
+      size_t tb = w.temp_bytes;
+      const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
+      CK(cudaEventRecord(w.ev2, w.stream));
+      CK(acb::sort_pairs(w.d_temp, tb, w.d_keys[0], w.d_keys[1], w.d_pids[0], w.d_pids[1], want, end_bit,
+                         w.stream));
+      CK(cudaEventRecord(w.ev3, w.stream));
+      CK(cudaStreamSynchronize(w.stream));
+      cudaEventElapsedTime(&ms, w.ev2, w.ev3);
+      a->stats.order_ms = ms;
+      a->stats.launches += 8;  // radix passes (upper bound, library code)
+      res->sorted_buf = 1;
+    } else {
+      res->sorted_buf = 0;
+    }
+    return ACG_OK;
+  }
+  return ACG_E_NOMEM;
+}
+
+// D2H + expansion of ordered (key,pid) tuples into acg_match / count / fnv.
+int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, acg_match* out,
+                 uint64_t cap, uint64_t* n_out, uint64_t* fnv) {
+  Workspace& w = a->ws;
+  *n_out = r.n;
+  if (fnv) *fnv = 0xcbf29ce484222325ull;
+  if (r.n == 0) return ACG_OK;
+  if (!fnv && r.n > cap) return ACG_E_OVERFLOW;
+  int rc = ensure_host_staging(w, r.n);
+  if (rc) return rc;
+  CK(cudaEventRecord(w.ev0, w.stream));
+  CK(cudaMemcpyAsync(w.h_keys, w.d_keys[r.sorted_buf], r.n * 8, cudaMemcpyDeviceToHost, w.stream));
+  CK(cudaMemcpyAsync(w.h_pids, w.d_pids[r.sorted_buf], r.n * 4, cudaMemcpyDeviceToHost, w.stream));
+  CK(cudaEventRecord(w.ev1, w.stream));
+  CK(cudaStreamSynchronize(w.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, w.ev0, w.ev1);
+  a->stats.d2h_ms += ms;
+  const uint32_t* plens = a->h.pattern_lens.data();
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  auto mix = [&](uint64_t v) {
+    for (int k = 0; k < 8; ++k) { hsh ^= (v >> (8 * k)) & 0xFF; hsh *= 0x100000001b3ull; }
+  };
+  for (uint64_t i = 0; i < r.n; ++i) {
+    const uint32_t pid = w.h_pids[i];
+    const uint64_t end = span_start + (w.h_keys[i] >> acb::kTieBits);
+    const uint64_t start = end - plens[pid];
+    if (out && i < cap) {
+      out[i].pid = pid;
+      out[i]._pad = 0;
+      out[i].start = start;
+      out[i].end = end;
+    }
+    if (fnv) { mix(pid); mix(start); mix(end); }
+  }
+  if (fnv) *fnv = hsh;
+  if (out == nullptr && !fnv) return ACG_E_INVALID_ARG;
+  return (out && r.n > cap) ? ACG_E_OVERFLOW : ACG_OK;
+}
+
+int run_seq(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start, uint64_t span_end,
+            int anchored, int earliest, int single, acg_match* out, uint64_t cap, uint64_t* n_out) {
+  Workspace& w = a->ws;
+  uint64_t scap = std::max<uint64_t>(std::max<uint64_t>(cap, 1024), w.seq_cap);
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    int rc = ensure_seq(w, scap);
+    if (rc) return rc;
+    acb::SeqLaunch p;
+    p.hay = d_hay;
+    p.span_start = span_start;
+    p.span_end = span_end;
+    p.anchored = anchored;
+    p.match_kind = a->h.match_kind;
+    p.earliest = earliest;
+    p.single = single;
+    p.out = w.d_seq;
+    p.counter = w.d_counter;
+    p.cap = w.seq_cap;
+    CK(cudaEventRecord(w.ev0, w.stream));
+    CK(acb::launch_seq_find(a->dev, p, w.stream));
+    CK(cudaEventRecord(w.ev1, w.stream));
+    CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    a->stats.launches += 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, w.ev0, w.ev1);
+    a->stats.scan_ms = ms;
+    const uint64_t n = *w.h_counter;
+    *n_out = n;
+    a->stats.raw_matches = n;
+    if (n > cap) return ACG_E_OVERFLOW;  // caller retries with a bigger buffer (two-call protocol)
+    if (n > w.seq_cap) { scap = n; continue; }
+    if (n) {
+      CK(cudaMemcpyAsync(w.h_seq, w.d_seq, n * 24, cudaMemcpyDeviceToHost, w.stream));
+      CK(cudaStreamSynchronize(w.stream));
+      for (uint64_t i = 0; i < n; ++i) {
+        out[i].pid = uint32_t(w.h_seq[i * 3]);
+        out[i]._pad = 0;
+        out[i].start = w.h_seq[i * 3 + 1];
+        out[i].end = w.h_seq[i * 3 + 2];
+      }
+    }
+    return ACG_OK;
+  }
+  return ACG_E_NOMEM;
+}
+
+// Stage [span_start, span_end) of a host haystack on the device; returns a
+// pointer that can be indexed with ABSOLUTE haystack offsets in that range.
+int stage_host_span(const acg_dfa* a, const uint8_t* hay, uint64_t span_start, uint64_t span_end,
+                    const uint8_t** d_base) {
+  Workspace& w = a->ws;
+  // keep the 16-byte phase of the host offsets so vector loads stay aligned
+  const uint64_t lead = span_start & 15;
+  const uint64_t bytes = span_end - span_start;
+  int rc = ensure_hay(w, bytes + lead + 64);
+  if (rc) return rc;
+  CK(cudaEventRecord(w.ev0, w.stream));
+  if (bytes)
+    CK(cudaMemcpyAsync(w.d_hay + lead, hay + span_start, bytes, cudaMemcpyHostToDevice, w.stream));
+  CK(cudaEventRecord(w.ev1, w.stream));
+  CK(cudaStreamSynchronize(w.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, w.ev0, w.ev1);
+  a->stats.h2d_ms = ms;
+  *d_base = w.d_hay + lead - span_start;  // never dereferenced outside [span_start, span_end)
+  return ACG_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int validate_common(const acg_dfa* a, uint64_t hay_len, uint64_t s, uint64_t e, int anchored) {
+  if (!a) return ACG_E_INVALID_ARG;
+  if (!span_ok(hay_len, s, e)) return ACG_E_INVALID_SPAN;
+  int rc = check_anchored(a->h.start_kind, anchored);
+  if (rc) return rc;
+  return ACG_OK;
+}
+
+int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
+                     uint64_t span_start, uint64_t span_end, int anchored, acg_match* out,
+                     uint64_t cap, uint64_t* n_out, uint64_t* fnv, float* kernel_ms) {
+  if (!n_out) return ACG_E_INVALID_ARG;
+  *n_out = 0;
+  int rc = validate_common(a, hay_len, span_start, span_end, anchored);
+  if (rc) return rc;
+  // Automaton::try_find_overlapping_iter, src/automaton.rs:397-423
+  if (a->h.match_kind != ACG_STANDARD) return ACG_E_UNSUPPORTED_OVERLAPPING;
+  if (anchored) return ACG_E_INVALID_INPUT_ANCHORED;
+  if ((rc = check_start(a->h, 0))) return rc;
+  if (!a->on_device) return ACG_E_NO_DEVICE;
+  if (fnv) *fnv = 0xcbf29ce484222325ull;
+  if (span_start > span_end) return ACG_OK;  // Input::is_done
+  std::lock_guard<std::mutex> lock(a->mu);
+  DeviceGuard guard(a->device);
+  a->stats = acg_stats{};
+  a->stats.engine = ACG_ENGINE_WALK;
+  const uint8_t* d_base = hay;
+  if (!hay_on_device) {
+    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+  }
+  TupleResult r;
+  if ((rc = run_walk_overlapping(a, d_base, span_start, span_end, &r))) return rc;
+  if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
+  return drain_tuples(a, r, span_start, out, cap, n_out, fnv);
+}
+
+int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
+                   uint64_t span_start, uint64_t span_end, int anchored, acg_match* out,
+                   uint64_t cap, uint64_t* n_out, float* kernel_ms) {
+  if (!n_out) return ACG_E_INVALID_ARG;
+  *n_out = 0;
+  int rc = validate_common(a, hay_len, span_start, span_end, anchored);
+  if (rc) return rc;
+  if ((rc = check_start(a->h, anchored))) return rc;  // FindIter::new, src/automaton.rs:861-870
+  if (!a->on_device) return ACG_E_NO_DEVICE;
+  if (span_start > span_end) return ACG_OK;
+  std::lock_guard<std::mutex> lock(a->mu);
+  DeviceGuard guard(a->device);
+  a->stats = acg_stats{};
+  a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+  const uint8_t* d_base = hay;
+  if (!hay_on_device) {
+    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+  }
+  rc = run_seq(a, d_base, span_start, span_end, anchored, 0, 0, out, cap, n_out);
+  if (kernel_ms) *kernel_ms = a->stats.scan_ms;
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+void acg_build_opts_default(acg_build_opts* o) {
+  o->match_kind = ACG_STANDARD;
+  o->start_kind = ACG_START_UNANCHORED;
+  o->ascii_case_insensitive = 0;
+  o->byte_classes = 1;
+  o->prefilter = 1;
+  o->kind = ACG_KIND_AUTO;
+  o->dense_depth = 3;
+}
+
+static int build_common(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                        const acg_build_opts* opts, bool to_device, acg_dfa** out) {
+  if (!out) return ACG_E_INVALID_ARG;
+  *out = nullptr;
+  acg_build_opts def;
+  acg_build_opts_default(&def);
+  if (!opts) opts = &def;
+  if (n && (!patterns || !lens)) return ACG_E_INVALID_ARG;
+  acb::BuildOptions bo;
+  bo.match_kind = opts->match_kind;
+  bo.start_kind = opts->start_kind;
+  bo.ascii_case_insensitive = opts->ascii_case_insensitive != 0;
+  bo.byte_classes = opts->byte_classes != 0;
+  bo.prefilter = opts->prefilter != 0;
+  bo.kind = opts->kind;
+  std::vector<acb::PatternRef> pats(n);
+  for (uint64_t i = 0; i < n; ++i) pats[i] = acb::PatternRef{patterns[i], lens[i]};
+  acg_dfa* a = new (std::nothrow) acg_dfa();
+  if (!a) return ACG_E_NOMEM;
+  int rc = ACG_OK;
+  try {
+    rc = acb::build_dfa(pats, bo, &a->h);
+    if (rc == ACG_OK) derive_metadata(a);
+  } catch (const std::bad_alloc&) {
+    rc = ACG_E_NOMEM;
+  }
+  if (rc == ACG_OK && to_device) rc = upload(a);
+  if (rc != ACG_OK) { acg_dfa_free(a); return rc; }
+  *out = a;
+  return ACG_OK;
+}
+
+int acg_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+              const acg_build_opts* opts, acg_dfa** out) {
+  return build_common(patterns, lens, n, opts, true, out);
+}
+int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                   const acg_build_opts* opts, acg_dfa** out) {
+  return build_common(patterns, lens, n, opts, false, out);
+}
+
+int acg_dfa_create(const acg_dfa_desc* d, acg_dfa** out) {
+  if (!d || !out) return ACG_E_INVALID_ARG;
+  *out = nullptr;
+  if (d->stride2 > 8 || (d->trans_len & ((1ull << d->stride2) - 1))) return ACG_E_INVALID_ARG;
+  acg_dfa* a = new (std::nothrow) acg_dfa();
+  if (!a) return ACG_E_NOMEM;
+  HostDfa& h = a->h;
+  try {
+    h.trans.assign(d->trans, d->trans + d->trans_len);
+    h.stride2 = d->stride2;
+    h.alphabet_len = d->alphabet_len;
+    std::memcpy(h.classes, d->byte_classes, 256);
+    h.max_special_id = d->max_special_id;
+    h.max_match_id = d->max_match_id;
+    h.start_unanchored_id = d->start_unanchored_id;
+    h.start_anchored_id = d->start_anchored_id;
+    const size_t nms = size_t(d->max_match_id >> d->stride2) - 1;
+    h.match_offsets.assign(d->match_offsets, d->match_offsets + nms + 1);
+    h.match_pids.assign(d->match_pids, d->match_pids + h.match_offsets[nms]);
+    h.pattern_lens.assign(d->pattern_lens, d->pattern_lens + d->n_patterns);
+    h.match_kind = int(d->match_kind);
+    h.start_kind = int(d->start_kind);
+    h.prefilter_kind = int(d->prefilter_kind);
+    h.reported_kind = ACG_KIND_DFA;
+    h.min_pattern_len = d->min_pattern_len;
+    h.max_pattern_len = d->max_pattern_len;
+    h.state_len = d->trans_len >> d->stride2;
+    derive_metadata(a);
+  } catch (const std::bad_alloc&) {
+    delete a;
+    return ACG_E_NOMEM;
+  }
+  int rc = upload(a);
+  if (rc != ACG_OK && rc != ACG_E_NO_DEVICE) { acg_dfa_free(a); return rc; }
+  *out = a;  // without a device the handle is host-only (searches report ACG_E_NO_DEVICE)
+  return ACG_OK;
+}
+
+void acg_dfa_free(acg_dfa* a) {
+  if (!a) return;
+  if (a->on_device) {
+    DeviceGuard guard(a->device);
+    Workspace& w = a->ws;
+    if (w.stream) cudaStreamSynchronize(w.stream);
+    cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
+    cudaFree(a->d_plens); cudaFree(a->d_depth8);
+    for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
+    cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
+    if (w.h_counter) cudaFreeHost(w.h_counter);
+    if (w.h_keys) cudaFreeHost(w.h_keys);
+    if (w.h_pids) cudaFreeHost(w.h_pids);
+    if (w.h_seq) cudaFreeHost(w.h_seq);
+    if (w.ev0) cudaEventDestroy(w.ev0);
+    if (w.ev1) cudaEventDestroy(w.ev1);
+    if (w.ev2) cudaEventDestroy(w.ev2);
+    if (w.ev3) cudaEventDestroy(w.ev3);
+    if (w.stream) cudaStreamDestroy(w.stream);
+    if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+  }
+  delete a;
+}
+
+int acg_dfa_table(const acg_dfa* a, acg_dfa_desc* o) {
+  if (!a || !o) return ACG_E_INVALID_ARG;
+  const HostDfa& h = a->h;
+  o->trans = h.trans.data();
+  o->trans_len = h.trans.size();
+  o->stride2 = h.stride2;
+  o->alphabet_len = h.alphabet_len;
+  std::memcpy(o->byte_classes, h.classes, 256);
+  o->max_special_id = h.max_special_id;
+  o->max_match_id = h.max_match_id;
+  o->start_unanchored_id = h.start_unanchored_id;
+  o->start_anchored_id = h.start_anchored_id;
+  o->match_offsets = h.match_offsets.data();
+  o->match_pids = h.match_pids.data();
+  o->pattern_lens = h.pattern_lens.data();
+  o->n_patterns = uint32_t(h.pattern_lens.size());
+  o->match_kind = uint32_t(h.match_kind);
+  o->start_kind = uint32_t(h.start_kind);
+  o->prefilter_kind = uint32_t(h.prefilter_kind);
+  o->min_pattern_len = h.min_pattern_len;
+  o->max_pattern_len = h.max_pattern_len;
+  return ACG_OK;
+}
+
+uint64_t acg_dfa_state_len(const acg_dfa* a) { return a ? a->h.state_len : 0; }
+int acg_kind(const acg_dfa* a) { return a ? a->h.reported_kind : 0; }
+int acg_match_kind(const acg_dfa* a) { return a ? a->h.match_kind : 0; }
+int acg_start_kind(const acg_dfa* a) { return a ? a->h.start_kind : 0; }
+uint64_t acg_patterns_len(const acg_dfa* a) { return a ? a->h.pattern_lens.size() : 0; }
+uint64_t acg_min_pattern_len(const acg_dfa* a) { return a ? a->h.min_pattern_len : 0; }
+uint64_t acg_max_pattern_len(const acg_dfa* a) { return a ? a->h.max_pattern_len : 0; }
+uint64_t acg_memory_usage(const acg_dfa* a) {
+  if (!a) return 0;  // DFA::memory_usage, src/dfa.rs:289-297 (heap of the tables)
+  const HostDfa& h = a->h;
+  return h.trans.size() * 4 + (h.match_offsets.size() - 1) * 24 + h.match_pids.size() * 4 +
+         h.pattern_lens.size() * 4;
+}
+int acg_prefilter_kind(const acg_dfa* a) { return a ? a->h.prefilter_kind : 0; }
+int acg_packed_variant(const acg_dfa* a, int* fat, int* mask_len) {
+  if (!a || !a->h.packed.active) return 0;
+  if (fat) *fat = a->h.packed.fat;
+  if (mask_len) *mask_len = a->h.packed.mask_len;
+  return 1;
+}
+
+int acg_set_engine(acg_dfa* a, int engine) {
+  if (!a || engine < ACG_ENGINE_AUTO || engine > ACG_ENGINE_SEQUENTIAL) return ACG_E_INVALID_ARG;
+  a->engine_override = engine;
+  return ACG_OK;
+}
+int acg_last_engine(const acg_dfa* a) { return a ? a->stats.engine : 0; }
+int acg_last_stats(const acg_dfa* a, acg_stats* out) {
+  if (!a || !out) return ACG_E_INVALID_ARG;
+  *out = a->stats;
+  return ACG_OK;
+}
+
+int acg_find_overlapping(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+                         uint64_t span_end, int anchored, acg_match* out, uint64_t cap,
+                         uint64_t* n_out) {
+  return overlapping_impl(a, hay, false, hay_len, span_start, span_end, anchored, out, cap, n_out,
+                          nullptr, nullptr);
+}
+int acg_find_overlapping_dev(const acg_dfa* a, const void* d_hay, uint64_t hay_len,
+                             uint64_t span_start, uint64_t span_end, acg_match* out, uint64_t cap,
+                             uint64_t* n_out, float* kernel_ms) {
+  return overlapping_impl(a, static_cast<const uint8_t*>(d_hay), true, hay_len, span_start, span_end,
+                          0, out, cap, n_out, nullptr, kernel_ms);
+}
+int acg_count_overlapping_dev(const acg_dfa* a, const void* d_hay, uint64_t hay_len,
+                              uint64_t span_start, uint64_t span_end, uint64_t* n_out, uint64_t* fnv,
+                              float* kernel_ms) {
+  uint64_t dummy_fnv = 0;
+  return overlapping_impl(a, static_cast<const uint8_t*>(d_hay), true, hay_len, span_start, span_end,
+                          0, nullptr, 0, n_out, fnv ? fnv : &dummy_fnv, kernel_ms);
+}
+
+int acg_find_iter(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+                  uint64_t span_end, int anchored, acg_match* out, uint64_t cap, uint64_t* n_out) {
+  return find_iter_impl(a, hay, false, hay_len, span_start, span_end, anchored, out, cap, n_out,
+                        nullptr);
+}
+int acg_find_iter_dev(const acg_dfa* a, const void* d_hay, uint64_t hay_len, uint64_t span_start,
+                      uint64_t span_end, acg_match* out, uint64_t cap, uint64_t* n_out,
+                      float* kernel_ms) {
+  return find_iter_impl(a, static_cast<const uint8_t*>(d_hay), true, hay_len, span_start, span_end, 0,
+                        out, cap, n_out, kernel_ms);
+}
+
+int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+             uint64_t span_end, int anchored, int earliest, acg_match* out, int* found) {
+  if (!out || !found) return ACG_E_INVALID_ARG;
+  *found = 0;
+  int rc = validate_common(a, hay_len, span_start, span_end, anchored);
+  if (rc) return rc;
+  if ((rc = check_start(a->h, anchored))) return rc;
+  if (!a->on_device) return ACG_E_NO_DEVICE;
+  if (span_start > span_end) return ACG_OK;
+  std::lock_guard<std::mutex> lock(a->mu);
+  DeviceGuard guard(a->device);
+  a->stats = acg_stats{};
+  a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+  const uint8_t* d_base = nullptr;
+  if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+  uint64_t n = 0;
+  rc = run_seq(a, d_base, span_start, span_end, anchored, earliest, 1, out, 1, &n);
+  if (rc == ACG_OK && n) *found = 1;
+  return rc;
+}
+
+const char* acg_strerror(int code) {
+  switch (code) {
+    case ACG_OK: return "ok";
+    case ACG_E_STATE_ID_OVERFLOW: return "state identifier overflow";
+    case ACG_E_PATTERN_ID_OVERFLOW: return "pattern identifier overflow";
+    case ACG_E_PATTERN_TOO_LONG: return "pattern exceeds the maximum pattern length";
+    case ACG_E_INVALID_INPUT_ANCHORED: return "anchored searches are not supported or enabled";
+    case ACG_E_INVALID_INPUT_UNANCHORED: return "unanchored searches are not supported or enabled";
+    case ACG_E_UNSUPPORTED_STREAM: return "match kind does not support stream searching";
+    case ACG_E_UNSUPPORTED_OVERLAPPING: return "match kind does not support overlapping searches";
+    case ACG_E_UNSUPPORTED_EMPTY: return "matching with an empty pattern string is not supported here";
+    case ACG_E_INVALID_SPAN: return "invalid span for haystack";
+    case ACG_E_OVERFLOW: return "output buffer too small";
+    case ACG_E_INVALID_ARG: return "invalid argument";
+    case ACG_E_CUDA: return "CUDA error";
+    case ACG_E_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case ACG_E_NOMEM: return "out of memory";
+    default: return "unknown error";
+  }
+}
+
+int acg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+}  // extern "C"

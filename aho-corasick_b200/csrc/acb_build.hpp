@@ -1,0 +1,65 @@
+// acb_build.hpp -- host-side automaton construction for the B200 search path.
+//
+// Produces the dense DFA the device kernels consume, with tables that are
+// bit-identical to what the reference's own builder produces for the same
+// patterns and options (AhoCorasickBuilder::build with kind = DFA:
+// src/ahocorasick.rs:2171-2207 -> src/nfa/noncontiguous.rs:963-1051 ->
+// src/dfa.rs:431-540).  The implementation is an independent design (explicit
+// trie with per-node sorted edge lists, failure links by BFS, DFA rows filled
+// by row inheritance from the failure state) -- it shares no code with the
+// test oracle under oracle/, which restates the reference's data structures.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace acb {
+
+enum : int { kStandard = 0, kLeftmostFirst = 1, kLeftmostLongest = 2 };
+enum : int { kStartUnanchored = 0, kStartAnchored = 1, kStartBoth = 2 };
+enum : int { kPreNone = 0, kPreMemmem = 1, kPreStartBytes = 2, kPreRareBytes = 3, kPrePacked = 4 };
+
+struct BuildOptions {
+  int match_kind = kStandard;
+  int start_kind = kStartUnanchored;
+  bool ascii_case_insensitive = false;
+  bool byte_classes = true;
+  bool prefilter = true;
+  int kind = 0;  // AhoCorasickKind requested (0 auto); only reported back
+};
+
+// Which packed (Teddy) searcher the reference would construct as a prefilter
+// (src/packed/api.rs:253-322, src/packed/teddy/builder.rs:98-231).
+struct PackedPlan {
+  bool active = false;
+  bool fat = false;
+  int mask_len = 0;
+};
+
+struct HostDfa {
+  std::vector<uint32_t> trans;  // premultiplied ids, [state_len << stride2]
+  uint32_t stride2 = 0;
+  uint32_t alphabet_len = 0;
+  uint8_t classes[256] = {0};
+  uint32_t max_special_id = 0, max_match_id = 0, start_unanchored_id = 0, start_anchored_id = 0;
+  std::vector<uint32_t> match_offsets;  // [num_match_states + 1]
+  std::vector<uint32_t> match_pids;
+  std::vector<uint32_t> pattern_lens;
+  int match_kind = kStandard;
+  int start_kind = kStartUnanchored;
+  int reported_kind = 3;
+  uint64_t min_pattern_len = UINT64_MAX, max_pattern_len = 0;
+  uint64_t state_len = 0;
+  int prefilter_kind = kPreNone;
+  PackedPlan packed;
+};
+
+struct PatternRef {
+  const uint8_t* p;
+  uint64_t n;
+};
+
+// Returns 0 or a negative ACG_E_* build error code.
+int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts, HostDfa* out);
+
+}  // namespace acb

@@ -1,0 +1,205 @@
+// acb_kernels.cu -- sm_100a kernels of the Aho-Corasick search path.
+//
+//   K1  walk_overlapping_kernel   sharded DFA state-transition scan; replaces the
+//                                 loop of try_find_overlapping_fwd_imp
+//                                 (src/automaton.rs:1491-1534) + DFA::next_state
+//                                 (src/dfa.rs:218-226) + match expansion (:275-286)
+//   Kseq seq_find_kernel          single-lane FindIter/try_find (anchored inputs,
+//                                 empty-pattern automata)
+//   K4  sort_pairs                ordering of the appended tuples (CUB radix sort)
+#include "acb_device.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace acb {
+
+namespace {
+
+__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// Append the whole pattern list of match state `sid` (entered after consuming
+// the byte at absolute offset end-1) to the tuple buffer.
+__device__ __forceinline__ void emit_state_matches(const DfaDev& d, uint32_t sid, uint64_t end_rel,
+                                                   uint64_t* keys, uint32_t* pids,
+                                                   unsigned long long* counter, uint64_t cap) {
+  const uint32_t row = (sid >> d.stride2) - 2;
+  const uint32_t lo = d.match_offsets[row], hi = d.match_offsets[row + 1];
+  const uint32_t n = hi - lo;
+  const unsigned long long base = atomicAdd(counter, (unsigned long long)n);
+  if (base + n > cap) return;  // overflow: the host sees counter > cap and retries
+  for (uint32_t i = 0; i < n; ++i) {
+    keys[base + i] = (end_rel << kTieBits) | (uint64_t)i;
+    pids[base + i] = d.match_pids[lo + i];
+  }
+}
+
+constexpr int kWalkThreads = 256;
+
+// One lane per haystack shard.  A lane starts cold (start state) at most
+// max_pattern_len-1 bytes before its shard -- the Aho-Corasick state depends on
+// at most that many trailing bytes -- and only reports matches whose end lies
+// inside its shard, so every end offset is owned by exactly one lane.
+__global__ void __launch_bounds__(kWalkThreads)
+walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
+  __shared__ uint8_t s_cls[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = d.classes[i];
+  __syncthreads();
+
+  const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= p.n_segs) return;
+  const uint64_t g0 = p.span_start + seg * p.seg_len;
+  uint64_t g1 = g0 + p.seg_len;
+  if (g1 > p.span_end) g1 = p.span_end;
+  const uint64_t back = d.max_pattern_len > 0 ? (uint64_t)d.max_pattern_len - 1 : 0;
+  uint64_t pos = (g0 - p.span_start > back) ? g0 - back : p.span_start;
+
+  const uint32_t* __restrict__ trans = d.trans;
+  const uint32_t max_match = d.max_match_id;
+  uint32_t sid = d.start_unanchored_id;
+
+  // matches of the start state itself (empty patterns) at the very beginning of
+  // the span are reported before the first byte (src/automaton.rs:1456-1464)
+  if (seg == 0 && sid != 0 && sid <= max_match)
+    emit_state_matches(d, sid, 0, p.keys, p.pids, p.counter, p.cap);
+
+#define ACB_STEP(byte_expr)                                                          \
+  do {                                                                               \
+    sid = __ldg(trans + sid + s_cls[(byte_expr)]);                                   \
+    if (sid <= max_match) {                                                          \
+      if (sid == 0) { pos = g1; break; }                                             \
+      if (pos >= g0)                                                                 \
+        emit_state_matches(d, sid, pos + 1 - p.span_start, p.keys, p.pids, p.counter, p.cap); \
+    }                                                                                \
+    ++pos;                                                                           \
+  } while (0)
+
+  const uint8_t* __restrict__ hay = p.hay;
+  while (pos < g1 && ((reinterpret_cast<uintptr_t>(hay + pos)) & 15)) ACB_STEP(hay[pos]);
+  while (pos + 16 <= g1) {
+    const uint4 v = ld_nc_u4(hay + pos);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    bool dead = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t b = (w[k >> 2] >> ((k & 3) * 8)) & 0xFF;
+      sid = __ldg(trans + sid + s_cls[b]);
+      if (sid <= max_match) {
+        if (sid == 0) { dead = true; break; }
+        if (pos >= g0)
+          emit_state_matches(d, sid, pos + 1 - p.span_start, p.keys, p.pids, p.counter, p.cap);
+      }
+      ++pos;
+    }
+    if (dead) { pos = g1; break; }
+  }
+  while (pos < g1) ACB_STEP(hay[pos]);
+#undef ACB_STEP
+}
+
+// ---- sequential engine -------------------------------------------------------
+
+struct SeqMatch {
+  uint32_t pid;
+  uint64_t start, end;
+};
+
+__device__ __forceinline__ bool seq_is_match(const DfaDev& d, uint32_t sid) {
+  return sid != 0 && sid <= d.max_match_id;
+}
+__device__ __forceinline__ SeqMatch seq_get_match(const DfaDev& d, uint32_t sid, uint32_t idx, uint64_t at) {
+  const uint32_t row = (sid >> d.stride2) - 2;
+  const uint32_t pid = d.match_pids[d.match_offsets[row] + idx];
+  SeqMatch m;
+  m.pid = pid;
+  m.start = at - d.pattern_lens[pid];
+  m.end = at;
+  return m;
+}
+
+// try_find_fwd_imp, src/automaton.rs:1285-1420 (prefilter-free instance)
+__device__ bool seq_try_find(const DfaDev& d, const uint8_t* hay, uint64_t start, uint64_t end,
+                             bool anchored, bool earliest, SeqMatch* out) {
+  if (start > end) return false;
+  uint32_t sid = anchored ? d.start_anchored_id : d.start_unanchored_id;
+  uint64_t at = start;
+  bool have = false;
+  SeqMatch mat;
+  if (seq_is_match(d, sid)) {
+    mat = seq_get_match(d, sid, 0, at);
+    have = true;
+    if (earliest) { *out = mat; return true; }
+  }
+  while (at < end) {
+    sid = d.trans[sid + d.classes[hay[at]]];
+    if (sid <= d.max_match_id) {
+      if (sid == 0) break;
+      SeqMatch m = seq_get_match(d, sid, 0, at + 1);
+      if (!(anchored && m.start > start)) {
+        mat = m;
+        have = true;
+        if (earliest) break;
+      }
+    }
+    ++at;
+  }
+  if (have) *out = mat;
+  return have;
+}
+
+__global__ void seq_find_kernel(DfaDev d, SeqLaunch p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const bool anchored = p.anchored != 0;
+  const bool earliest = p.match_kind == 0 || p.earliest != 0;
+  uint64_t start = p.span_start;
+  unsigned long long n = 0;
+  bool have_last = false;
+  uint64_t last_end = 0;
+  for (;;) {
+    SeqMatch m;
+    if (!seq_try_find(d, p.hay, start, p.span_end, anchored, earliest, &m)) break;
+    if (!p.single && m.start == m.end && have_last && m.end == last_end) {
+      // FindIter::handle_overlapping_empty_match, src/automaton.rs:910-920
+      start += 1;
+      if (!seq_try_find(d, p.hay, start, p.span_end, anchored, earliest, &m)) break;
+    }
+    if (n < p.cap) {
+      p.out[n * 3 + 0] = m.pid;
+      p.out[n * 3 + 1] = m.start;
+      p.out[n * 3 + 2] = m.end;
+    }
+    ++n;
+    if (p.single) break;
+    start = m.end;
+    last_end = m.end;
+    have_last = true;
+  }
+  *p.counter = n;
+}
+
+}  // namespace
+
+cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s) {
+  const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;
+  walk_overlapping_kernel<<<(unsigned)blocks, kWalkThreads, 0, s>>>(dfa, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seq_find(const DfaDev& dfa, const SeqLaunch& p, cudaStream_t s) {
+  seq_find_kernel<<<1, 32, 0, s>>>(dfa, p);
+  return cudaGetLastError();
+}
+
+cudaError_t sort_pairs(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
+                       const uint32_t* vals_in, uint32_t* vals_out, uint64_t n, int end_bit,
+                       cudaStream_t s) {
+  return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, keys_in, keys_out, vals_in, vals_out, n,
+                                         0, end_bit, s);
+}
+
+}  // namespace acb

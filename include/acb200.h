@@ -1,0 +1,195 @@
+/*
+ * acb200.h -- C ABI of the B200-native Aho-Corasick search path (libacb200.so).
+ *
+ * This is the drop-in boundary.  The reference has no
+ * FFI in-tree; the seam its hot path sits behind is the sealed trait
+ * `unsafe trait Automaton` (src/automaton.rs:198) reached from `AhoCorasick`
+ * through `Arc<dyn AcAutomaton>` (src/ahocorasick.rs:177-180) with exactly two
+ * virtual entry points on the search path -- `try_find` and
+ * `try_find_overlapping` (src/ahocorasick.rs:2757-2772).  Every export below
+ * cites the reference interface it replaces.  Plain pointers and sizes only,
+ * no exceptions/panics cross the boundary, handles are immutable after
+ * creation and safe for concurrent searches (the reference's automata are
+ * Send + Sync, src/lib.rs:274-326).
+ *
+ * There is no CPU fallback: every search entry point returns ACG_E_CUDA /
+ * ACG_E_NO_DEVICE if no CUDA device is usable.
+ */
+#ifndef ACB200_H
+#define ACB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/util/search.rs:1052 MatchKind */
+enum { ACG_STANDARD = 0, ACG_LEFTMOST_FIRST = 1, ACG_LEFTMOST_LONGEST = 2 };
+/* src/util/search.rs:1133 StartKind */
+enum { ACG_START_UNANCHORED = 0, ACG_START_ANCHORED = 1, ACG_START_BOTH = 2 };
+/* src/ahocorasick.rs:2624 AhoCorasickKind (0 = None / auto, :2213-2261) */
+enum { ACG_KIND_AUTO = 0, ACG_KIND_NONCONTIGUOUS_NFA = 1, ACG_KIND_CONTIGUOUS_NFA = 2, ACG_KIND_DFA = 3 };
+/* which prefilter the reference would have built, src/util/prefilter.rs:163-305 */
+enum { ACG_PRE_NONE = 0, ACG_PRE_MEMMEM = 1, ACG_PRE_START_BYTES = 2, ACG_PRE_RARE_BYTES = 3, ACG_PRE_PACKED = 4 };
+/* device engines (acg_set_engine / acg_last_engine) */
+enum {
+  ACG_ENGINE_AUTO = 0,
+  ACG_ENGINE_WALK = 1,      /* sharded DFA state-transition scan (K1) */
+  ACG_ENGINE_PREFILTER = 2, /* k-gram prefilter + anchored DFA verify (K3/K3b), the packed/Teddy role */
+  ACG_ENGINE_SEQUENTIAL = 3 /* single-lane restatement of the reference loop (anchored inputs, empty patterns) */
+};
+
+/* Error convention: 0 = OK; negative codes map 1:1 to BuildError
+ * (src/util/error.rs:23-49) and MatchErrorKind (:200-223), plus boundary codes. */
+enum {
+  ACG_OK = 0,
+  ACG_E_STATE_ID_OVERFLOW = -1,
+  ACG_E_PATTERN_ID_OVERFLOW = -2,
+  ACG_E_PATTERN_TOO_LONG = -3,
+  ACG_E_INVALID_INPUT_ANCHORED = -10,
+  ACG_E_INVALID_INPUT_UNANCHORED = -11,
+  ACG_E_UNSUPPORTED_STREAM = -12,
+  ACG_E_UNSUPPORTED_OVERLAPPING = -13,
+  ACG_E_UNSUPPORTED_EMPTY = -14,
+  ACG_E_INVALID_SPAN = -20, /* the reference panics, src/util/search.rs:332-343 */
+  ACG_E_OVERFLOW = -21,     /* out buffer too small; *n_out holds the required count */
+  ACG_E_INVALID_ARG = -22,
+  ACG_E_CUDA = -30,
+  ACG_E_NO_DEVICE = -31,
+  ACG_E_NOMEM = -32
+};
+
+/* `Match { pattern: PatternID, span: Span }`, src/util/search.rs:825-830 */
+typedef struct {
+  uint32_t pid;
+  uint32_t _pad;
+  uint64_t start;
+  uint64_t end;
+} acg_match;
+
+/* AhoCorasickBuilder knobs, src/ahocorasick.rs:2135-2617 */
+typedef struct {
+  int32_t match_kind;             /* default ACG_STANDARD */
+  int32_t start_kind;             /* default ACG_START_UNANCHORED */
+  int32_t ascii_case_insensitive; /* default 0 */
+  int32_t byte_classes;           /* default 1 */
+  int32_t prefilter;              /* default 1 */
+  int32_t kind;                   /* default ACG_KIND_AUTO; the device always executes a DFA */
+  int64_t dense_depth;            /* accepted for API parity; has no effect on a DFA */
+} acg_build_opts;
+
+/* The data `DFA` exposes through the Automaton trait (src/dfa.rs:91-132,
+ * 192-302).  This is what a Rust `-sys` shim passes after building the
+ * automaton with the reference's own builder. */
+typedef struct {
+  const uint32_t* trans;        /* premultiplied next-state ids, row-major [state_len][1<<stride2] */
+  uint64_t trans_len;
+  uint32_t stride2;
+  uint32_t alphabet_len;
+  uint8_t byte_classes[256];
+  uint32_t max_special_id, max_match_id, start_unanchored_id, start_anchored_id;
+  const uint32_t* match_offsets; /* CSR over match states 2..=max_match_id>>stride2: [n+1] */
+  const uint32_t* match_pids;
+  const uint32_t* pattern_lens;
+  uint32_t n_patterns;
+  uint32_t match_kind;
+  uint32_t start_kind;
+  uint32_t prefilter_kind;       /* informative (ACG_PRE_*) */
+  uint64_t min_pattern_len, max_pattern_len;
+} acg_dfa_desc;
+
+typedef struct acg_dfa acg_dfa;
+
+void acg_build_opts_default(acg_build_opts* o);
+
+/* AhoCorasickBuilder::build (src/ahocorasick.rs:2171-2207) with kind=DFA:
+ * noncontiguous construction (src/nfa/noncontiguous.rs:963-1051) followed by
+ * dfa::Builder::build_from_noncontiguous (src/dfa.rs:431-540), then upload.
+ * The host tables are bit-identical to the reference's. */
+int acg_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+              const acg_build_opts* opts, acg_dfa** out);
+/* Same, host tables only (no CUDA needed): for table-parity checks. Searches
+ * on such a handle return ACG_E_NO_DEVICE. */
+int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                   const acg_build_opts* opts, acg_dfa** out);
+/* Adopt a DFA built by the reference itself (pointers borrowed for the call). */
+int acg_dfa_create(const acg_dfa_desc* desc, acg_dfa** out);
+void acg_dfa_free(acg_dfa* dfa);
+
+/* Host view of the tables held by the handle (borrowed until acg_dfa_free). */
+int acg_dfa_table(const acg_dfa* dfa, acg_dfa_desc* out);
+uint64_t acg_dfa_state_len(const acg_dfa* dfa);
+/* getters, src/ahocorasick.rs:1867-2021 */
+int acg_kind(const acg_dfa* dfa); /* what AhoCorasick::kind() would report for these options */
+int acg_match_kind(const acg_dfa* dfa);
+int acg_start_kind(const acg_dfa* dfa);
+uint64_t acg_patterns_len(const acg_dfa* dfa);
+uint64_t acg_min_pattern_len(const acg_dfa* dfa);
+uint64_t acg_max_pattern_len(const acg_dfa* dfa);
+uint64_t acg_memory_usage(const acg_dfa* dfa);
+int acg_prefilter_kind(const acg_dfa* dfa);
+/* Teddy variant the reference would pick (src/packed/teddy/builder.rs:98-231); 0 if not packed */
+int acg_packed_variant(const acg_dfa* dfa, int* fat, int* mask_len);
+
+/* Engine override (default AUTO) and introspection for tests/bench. */
+int acg_set_engine(acg_dfa* dfa, int engine);
+int acg_last_engine(const acg_dfa* dfa);
+
+/* ---- searches over HOST buffers (copies are part of the call) ------------- */
+
+/* AhoCorasick::try_find_overlapping_iter(...).collect()
+ * (src/ahocorasick.rs:1350 -> src/automaton.rs:397-423, 954-970, 1423-1537):
+ * all matches in the reference's iteration order. Two-call protocol on
+ * ACG_E_OVERFLOW. */
+int acg_find_overlapping(const acg_dfa* dfa, const uint8_t* hay, uint64_t hay_len,
+                         uint64_t span_start, uint64_t span_end, int anchored,
+                         acg_match* out, uint64_t cap, uint64_t* n_out);
+/* AhoCorasick::try_find_iter(...).collect()
+ * (src/ahocorasick.rs:1275 -> src/automaton.rs:844-936, 1259-1420). */
+int acg_find_iter(const acg_dfa* dfa, const uint8_t* hay, uint64_t hay_len,
+                  uint64_t span_start, uint64_t span_end, int anchored,
+                  acg_match* out, uint64_t cap, uint64_t* n_out);
+/* AhoCorasick::try_find (src/ahocorasick.rs:1021) / is_match (:311, earliest=1). */
+int acg_find(const acg_dfa* dfa, const uint8_t* hay, uint64_t hay_len,
+             uint64_t span_start, uint64_t span_end, int anchored, int earliest,
+             acg_match* out, int* found);
+
+/* ---- searches over DEVICE-resident haystacks (roofline measurement; no H2D) -
+ * d_hay points at haystack byte 0 in device memory.  Results are written to the
+ * host array `out` (matches are sparse); *kernel_ms, if non-NULL, receives the
+ * CUDA-event time of the scan kernels on the library's stream. */
+int acg_find_overlapping_dev(const acg_dfa* dfa, const void* d_hay, uint64_t hay_len,
+                             uint64_t span_start, uint64_t span_end,
+                             acg_match* out, uint64_t cap, uint64_t* n_out, float* kernel_ms);
+int acg_find_iter_dev(const acg_dfa* dfa, const void* d_hay, uint64_t hay_len,
+                      uint64_t span_start, uint64_t span_end,
+                      acg_match* out, uint64_t cap, uint64_t* n_out, float* kernel_ms);
+/* Count-only variants: scan + order on the device, return the number of matches
+ * and an FNV-1a checksum of the ordered (pid,start,end) stream computed on the
+ * device-ordered tuples (host side folds it).  `d_out`/cap may be 0/NULL. */
+int acg_count_overlapping_dev(const acg_dfa* dfa, const void* d_hay, uint64_t hay_len,
+                              uint64_t span_start, uint64_t span_end,
+                              uint64_t* n_out, uint64_t* fnv, float* kernel_ms);
+
+/* per-call statistics of the most recent search on this handle (bench glue) */
+typedef struct {
+  int32_t engine;
+  int32_t launches;          /* kernels launched by the library in the call */
+  uint64_t candidates;       /* prefilter survivors (ACG_ENGINE_PREFILTER) */
+  uint64_t raw_matches;      /* tuples appended before ordering/stitching */
+  float scan_ms;             /* dominant scan kernel(s) */
+  float order_ms;            /* ordering / compaction */
+  float h2d_ms, d2h_ms;
+} acg_stats;
+int acg_last_stats(const acg_dfa* dfa, acg_stats* out);
+
+const char* acg_strerror(int code);
+/* number of CUDA devices visible (0 if none / driver missing) */
+int acg_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

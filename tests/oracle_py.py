@@ -137,7 +137,9 @@ class Oracle:
         rc = _lib.orc_dfa_get(self._h, C.byref(v))
         if rc:
             raise OracleError(rc)
-        nms = v.num_match_states
+        # meaningful CSR prefix: rows 2 ..= max_match_id >> stride2 (StartKind::Both over-allocates
+        # `matches` when the start states are match states, src/dfa.rs:479-491)
+        nms = min(v.num_match_states, (v.max_match_id >> v.stride2) - 1)
         offs = np.ctypeslib.as_array(v.match_offsets, (nms + 1,)).copy()
         return {
             "trans": np.ctypeslib.as_array(v.trans, (v.trans_len,)).copy() if v.trans_len else np.zeros(0, np.uint32),
@@ -146,7 +148,8 @@ class Oracle:
             "max_special_id": v.max_special_id, "max_match_id": v.max_match_id,
             "start_unanchored_id": v.start_unanchored_id, "start_anchored_id": v.start_anchored_id,
             "match_offsets": offs,
-            "match_pids": np.ctypeslib.as_array(v.match_pids, (max(int(offs[-1]), 1),)).copy()[: int(offs[-1])],
+            "match_pids": (np.ctypeslib.as_array(v.match_pids, (int(offs[-1]),)).copy()
+                           if int(offs[-1]) else np.zeros(0, np.uint32)),
             "pattern_lens": (np.ctypeslib.as_array(v.pattern_lens, (v.n_patterns,)).copy()
                              if v.n_patterns else np.zeros(0, np.uint32)),
             "match_kind": v.match_kind, "min_pattern_len": v.min_pattern_len,

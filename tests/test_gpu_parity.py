@@ -1,0 +1,191 @@
+"""GPU parity tests: every search goes through the C ABI (libacb200.so) into the CUDA kernels and
+is compared tuple-for-tuple (order included) with the CPU oracle / the committed golden vectors."""
+import random
+
+import numpy as np
+import pytest
+
+import aho_corasick_b200 as ab
+import golden_util as G
+import oracle_py as O
+from aho_corasick_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+
+AC = G.load("ac_vectors.json")
+PK = G.load("packed_vectors.json")
+
+
+def build(pats, match_kind=0, **kw):
+    b = ab.AhoCorasick.builder().match_kind(match_kind)
+    for k, v in kw.items():
+        getattr(b, k)(v)
+    return b.build(pats)
+
+
+def tuples(ms):
+    return [m.as_tuple() for m in ms]
+
+
+def np_tuples(r):
+    return list(zip(r["pid"].tolist(), r["start"].tolist(), r["end"].tolist()))
+
+
+def assert_np_equal(got, want, ctx=None):
+    assert len(got) == len(want), (len(got), len(want), ctx)
+    for k in ("pid", "start", "end"):
+        if not np.array_equal(got[k], want[k]):
+            i = int(np.nonzero(got[k] != want[k])[0][0])
+            raise AssertionError((k, i, np_tuples(got[max(0, i - 2): i + 3]), np_tuples(want[max(0, i - 2): i + 3]), ctx))
+
+
+# ---- golden vectors through the device path (DFA rows of src/tests.rs:808-860, 937-994) -------
+@pytest.mark.parametrize("combo", list(G.COMBO_DFA) + ["default"])
+@pytest.mark.parametrize("coll,kind", G.NON_OVERLAPPING_COLLECTIONS)
+def test_golden_find_iter(coll, kind, combo):
+    kw = {k: v for k, v in G.COMBO[combo].items()}
+    for t in G.collection(AC, coll):
+        ac = build(t["patterns"], kind, **kw)
+        assert tuples(ac.find_iter(t["haystack"])) == t["matches"], (t["name"], combo)
+
+
+@pytest.mark.parametrize("combo", list(G.COMBO_DFA) + ["default"])
+def test_golden_find_overlapping_iter(combo):
+    kw = {k: v for k, v in G.COMBO[combo].items()}
+    for t in G.collection(AC, "AC_STANDARD_OVERLAPPING"):
+        ac = build(t["patterns"], 0, **kw)
+        assert tuples(ac.find_overlapping_iter(t["haystack"])) == t["matches"], (t["name"], combo)
+
+
+@pytest.mark.parametrize("combo", ["dfa_default", "dfa_start_both"])
+@pytest.mark.parametrize("coll,kind", G.ANCHORED)
+def test_golden_anchored(coll, kind, combo):
+    kw = dict(G.ANCHORED_COMBO[combo])
+    for t in G.collection(AC, coll):
+        ac = build(t["patterns"], kind, **kw)
+        assert tuples(ac.find_iter(t["haystack"], anchored=ab.Anchored.Yes)) == t["matches"], (t["name"], combo)
+
+
+def test_golden_ascii_case_insensitive():
+    for kind, groups, overlapping in [
+        (0, ["ASCII_CASE_INSENSITIVE", "ASCII_CASE_INSENSITIVE_NON_OVERLAPPING"], False),
+        (0, ["ASCII_CASE_INSENSITIVE", "ASCII_CASE_INSENSITIVE_OVERLAPPING"], True),
+        (1, ["ASCII_CASE_INSENSITIVE", "ASCII_CASE_INSENSITIVE_NON_OVERLAPPING"], False),
+        (2, ["ASCII_CASE_INSENSITIVE", "ASCII_CASE_INSENSITIVE_NON_OVERLAPPING"], False),
+    ]:
+        for g in groups:
+            for t in AC["groups"][g]:
+                ac = build(t["patterns"], kind, ascii_case_insensitive=True, kind=ab.AhoCorasickKind.DFA)
+                got = ac.find_overlapping_iter(t["haystack"]) if overlapping else ac.find_iter(t["haystack"])
+                assert tuples(got) == t["matches"], (t["name"], kind, overlapping)
+
+
+def test_readme_and_doc_examples():
+    hay = b"Nobody likes maple in their apple flavored Snapple."
+    assert tuples(ab.AhoCorasick.new([b"apple", b"maple", b"Snapple"]).find_iter(hay)) == \
+        [(1, 13, 18), (0, 28, 33), (2, 43, 50)]
+    pats, hay = [b"append", b"appendage", b"app"], b"append the app to the appendage"
+    assert tuples(build(pats).find_overlapping_iter(hay)) == \
+        [(2, 0, 3), (0, 0, 6), (2, 11, 14), (2, 22, 25), (0, 22, 28), (1, 22, 31)]
+    assert tuples(build(pats, 1).find_iter(hay)) == [(0, 0, 6), (2, 11, 14), (0, 22, 28)]
+    assert tuples(build(pats, 2).find_iter(hay)) == [(0, 0, 6), (2, 11, 14), (1, 22, 31)]
+    ac = build(pats, 1)
+    assert ac.find(hay).as_tuple() == (0, 0, 6)
+    assert ac.is_match(hay) and not ac.is_match(b"xyz")
+    assert ac.find(b"abc") is None
+
+
+# ---- packed vectors with the 3 x 261 "Z" padding sweep (src/packed/tests.rs:42-92); on the device
+# the padding doubles as a shard-alignment sweep --------------------------------------------------
+@pytest.mark.parametrize("coll,kind", [("PACKED_LEFTMOST_FIRST", 1), ("PACKED_LEFTMOST_LONGEST", 2)])
+def test_packed_vectors_padding_sweep(coll, kind):
+    for t in G.collection(PK, coll):
+        ac = build(t["patterns"], kind, kind=ab.AhoCorasickKind.DFA)
+        for off in list(range(0, 40)) + [63, 64, 65, 127, 128, 129, 255, 256, 257, 260]:
+            z = b"Z" * off
+            sh = [(p, s + off, e + off) for p, s, e in t["matches"]]
+            assert tuples(ac.find_iter(z + t["haystack"])) == sh, (t["name"], off, "prefix")
+            assert tuples(ac.find_iter(t["haystack"] + z)) == list(t["matches"]), (t["name"], off, "suffix")
+            assert tuples(ac.find_iter(z + t["haystack"] + z)) == sh, (t["name"], off, "both")
+
+
+# ---- randomized differential tests vs the oracle ------------------------------------------------
+def rand_case(rng, it, allow_empty):
+    alphabet = [b"ab", b"abcd", bytes(range(256)), b"aAbBcC ", b"abcdefghijklmnopqrstuvwxyz"][it % 5]
+    npat = rng.choice([1, 2, 5, 20, 200])
+    lo = 0 if (allow_empty and it % 6 == 0) else 1
+    pats = [bytes(rng.choice(alphabet) for _ in range(rng.randint(lo, rng.choice([3, 8, 20]))))
+            for _ in range(npat)]
+    if it % 4 == 0:
+        pats += [pats[0], pats[-1][:2] or b"a"]
+    n = rng.choice([0, 1, 7, 100, 1000, 5000, 70000, 300000])
+    hay = np.frombuffer(bytes(rng.choice(alphabet) for _ in range(min(n, 5000))), dtype=np.uint8)
+    if n > 5000:
+        reps = (n + hay.size - 1) // hay.size
+        hay = np.tile(hay, reps)[:n].copy()
+        # break the periodicity a little
+        idx = np.array([rng.randrange(n) for _ in range(50)])
+        hay[idx] = np.frombuffer(bytes(rng.choice(alphabet) for _ in range(50)), dtype=np.uint8)
+    s = rng.randint(0, hay.size)
+    e = rng.randint(s, hay.size)
+    span = (s, e) if it % 3 == 0 else None
+    return pats, hay, span, alphabet == b"aAbBcC "
+
+
+def test_random_overlapping_vs_oracle():
+    rng = random.Random(0x6A11)
+    for it in range(120):
+        pats, hay, span, ci = rand_case(rng, it, allow_empty=True)
+        kw = {"ascii_case_insensitive": ci, "byte_classes": it % 7 != 0}
+        ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA, **kw)
+        o = O.Oracle(pats, kind=O.KIND_DFA, **kw)
+        assert_np_equal(ac.try_find_overlapping_iter_np(hay, span), o.find_overlapping_iter_np(hay, span),
+                        (it, pats[:5], hay.size, span))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_random_find_iter_vs_oracle(kind):
+    rng = random.Random(0xF17E + kind)
+    for it in range(90):
+        pats, hay, span, ci = rand_case(rng, it, allow_empty=True)
+        if hay.size > 70000:
+            hay = hay[:70000].copy()
+            span = None
+        kw = {"ascii_case_insensitive": ci}
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA, **kw)
+        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA, prefilter=False, **kw)
+        assert_np_equal(ac.try_find_iter_np(hay, span), o.find_iter_np(hay, span), (it, pats[:5], hay.size, span))
+
+
+def test_adopted_reference_tables():
+    """acg_dfa_create: the tables come from elsewhere (here: the oracle's restatement of the
+    reference builder) -- exactly what a Rust -sys shim would pass."""
+    pats, hay, _ = W.make_config("cfg2", 4 << 20)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    t = o.dfa()
+    t["start_kind"] = 0
+    ac = ab.AhoCorasick.from_dfa_tables(t)
+    assert_np_equal(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay))
+
+
+# ---- BASELINE config 2 at reduced size, full tuple stream; and a size-independent property ------
+def test_config2_reduced_full_tuple_parity():
+    import torch
+    pats, hay, planted = W.make_config("cfg2", 64 << 20)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    want = o.find_overlapping_iter_np(hay)
+    assert len(want) >= planted
+    d = torch.from_numpy(hay).cuda()
+    got, ms = ac.find_overlapping_iter_dev_np(d.data_ptr(), hay.size)
+    assert_np_equal(got, want)
+    # host-buffer entry point (H2D inside the call) gives the same stream
+    assert_np_equal(ac.try_find_overlapping_iter_np(hay), want)
+    # count + FNV of the ordered stream agree with the oracle's scalar scan loop
+    cnt, fnv, _ = ac.count_overlapping_dev(d.data_ptr(), hay.size)
+    assert (cnt, fnv) == o.scan_overlapping_count(hay)
+    # property: the stream over a span equals the full stream filtered to matches inside the span
+    s, e = 12345677, 50000003
+    sub, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), hay.size, span=(s, e))
+    keep = (want["start"] >= s) & (want["end"] <= e)
+    assert_np_equal(sub, want[keep])
