@@ -7,7 +7,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libacb200.so"
-SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_api.cu"]
+SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_prefilter.cu", "acb_api.cu"]
 HEADERS = ["acb_build.hpp", "acb_device.cuh", "../../include/acb200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -43,6 +43,11 @@ struct Workspace {
   uint64_t h_cap = 0;
   uint8_t* d_hay = nullptr;  // staging of host haystacks
   uint64_t d_hay_cap = 0;
+  uint64_t* d_scratch = nullptr;  // chain resolution: end offsets / prefix max [cap]
+  uint8_t* d_flags = nullptr;     // [cap]
+  void* d_temp2 = nullptr;        // scan / select temp
+  size_t temp2_bytes = 0;
+  uint64_t chain_cap = 0;
   uint64_t* d_seq = nullptr;  // sequential engine output [cap*3]
   uint64_t seq_cap = 0;
   uint64_t* h_seq = nullptr;
@@ -51,9 +56,23 @@ struct Workspace {
 
 }  // namespace
 
+// Plan of the prefilter engine for one automaton (derived from the tables alone, so it also
+// works for DFAs adopted through acg_dfa_create).
+struct PrefilterPlan {
+  bool supported = false;
+  uint32_t k = 0, kmask = 0, fold = 0, mult = 1, shift = 0, log_bits = 0;
+  bool brute = false;
+  uint32_t dup_shift = 0;
+  double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
+  uint64_t n_grams = 0;
+  std::vector<uint32_t> bitmap;
+};
+
 struct acg_dfa {
   HostDfa h;
-  std::vector<uint8_t> depth8;
+  std::vector<uint16_t> depth16;
+  PrefilterPlan pf;
+  uint32_t* d_bitmap = nullptr;
   bool has_empty = false;
   uint32_t max_list_len = 0;
   bool on_device = false;
@@ -63,7 +82,7 @@ struct acg_dfa {
   uint32_t* d_moff = nullptr;
   uint32_t* d_mpids = nullptr;
   uint32_t* d_plens = nullptr;
-  uint8_t* d_depth8 = nullptr;
+  uint16_t* d_depth16 = nullptr;
   DfaDev dev{};
   int engine_override = ACG_ENGINE_AUTO;
   mutable std::mutex mu;
@@ -73,26 +92,29 @@ struct acg_dfa {
 
 namespace {
 
+int bits_for(uint64_t v) {
+  int b = 0;
+  while (v) { ++b; v >>= 1; }
+  return b;
+}
+
 void derive_metadata(acg_dfa* a) {
   HostDfa& h = a->h;
   a->has_empty = h.min_pattern_len == 0 && !h.pattern_lens.empty();
   a->max_list_len = 0;
   for (size_t i = 0; i + 1 < h.match_offsets.size(); ++i)
     a->max_list_len = std::max(a->max_list_len, h.match_offsets[i + 1] - h.match_offsets[i]);
-  // trie depth of every row = BFS distance from the start row (each transition
-  // deepens the longest-suffix state by at most one byte).
+  // Trie depth of every row = BFS distance from the unanchored start row: one transition
+  // deepens the longest-suffix state by at most one byte, and a state of depth d is reached by
+  // its own d bytes.
   const uint32_t s2 = h.stride2;
   const size_t rows = size_t(h.state_len);
-  a->depth8.assign(rows, 255);
-  std::vector<uint32_t> q;
-  auto seed = [&](uint32_t sid) {
-    if (sid == 0) return;
-    a->depth8[sid >> s2] = 0;
-    q.push_back(sid >> s2);
-  };
-  seed(h.start_unanchored_id);
   std::vector<uint32_t> dist(rows, UINT32_MAX);
-  if (h.start_unanchored_id) dist[h.start_unanchored_id >> s2] = 0;
+  std::vector<uint32_t> q;
+  if (h.start_unanchored_id) {
+    dist[h.start_unanchored_id >> s2] = 0;
+    q.push_back(h.start_unanchored_id >> s2);
+  }
   for (size_t qi = 0; qi < q.size(); ++qi) {
     const uint32_t r = q[qi];
     const uint32_t* row = h.trans.data() + (size_t(r) << s2);
@@ -100,10 +122,90 @@ void derive_metadata(acg_dfa* a) {
       const uint32_t nr = row[c] >> s2;
       if (nr == 0 || dist[nr] != UINT32_MAX) continue;
       dist[nr] = dist[r] + 1;
-      a->depth8[nr] = uint8_t(std::min<uint32_t>(dist[nr], 255));
       q.push_back(nr);
     }
   }
+  a->depth16.assign(rows, 0xFFFF);
+  for (size_t r = 0; r < rows; ++r)
+    if (dist[r] != UINT32_MAX) a->depth16[r] = uint16_t(std::min<uint32_t>(dist[r], 0xFFFE));
+
+  // ---- prefilter plan ----
+  PrefilterPlan& pf = a->pf;
+  pf = PrefilterPlan{};
+  if (h.pattern_lens.empty() || a->has_empty || h.start_unanchored_id == 0) return;
+  if (h.max_pattern_len >= 0xFFFE || h.min_pattern_len == 0) return;
+  // tie-break layout: (max_len - len) << dup_shift | index among the node's own patterns
+  uint32_t max_dups = 1;
+  for (size_t m = 0; m + 1 < h.match_offsets.size(); ++m) {
+    const uint32_t lo = h.match_offsets[m], hi = h.match_offsets[m + 1];
+    const uint32_t dep = (m + 2 < rows) ? a->depth16[m + 2] : 0xFFFF;
+    uint32_t own = 0;
+    for (uint32_t i = lo; i < hi && h.pattern_lens[h.match_pids[i]] == dep; ++i) ++own;
+    max_dups = std::max(max_dups, own);
+  }
+  pf.dup_shift = uint32_t(bits_for(max_dups - 1));
+  if (bits_for(h.max_pattern_len) + int(pf.dup_shift) > acb::kTieBits) return;
+
+  // k-gram fingerprints: every trie path of length k from the start row, over raw bytes
+  const uint32_t kmax = uint32_t(std::min<uint64_t>(4, h.min_pattern_len));
+  struct Item { uint32_t row; uint32_t gram; };
+  std::vector<std::vector<uint32_t>> grams(kmax + 1);
+  std::vector<Item> cur{{h.start_unanchored_id >> s2, 0u}}, nxt;
+  for (uint32_t j = 0; j < kmax; ++j) {
+    nxt.clear();
+    for (const Item& it : cur) {
+      const uint32_t* row = h.trans.data() + (size_t(it.row) << s2);
+      for (uint32_t b = 0; b < 256; ++b) {
+        const uint32_t nr = row[h.classes[b]] >> s2;
+        if (nr == 0 || a->depth16[nr] != j + 1) continue;
+        nxt.push_back(Item{nr, it.gram | (b << (8 * j))});
+      }
+    }
+    cur.swap(nxt);
+    auto& g = grams[j + 1];
+    g.reserve(cur.size());
+    for (const Item& it : cur) g.push_back(it.gram);
+    std::sort(g.begin(), g.end());
+    g.erase(std::unique(g.begin(), g.end()), g.end());
+    if (cur.size() > (64u << 20)) break;  // pathological fan-out: give up on longer fingerprints
+  }
+  // pick the fingerprint length with the sparsest bitmap (ties -> longer)
+  double best_fill = 2.0;
+  for (uint32_t k = 1; k <= kmax; ++k) {
+    if (grams[k].empty()) continue;
+    std::vector<uint32_t> raw = grams[k], folded = grams[k];
+    for (uint32_t& g : folded) g |= 0x20202020u & (k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1));
+    std::sort(folded.begin(), folded.end());
+    folded.erase(std::unique(folded.begin(), folded.end()), folded.end());
+    const bool use_fold = folded.size() * 3 < raw.size() * 2;
+    const std::vector<uint32_t>& set = use_fold ? folded : raw;
+    uint32_t log_bits, mult, shift;
+    if (k <= 2) { log_bits = 8 * k; mult = 1; shift = 0; }
+    else {
+      log_bits = uint32_t(std::min(19, std::max(13, bits_for(uint64_t(set.size()) * 128 - 1))));
+      mult = 0x9E3779B1u;
+      shift = 32 - log_bits;
+    }
+    const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
+    std::vector<uint32_t> bm(size_t(1) << (log_bits - 5), 0u);
+    uint64_t set_bits = 0;
+    for (uint32_t g : set) {
+      const uint32_t idx = uint32_t(((g & kmask) * mult)) >> shift;
+      uint32_t& wd = bm[idx >> 5];
+      if (!(wd >> (idx & 31) & 1)) { wd |= 1u << (idx & 31); ++set_bits; }
+    }
+    const double fill = double(set_bits) / double(uint64_t(1) << log_bits);
+    if (fill <= best_fill) {
+      best_fill = fill;
+      pf.k = k; pf.kmask = kmask; pf.fold = use_fold ? (0x20202020u & kmask) : 0u;
+      pf.mult = mult; pf.shift = shift; pf.log_bits = log_bits;
+      pf.fill = fill; pf.n_grams = set.size();
+      pf.bitmap.swap(bm);
+    }
+  }
+  if (pf.k == 0) return;
+  pf.brute = pf.fill > 0.25;
+  pf.supported = true;
 }
 
 int upload(acg_dfa* a) {
@@ -125,14 +227,15 @@ int upload(acg_dfa* a) {
   CK(up(&a->d_moff, h.match_offsets.data(), h.match_offsets.size() * 4));
   CK(up(&a->d_mpids, h.match_pids.data(), h.match_pids.size() * 4));
   CK(up(&a->d_plens, h.pattern_lens.data(), h.pattern_lens.size() * 4));
-  CK(up(&a->d_depth8, a->depth8.data(), a->depth8.size()));
+  CK(up(&a->d_depth16, a->depth16.data(), a->depth16.size() * 2));
+  if (a->pf.supported && !a->pf.bitmap.empty()) CK(up(&a->d_bitmap, a->pf.bitmap.data(), a->pf.bitmap.size() * 4));
   DfaDev& d = a->dev;
   d.trans = a->d_trans;
   d.classes = a->d_classes;
   d.match_offsets = a->d_moff;
   d.match_pids = a->d_mpids;
   d.pattern_lens = a->d_plens;
-  d.depth8 = a->d_depth8;
+  d.depth16 = a->d_depth16;
   d.stride2 = h.stride2;
   d.max_match_id = h.max_match_id;
   d.start_unanchored_id = h.start_unanchored_id;
@@ -231,12 +334,6 @@ int check_start(const HostDfa& h, int anchored) {
   return h.start_unanchored_id == 0 ? ACG_E_INVALID_INPUT_UNANCHORED : ACG_OK;
 }
 
-int bits_for(uint64_t v) {
-  int b = 0;
-  while (v) { ++b; v >>= 1; }
-  return b;
-}
-
 struct TupleResult {
   uint64_t n = 0;
   int sorted_buf = 0;
@@ -307,9 +404,147 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   return ACG_E_NOMEM;
 }
 
+// K3/K3b (+ K4): prefilter engine on a device-resident haystack.  mode 0 leaves all occurrences
+// ordered like find_overlapping_iter; mode 1 leaves the best match per start offset ordered by
+// start (input of the chain resolution).
+int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t hay_len, uint64_t span_start,
+                  uint64_t span_end, int mode, TupleResult* res) {
+  Workspace& w = a->ws;
+  const PrefilterPlan& pf = a->pf;
+  const uint64_t n_bytes = span_end - span_start;
+  if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
+  int dev_sms = 148;
+  cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
+  // 16-byte aligned filter region whose 4-byte look-ahead stays inside the haystack allocation
+  const uintptr_t base = reinterpret_cast<uintptr_t>(d_hay);
+  uint64_t lo = span_start + ((16 - ((base + span_start) & 15)) & 15);
+  uint64_t limit = std::min<uint64_t>(span_end, hay_len >= 20 ? hay_len - 20 : 0);
+  uint64_t hi = lo;
+  if (limit > lo) hi = lo + ((limit - lo) & ~15ull);
+  if (lo > span_end) { lo = span_end; hi = span_end; }
+  const uint64_t tile_bytes = 16 * 1024;
+  const uint64_t n_tiles = (hi - lo + tile_bytes - 1) / tile_bytes;
+  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 64));
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    int rc = ensure_tuple_cap(w, cap);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(w.d_counter, 0, 16, w.stream));
+    acb::PrefilterLaunch p;
+    p.hay = d_hay;
+    p.hay_len = hay_len;
+    p.span_start = span_start;
+    p.span_end = span_end;
+    p.bitmap = a->d_bitmap;
+    p.log_bits = pf.log_bits;
+    p.k = pf.k;
+    p.kmask = pf.kmask;
+    p.fold = pf.fold;
+    p.mult = pf.mult;
+    p.shift = pf.shift;
+    p.brute = pf.brute ? 1 : 0;
+    p.mode = mode;
+    p.dup_shift = pf.dup_shift;
+    p.region_lo = lo;
+    p.region_hi = hi;
+    p.tile_bytes = tile_bytes;
+    p.n_tiles = n_tiles;
+    p.keys = w.d_keys[0];
+    p.pids = w.d_pids[0];
+    p.counter = w.d_counter;
+    p.cap = w.cap;
+    CK(cudaEventRecord(w.ev0, w.stream));
+    CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
+    CK(cudaEventRecord(w.ev1, w.stream));
+    CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 16, cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    a->stats.launches += 1;
+    const uint64_t want = w.h_counter[0];
+    a->stats.candidates = w.h_counter[1];
+    if (want > w.cap) { cap = want + want / 8 + 1024; continue; }
+    res->n = want;
+    a->stats.raw_matches = want;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, w.ev0, w.ev1);
+    a->stats.scan_ms = ms;
+    if (want > 1) {
+      size_t tb = w.temp_bytes;
+      const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
+      CK(cudaEventRecord(w.ev2, w.stream));
+      CK(acb::sort_pairs(w.d_temp, tb, w.d_keys[0], w.d_keys[1], w.d_pids[0], w.d_pids[1], want, end_bit,
+                         w.stream));
+      CK(cudaEventRecord(w.ev3, w.stream));
+      CK(cudaStreamSynchronize(w.stream));
+      cudaEventElapsedTime(&ms, w.ev2, w.ev3);
+      a->stats.order_ms = ms;
+      a->stats.launches += 8;
+      res->sorted_buf = 1;
+    } else {
+      res->sorted_buf = 0;
+    }
+    return ACG_OK;
+  }
+  return ACG_E_NOMEM;
+}
+
+int ensure_chain(Workspace& w, uint64_t n) {
+  if (n <= w.chain_cap) return ACG_OK;
+  if (w.d_scratch) cudaFree(w.d_scratch);
+  if (w.d_flags) cudaFree(w.d_flags);
+  if (w.d_temp2) cudaFree(w.d_temp2);
+  w.d_scratch = nullptr; w.d_flags = nullptr; w.d_temp2 = nullptr; w.chain_cap = 0;
+  const uint64_t cap = std::max<uint64_t>(n, 1 << 16);
+  CK(cudaMalloc(&w.d_scratch, cap * 8));
+  CK(cudaMalloc(&w.d_flags, cap));
+  size_t t1 = 0, t2 = 0;
+  CK(acb::scan_max_u64(nullptr, t1, w.d_scratch, cap, w.stream));
+  CK(acb::select_flagged(nullptr, t2, w.d_keys[0], w.d_pids[0], w.d_flags, w.d_keys[1], w.d_pids[1],
+                         w.d_counter, cap, w.stream));
+  w.temp2_bytes = std::max(t1, t2);
+  CK(cudaMalloc(&w.d_temp2, std::max<size_t>(w.temp2_bytes, 16)));
+  w.chain_cap = cap;
+  return ACG_OK;
+}
+
+// FindIter over ordered candidate tuples, on the device: marks the tuples the reference's
+// iterator yields and compacts them into the other tuple buffer.
+int run_chain(const acg_dfa* a, int mode, TupleResult* r) {
+  Workspace& w = a->ws;
+  if (r->n == 0) return ACG_OK;
+  int rc = ensure_chain(w, r->n);
+  if (rc) return rc;
+  const int src = r->sorted_buf, dst = 1 - src;
+  acb::ChainLaunch c;
+  c.keys = w.d_keys[src];
+  c.pids = w.d_pids[src];
+  c.pattern_lens = a->d_plens;
+  c.n = r->n;
+  c.mode = mode;
+  c.scratch_end = w.d_scratch;
+  c.flags = w.d_flags;
+  CK(cudaEventRecord(w.ev2, w.stream));
+  CK(cudaMemsetAsync(w.d_flags, 0, r->n, w.stream));
+  CK(acb::launch_chain_ends(c, w.stream));
+  size_t tb = w.temp2_bytes;
+  CK(acb::scan_max_u64(w.d_temp2, tb, w.d_scratch, r->n, w.stream));
+  CK(acb::launch_chain_select(c, w.stream));
+  tb = w.temp2_bytes;
+  CK(acb::select_flagged(w.d_temp2, tb, w.d_keys[src], w.d_pids[src], w.d_flags, w.d_keys[dst],
+                         w.d_pids[dst], w.d_counter, r->n, w.stream));
+  CK(cudaEventRecord(w.ev3, w.stream));
+  CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
+  CK(cudaStreamSynchronize(w.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, w.ev2, w.ev3);
+  a->stats.order_ms += ms;
+  a->stats.launches += 8;
+  r->n = *w.h_counter;
+  r->sorted_buf = dst;
+  return ACG_OK;
+}
+
 // D2H + expansion of ordered (key,pid) tuples into acg_match / count / fnv.
 int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, acg_match* out,
-                 uint64_t cap, uint64_t* n_out, uint64_t* fnv) {
+                 uint64_t cap, uint64_t* n_out, uint64_t* fnv, int key_mode = 0) {
   Workspace& w = a->ws;
   *n_out = r.n;
   if (fnv) *fnv = 0xcbf29ce484222325ull;
@@ -332,8 +567,14 @@ int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, ac
   };
   for (uint64_t i = 0; i < r.n; ++i) {
     const uint32_t pid = w.h_pids[i];
-    const uint64_t end = span_start + (w.h_keys[i] >> acb::kTieBits);
-    const uint64_t start = end - plens[pid];
+    uint64_t start, end;
+    if (key_mode == 1) {  // (start_rel << 24 | len)
+      start = span_start + (w.h_keys[i] >> acb::kTieBits);
+      end = start + (w.h_keys[i] & acb::kTieMask);
+    } else {              // (end_rel << 24 | tie)
+      end = span_start + (w.h_keys[i] >> acb::kTieBits);
+      start = end - plens[pid];
+    }
     if (out && i < cap) {
       out[i].pid = pid;
       out[i]._pad = 0;
@@ -453,13 +694,21 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
   a->stats = acg_stats{};
-  a->stats.engine = ACG_ENGINE_WALK;
+  int engine = a->engine_override;
+  if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) return ACG_E_INVALID_ARG;
+  if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
+    engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
+  a->stats.engine = engine;
   const uint8_t* d_base = hay;
+  uint64_t readable = hay_len;
   if (!hay_on_device) {
     if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+    readable = span_end + 32;  // the staging buffer has slack behind the span
   }
   TupleResult r;
-  if ((rc = run_walk_overlapping(a, d_base, span_start, span_end, &r))) return rc;
+  if (engine == ACG_ENGINE_PREFILTER) rc = run_prefilter(a, d_base, readable, span_start, span_end, 0, &r);
+  else rc = run_walk_overlapping(a, d_base, span_start, span_end, &r);
+  if (rc) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
   return drain_tuples(a, r, span_start, out, cap, n_out, fnv);
 }
@@ -477,14 +726,30 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
   a->stats = acg_stats{};
-  a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+  int engine = a->engine_override;
+  if (engine == ACG_ENGINE_PREFILTER && (!a->pf.supported || anchored)) return ACG_E_INVALID_ARG;
+  if (engine != ACG_ENGINE_SEQUENTIAL && engine != ACG_ENGINE_PREFILTER)
+    engine = (a->pf.supported && !anchored) ? ACG_ENGINE_PREFILTER : ACG_ENGINE_SEQUENTIAL;
+  a->stats.engine = engine;
   const uint8_t* d_base = hay;
+  uint64_t readable = hay_len;
   if (!hay_on_device) {
     if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+    readable = span_end + 32;
   }
-  rc = run_seq(a, d_base, span_start, span_end, anchored, 0, 0, out, cap, n_out);
-  if (kernel_ms) *kernel_ms = a->stats.scan_ms;
-  return rc;
+  if (engine == ACG_ENGINE_SEQUENTIAL) {
+    rc = run_seq(a, d_base, span_start, span_end, anchored, 0, 0, out, cap, n_out);
+    if (kernel_ms) *kernel_ms = a->stats.scan_ms;
+    return rc;
+  }
+  // Standard: all occurrences in (end, len desc, list) order, then the iterator's greedy choice;
+  // leftmost kinds: best match per start offset ordered by start, then the same greedy choice.
+  const int mode = a->h.match_kind == ACG_STANDARD ? 0 : 1;
+  TupleResult r;
+  if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode, &r))) return rc;
+  if ((rc = run_chain(a, mode, &r))) return rc;
+  if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
+  return drain_tuples(a, r, span_start, out, cap, n_out, nullptr, mode);
 }
 
 }  // namespace
@@ -587,9 +852,10 @@ void acg_dfa_free(acg_dfa* a) {
     Workspace& w = a->ws;
     if (w.stream) cudaStreamSynchronize(w.stream);
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
-    cudaFree(a->d_plens); cudaFree(a->d_depth8);
+    cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap);
     for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
     cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
+    cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);
     if (w.h_counter) cudaFreeHost(w.h_counter);
     if (w.h_keys) cudaFreeHost(w.h_keys);
     if (w.h_pids) cudaFreeHost(w.h_pids);

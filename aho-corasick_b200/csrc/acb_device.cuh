@@ -24,7 +24,7 @@ struct DfaDev {
   const uint32_t* match_offsets;  // CSR over match-state rows 2..
   const uint32_t* match_pids;
   const uint32_t* pattern_lens;
-  const uint8_t* depth8;          // trie depth per row (min(depth,255)); prefilter engine
+  const uint16_t* depth16;        // trie depth per row (prefilter engine's anchored walk)
   uint32_t stride2;
   uint32_t max_match_id;
   uint32_t start_unanchored_id;
@@ -62,6 +62,56 @@ struct SeqLaunch {
   uint64_t cap;
 };
 cudaError_t launch_seq_find(const DfaDev& dfa, const SeqLaunch& p, cudaStream_t s);
+
+// K3/K3b: position-parallel k-gram prefilter fused with the anchored DFA verify.
+// Plays the role of the reference's packed/Teddy prefilter (src/packed/teddy/
+// generic.rs:114-713 candidate + :820-870 verify): a cheap per-position
+// fingerprint test with no false negatives, then exact verification -- except
+// that the fingerprint is a hashed k-gram bitmap in shared memory (one LDS per
+// position) instead of PSHUFB nybble masks, and the verifier is the shipped DFA
+// walked from the candidate position while it stays on the trie path.
+struct PrefilterLaunch {
+  const uint8_t* hay;
+  uint64_t hay_len;             // bytes readable behind `hay`
+  uint64_t span_start, span_end;
+  const uint32_t* bitmap;       // global copy, staged into shared memory per CTA
+  uint32_t log_bits;            // bitmap size = 1 << log_bits bits
+  uint32_t k;                   // fingerprint length in bytes (1..4), <= min_pattern_len
+  uint32_t kmask;               // mask of the low k bytes
+  uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
+  uint32_t mult;                // multiplicative hash constant (1 => direct index)
+  uint32_t shift;               // hash >> shift
+  int brute;                    // 1: skip the bitmap, every position is a candidate
+  int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)
+  uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break
+  uint64_t region_lo, region_hi;  // 16-byte aligned filter region (absolute offsets)
+  uint64_t tile_bytes, n_tiles;
+  uint64_t* keys;
+  uint32_t* pids;
+  unsigned long long* counter;  // [0] tuples, [1] candidates
+  uint64_t cap;
+};
+cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s);
+
+// Non-overlapping iteration (FindIter, src/automaton.rs:857-936) over ordered candidate tuples.
+// mode 1 (leftmost): keys = (start_rel << 24 | len), sorted by start;
+// mode 0 (standard): keys = (end_rel << 24 | tie), sorted by (end, len desc, list order).
+// Writes flags[i] = 1 for the tuples the reference's iterator would yield.
+struct ChainLaunch {
+  const uint64_t* keys;
+  const uint32_t* pids;
+  const uint32_t* pattern_lens;
+  uint64_t n;
+  int mode;
+  uint64_t* scratch_end;   // [n] end offsets (leftmost) -> inclusive prefix max
+  uint8_t* flags;          // [n]
+};
+cudaError_t launch_chain_ends(const ChainLaunch& c, cudaStream_t s);
+cudaError_t launch_chain_select(const ChainLaunch& c, cudaStream_t s);
+cudaError_t scan_max_u64(void* d_temp, size_t& temp_bytes, uint64_t* data, uint64_t n, cudaStream_t s);
+cudaError_t select_flagged(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, const uint32_t* pids_in,
+                           const uint8_t* flags, uint64_t* keys_out, uint32_t* pids_out,
+                           unsigned long long* d_num_out, uint64_t n, cudaStream_t s);
 
 // key/pid pair sort (K4). temp storage is queried with d_temp == nullptr.
 cudaError_t sort_pairs(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,

@@ -16,11 +16,17 @@ AC = G.load("ac_vectors.json")
 PK = G.load("packed_vectors.json")
 
 
-def build(pats, match_kind=0, **kw):
+def build(pats, match_kind=0, engine=ab.Engine.Auto, **kw):
     b = ab.AhoCorasick.builder().match_kind(match_kind)
     for k, v in kw.items():
         getattr(b, k)(v)
-    return b.build(pats)
+    return b.build(pats).set_engine(engine)
+
+
+# Auto picks the prefilter engine whenever the automaton allows it; the second entry forces the
+# state-transition walk (overlapping) / the single-lane reference loop (find_iter).
+OVERLAPPING_ENGINES = [ab.Engine.Auto, ab.Engine.Walk]
+FIND_ITER_ENGINES = [ab.Engine.Auto, ab.Engine.Sequential]
 
 
 def tuples(ms):
@@ -40,20 +46,22 @@ def assert_np_equal(got, want, ctx=None):
 
 
 # ---- golden vectors through the device path (DFA rows of src/tests.rs:808-860, 937-994) -------
+@pytest.mark.parametrize("engine", FIND_ITER_ENGINES)
 @pytest.mark.parametrize("combo", list(G.COMBO_DFA) + ["default"])
 @pytest.mark.parametrize("coll,kind", G.NON_OVERLAPPING_COLLECTIONS)
-def test_golden_find_iter(coll, kind, combo):
+def test_golden_find_iter(coll, kind, combo, engine):
     kw = {k: v for k, v in G.COMBO[combo].items()}
     for t in G.collection(AC, coll):
-        ac = build(t["patterns"], kind, **kw)
+        ac = build(t["patterns"], kind, engine=engine, **kw)
         assert tuples(ac.find_iter(t["haystack"])) == t["matches"], (t["name"], combo)
 
 
+@pytest.mark.parametrize("engine", OVERLAPPING_ENGINES)
 @pytest.mark.parametrize("combo", list(G.COMBO_DFA) + ["default"])
-def test_golden_find_overlapping_iter(combo):
+def test_golden_find_overlapping_iter(combo, engine):
     kw = {k: v for k, v in G.COMBO[combo].items()}
     for t in G.collection(AC, "AC_STANDARD_OVERLAPPING"):
-        ac = build(t["patterns"], 0, **kw)
+        ac = build(t["patterns"], 0, engine=engine, **kw)
         assert tuples(ac.find_overlapping_iter(t["haystack"])) == t["matches"], (t["name"], combo)
 
 
@@ -132,29 +140,60 @@ def rand_case(rng, it, allow_empty):
     return pats, hay, span, alphabet == b"aAbBcC "
 
 
-def test_random_overlapping_vs_oracle():
+@pytest.mark.parametrize("engine", OVERLAPPING_ENGINES)
+def test_random_overlapping_vs_oracle(engine):
     rng = random.Random(0x6A11)
+    used = set()
     for it in range(120):
         pats, hay, span, ci = rand_case(rng, it, allow_empty=True)
         kw = {"ascii_case_insensitive": ci, "byte_classes": it % 7 != 0}
-        ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA, **kw)
+        ac = build(pats, 0, engine=engine, kind=ab.AhoCorasickKind.DFA, **kw)
         o = O.Oracle(pats, kind=O.KIND_DFA, **kw)
         assert_np_equal(ac.try_find_overlapping_iter_np(hay, span), o.find_overlapping_iter_np(hay, span),
                         (it, pats[:5], hay.size, span))
+        used.add(ac.last_stats()["engine"])
+    if engine == ab.Engine.Auto:
+        assert int(ab.Engine.Prefilter) in used and int(ab.Engine.Walk) in used  # empty patterns -> walk
+    else:
+        assert used == {int(ab.Engine.Walk)}
 
 
+@pytest.mark.parametrize("engine", FIND_ITER_ENGINES)
 @pytest.mark.parametrize("kind", [0, 1, 2])
-def test_random_find_iter_vs_oracle(kind):
+def test_random_find_iter_vs_oracle(kind, engine):
     rng = random.Random(0xF17E + kind)
+    used = set()
     for it in range(90):
         pats, hay, span, ci = rand_case(rng, it, allow_empty=True)
-        if hay.size > 70000:
+        if engine == ab.Engine.Sequential and hay.size > 70000:
             hay = hay[:70000].copy()
             span = None
         kw = {"ascii_case_insensitive": ci}
-        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA, **kw)
+        ac = build(pats, kind, engine=engine, kind=ab.AhoCorasickKind.DFA, **kw)
         o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA, prefilter=False, **kw)
         assert_np_equal(ac.try_find_iter_np(hay, span), o.find_iter_np(hay, span), (it, pats[:5], hay.size, span))
+        used.add(ac.last_stats()["engine"])
+    if engine == ab.Engine.Auto:
+        assert int(ab.Engine.Prefilter) in used
+
+
+def test_pathological_chains():
+    """ab/ba on ababab...: per-start candidates all overlap, so the whole haystack is one run of
+    the chain resolution -- must still be exact."""
+    hay = np.frombuffer(b"ab" * 20000 + b"xx" + b"ba" * 3000, dtype=np.uint8)
+    for kind in (0, 1, 2):
+        ac = build([b"ab", b"ba"], kind, kind=ab.AhoCorasickKind.DFA)
+        o = O.Oracle([b"ab", b"ba"], match_kind=kind, kind=O.KIND_DFA)
+        assert_np_equal(ac.try_find_iter_np(hay), o.find_iter_np(hay), kind)
+        assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    pats = [b"aaaa", b"aa", b"a", b"aaaaaaa"]
+    hay = np.frombuffer(b"a" * 30001, dtype=np.uint8)
+    for kind in (0, 1, 2):
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA)
+        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA)
+        assert_np_equal(ac.try_find_iter_np(hay), o.find_iter_np(hay), kind)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    assert_np_equal(ac.try_find_overlapping_iter_np(hay), O.Oracle(pats, kind=O.KIND_DFA).find_overlapping_iter_np(hay))
 
 
 def test_adopted_reference_tables():
@@ -169,10 +208,34 @@ def test_adopted_reference_tables():
 
 
 # ---- BASELINE config 2 at reduced size, full tuple stream; and a size-independent property ------
-def test_config2_reduced_full_tuple_parity():
+@pytest.mark.parametrize("cfg,kind,ci", [("cfg3", 1, True), ("cfg3", 2, True), ("cfg4", 1, False), ("cfg2", 0, False)])
+def test_config3_4_reduced_find_iter_parity(cfg, kind, ci):
+    """BASELINE configs 3 (case-insensitive LeftmostFirst non-overlapping) and 4 (50 literals,
+    the pattern set for which the reference activates Fat Teddy) at 32 MiB, full tuple parity."""
+    import torch
+    pats = W.make_patterns(W.CONFIGS[cfg]["n_patterns"], W.CONFIGS[cfg]["pattern_seed"])
+    t = torch.empty(32 << 20, dtype=torch.uint8)
+    W.torch_fill_config(cfg, t, pats, chunk=1 << 24)
+    hay = t.numpy()
+    ac = build(pats, kind, ascii_case_insensitive=ci, kind=ab.AhoCorasickKind.DFA)
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    want = o.find_iter_np(hay)
+    assert len(want) > 7000
+    assert_np_equal(ac.try_find_iter_np(hay), want)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    d = t.cuda()
+    got, ms = ac.find_iter_dev_np(d.data_ptr(), hay.size)
+    assert_np_equal(got, want)
+    if cfg == "cfg4":
+        assert ac.prefilter_kind() == 4 and o.prefilter_kind == O.PRE_PACKED  # packed (Teddy) in the reference
+        assert ac.packed_variant() == {"fat": True, "mask_len": 4}
+
+
+@pytest.mark.parametrize("engine", OVERLAPPING_ENGINES)
+def test_config2_reduced_full_tuple_parity(engine):
     import torch
     pats, hay, planted = W.make_config("cfg2", 64 << 20)
-    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    ac = build(pats, 0, engine=engine, kind=ab.AhoCorasickKind.DFA)
     o = O.Oracle(pats, kind=O.KIND_DFA)
     want = o.find_overlapping_iter_np(hay)
     assert len(want) >= planted
