@@ -80,6 +80,7 @@ struct PrefilterLaunch {
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // multiplicative hash constant (1 => direct index)
+  uint32_t mult2;               // second Bloom hash (0 => single probe)
   uint32_t shift;               // hash >> shift
   int brute;                    // 1: skip the bitmap, every position is a candidate
   int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)

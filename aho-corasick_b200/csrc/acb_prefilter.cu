@@ -21,8 +21,8 @@ namespace acb {
 namespace {
 
 constexpr int kPfThreads = 512;
-constexpr int kPfQcap = 4096;   // candidate queue entries per CTA
-constexpr int kPfMcap = 512;    // staged match tuples per CTA
+constexpr int kPfWarps = kPfThreads / 32;
+constexpr int kPfQw = 256;      // candidate queue entries per warp
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 v;
@@ -32,38 +32,28 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   return v;
 }
 
-struct PfShared {
-  unsigned long long m_base;
-  unsigned long long q_base;  // absolute offset that queue entries are relative to
-  unsigned int q_count;
-  unsigned int q_tile_mark;   // q_count at the start of the current tile
-  unsigned int m_count;
-  unsigned int overflow;
-  unsigned long long cand_total;
-  uint8_t cls[256];
-};
-
 struct Emitter {
   uint64_t* g_keys;
   uint32_t* g_pids;
   unsigned long long* g_counter;
   uint64_t cap;
-  uint64_t* s_keys;
-  uint32_t* s_pids;
-  unsigned int* s_count;
+  // Matches are sparse (about one per 4 KiB in the BASELINE workloads) while candidates are
+  // verified by whole warps, so lanes that found something aggregate their append into one
+  // atomic per warp step (warp-ballot + warp-aggregated atomic).
   __device__ __forceinline__ void emit(uint64_t key, uint32_t pid) {
-    const unsigned int slot = atomicAdd(s_count, 1u);
-    if (slot < (unsigned)kPfMcap) {
-      s_keys[slot] = key;
-      s_pids[slot] = pid;
-    } else {  // staging full: append directly
-      const unsigned long long g = atomicAdd(g_counter, 1ull);
-      if (g < cap) { g_keys[g] = key; g_pids[g] = pid; }
-    }
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(g_counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long g = base + __popc(m & ((1u << lane) - 1));
+    if (g < cap) { g_keys[g] = key; g_pids[g] = pid; }
   }
 };
 
-// Verify one candidate start offset `s` (K3b).
+// Verify one candidate start offset `s` (K3b): walk the shipped DFA from the start state while
+// the state stays on the trie path anchored at s (depth == bytes consumed).
 template <int MODE>
 __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch& p, const uint8_t* s_cls,
                                           uint64_t s, Emitter& em) {
@@ -100,135 +90,141 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
   if (MODE == 1 && best_len) em.emit(((s - p.span_start) << kTieBits) | best_len, best_pid);
 }
 
+// One CTA owns a contiguous chunk of the filter region; each warp streams 512 B of it per step
+// (16 B per lane, coalesced), probes the k-gram Bloom bitmap once per position (second probe only
+// for first-probe hits), appends survivors to its own shared-memory queue and verifies them 32 at
+// a time.  There is no block-wide barrier in the steady state: a warp that is waiting on the
+// dependent loads of a verification overlaps with the other warps' fingerprint work.
 template <int MODE>
 __global__ void __launch_bounds__(kPfThreads, 2)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* s_mkeys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* s_mpids = reinterpret_cast<uint32_t*>(s_mkeys + kPfMcap);
-  uint32_t* s_queue = s_mpids + kPfMcap;
-  uint32_t* s_bitmap = s_queue + kPfQcap;
-  __shared__ PfShared sh;
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw);          // [kPfWarps][kPfQw]
+  uint32_t* s_bitmap = s_queue + kPfWarps * kPfQw;
+  __shared__ uint8_t s_cls[256];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   const uint32_t bitmap_words = p.brute ? 0u : (1u << (p.log_bits - 5));
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
-  if (tid < 256) sh.cls[tid] = d.classes[tid];
-  if (tid == 0) {
-    sh.q_count = 0;
-    sh.m_count = 0;
-    sh.overflow = 0;
-    sh.q_base = p.region_lo;
-    sh.cand_total = 0;
-  }
+  if (tid < 256) s_cls[tid] = d.classes[tid];
   __syncthreads();
 
-  Emitter em{p.keys, p.pids, p.counter, p.cap, s_mkeys, s_mpids, &sh.m_count};
-
-  auto flush_matches = [&]() {
-    // called by all threads, after a __syncthreads
-    const unsigned int n = min(sh.m_count, (unsigned)kPfMcap);
-    if (n) {
-      if (tid == 0) sh.m_base = atomicAdd(p.counter, (unsigned long long)n);
-      __syncthreads();
-      const unsigned long long base = sh.m_base;
-      for (unsigned int i = tid; i < n; i += kPfThreads)
-        if (base + i < p.cap) { p.keys[base + i] = s_mkeys[i]; p.pids[base + i] = s_mpids[i]; }
-    }
-    __syncthreads();
-    if (tid == 0) sh.m_count = 0;
-    __syncthreads();
-  };
-
-  auto drain_queue = [&]() {
-    // all threads; queue is stable
-    const unsigned int qn = sh.q_count;
-    const unsigned long long qb = sh.q_base;
-    for (unsigned int i = tid; i < qn; i += kPfThreads) verify_at<MODE>(d, p, sh.cls, qb + s_queue[i], em);
-    __syncthreads();
-    if (tid == 0) { sh.cand_total += qn; sh.q_count = 0; }
-    __syncthreads();
-    flush_matches();
-  };
+  Emitter em{p.keys, p.pids, p.counter, p.cap};
+  unsigned long long cand_total = 0;
 
   // head / tail positions outside the aligned filter region are unconditional candidates
   if (blockIdx.x == 0) {
     const uint64_t head_n = p.region_lo - p.span_start;
-    const uint64_t tail_n = p.span_end >= p.region_hi ? p.span_end - p.region_hi + 1 : 0;  // incl. s == span_end (no-op)
+    const uint64_t tail_n = p.span_end > p.region_hi ? p.span_end - p.region_hi : 0;
     for (uint64_t i = tid; i < head_n + tail_n; i += kPfThreads) {
       const uint64_t s = i < head_n ? p.span_start + i : p.region_hi + (i - head_n);
-      if (s < p.span_end) verify_at<MODE>(d, p, sh.cls, s, em);
+      verify_at<MODE>(d, p, s_cls, s, em);
     }
-    __syncthreads();
-    flush_matches();
   }
 
-  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, shift = p.shift;
+  // this CTA's chunk, in units of 16-byte blocks
+  const uint64_t n_blocks16 = (p.region_hi - p.region_lo) >> 4;
+  const uint64_t per_cta = (n_blocks16 + gridDim.x - 1) / gridDim.x;
+  const uint64_t b0 = (uint64_t)blockIdx.x * per_cta;
+  const uint64_t b1 = min(b0 + per_cta, n_blocks16);
+  const uint64_t chunk_lo = p.region_lo + (b0 << 4);
+  const uint64_t chunk_hi = b0 < b1 ? p.region_lo + (b1 << 4) : chunk_lo;
 
-  for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const uint64_t t0 = p.region_lo + tile * p.tile_bytes;
-    const uint64_t t1 = min(t0 + p.tile_bytes, p.region_hi);
-    if (tid == 0) {
-      sh.q_tile_mark = sh.q_count;
-      if (sh.q_count == 0) sh.q_base = t0;
-    }
-    __syncthreads();
-    const uint64_t qb = sh.q_base;
+  if (p.brute) {
+    for (uint64_t s = chunk_lo + tid; s < chunk_hi; s += kPfThreads) verify_at<MODE>(d, p, s_cls, s, em);
+    if (tid == 0 && chunk_hi > chunk_lo) atomicAdd(p.counter + 1, (unsigned long long)(chunk_hi - chunk_lo));
+    return;
+  }
 
-    if (!p.brute) {
-      // ---- K3: fingerprint test, 16 positions per lane per step ----
-      for (uint64_t blk = t0 + (uint64_t)tid * 16; blk < t1 + (uint64_t)lane * 16; blk += (uint64_t)kPfThreads * 16) {
-        // the loop bound keeps whole warps together (lane 0's block decides), so the shuffle is safe
-        const bool active = blk < t1;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (active) v = ld_stream_u4(p.hay + blk);
-        uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (active && (lane == 31 || blk + 16 >= t1)) nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + 16));
-        const uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
-        uint32_t mask = 0;
-#pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          const uint32_t win = (o & 3) ? __funnelshift_r(w[o >> 2], w[(o >> 2) + 1], (o & 3) * 8) : w[o >> 2];
-          const uint32_t idx = (((win | fold) & kmask) * mult) >> shift;
-          const uint32_t word = s_bitmap[idx >> 5];
-          mask |= ((word >> (idx & 31)) & 1u) << o;
-        }
-        if (active && mask) {
-          const unsigned int cnt = __popc(mask);
-          const unsigned int slot = atomicAdd(&sh.q_count, cnt);
-          if (slot + cnt <= (unsigned)kPfQcap) {
-            unsigned int k = slot;
-            const uint32_t rel = (uint32_t)(blk - qb);
-            while (mask) {
-              const int o = __ffs(mask) - 1;
-              mask &= mask - 1;
-              s_queue[k++] = rel + o;
-            }
-          } else {
-            sh.overflow = 1;
-          }
-        }
+  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, mult2 = p.mult2, shift = p.shift;
+  uint32_t* q = s_queue + warp * kPfQw;
+  uint32_t qlen = 0;  // warp-uniform
+
+  auto drain = [&]() {
+    __syncwarp();
+    for (uint32_t i = lane; i < qlen; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q[i], em);
+    cand_total += qlen;
+    qlen = 0;
+    __syncwarp();
+  };
+
+  const uint64_t wstride = (uint64_t)kPfWarps * 512;
+  uint64_t wbase = chunk_lo + (uint64_t)warp * 512;
+  uint4 v_next = make_uint4(0, 0, 0, 0);
+  if (wbase + (uint64_t)lane * 16 < chunk_hi) v_next = ld_stream_u4(p.hay + wbase + (uint64_t)lane * 16);
+  for (; wbase < chunk_hi; wbase += wstride) {
+    const uint64_t blk = wbase + (uint64_t)lane * 16;
+    const bool active = blk < chunk_hi;
+    const uint4 v = v_next;
+    // software prefetch of the next step's 16 bytes: keeps two loads in flight per lane
+    if (blk + wstride < chunk_hi) v_next = ld_stream_u4(p.hay + blk + wstride);
+    uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+    if (active && (lane == 31 || blk + 16 >= chunk_hi)) nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + 16));
+    const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = nx;
+    uint32_t mask = 0;
+#define ACB_PROBE(o, lo, hi)                                                              \
+  do {                                                                                    \
+    const uint32_t win = ((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo);       \
+    const uint32_t idx = (((win | fold) & kmask) * mult) >> shift;                        \
+    const uint32_t word = s_bitmap[idx >> 5];                                             \
+    mask |= ((word >> (idx & 31)) & 1u) << (o);                                           \
+  } while (0)
+    ACB_PROBE(0, w0, w1); ACB_PROBE(1, w0, w1); ACB_PROBE(2, w0, w1); ACB_PROBE(3, w0, w1);
+    ACB_PROBE(4, w1, w2); ACB_PROBE(5, w1, w2); ACB_PROBE(6, w1, w2); ACB_PROBE(7, w1, w2);
+    ACB_PROBE(8, w2, w3); ACB_PROBE(9, w2, w3); ACB_PROBE(10, w2, w3); ACB_PROBE(11, w2, w3);
+    ACB_PROBE(12, w3, w4); ACB_PROBE(13, w3, w4); ACB_PROBE(14, w3, w4); ACB_PROBE(15, w3, w4);
+#undef ACB_PROBE
+    if (!active) mask = 0;
+    if (mask && mult2) {
+      // second Bloom probe, only for positions that passed the first
+      uint32_t m = mask;
+      while (m) {
+        const int o = __ffs(m) - 1;
+        m &= m - 1;
+        const int wi = o >> 2;
+        const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+        const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : w4;
+        const uint32_t win = __funnelshift_r(lo, hi, (o & 3) * 8);
+        const uint32_t idx = (((win | fold) & kmask) * mult2) >> shift;
+        if (!((s_bitmap[idx >> 5] >> (idx & 31)) & 1u)) mask &= ~(1u << o);
       }
-      __syncthreads();
     }
-
-    if (p.brute || sh.overflow) {
-      // fingerprints not selective here: drop this tile's queue entries and verify every position
-      __syncthreads();
-      if (tid == 0) { sh.q_count = sh.q_tile_mark; sh.overflow = 0; }
-      __syncthreads();
-      for (uint64_t s = t0 + tid; s < t1; s += kPfThreads) verify_at<MODE>(d, p, sh.cls, s, em);
-      __syncthreads();
-      if (tid == 0) sh.cand_total += (t1 - t0);
-      __syncthreads();
-      flush_matches();
+    const uint32_t cnt = __popc(mask);
+    const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+    if (total == 0) continue;
+    if (qlen + total > (uint32_t)kPfQw) drain();
+    if (total > (uint32_t)kPfQw) {
+      // fingerprints not selective here: verify this step's hits in place
+      while (mask) {
+        const int o = __ffs(mask) - 1;
+        mask &= mask - 1;
+        verify_at<MODE>(d, p, s_cls, blk + o, em);
+      }
+      cand_total += total;
+      __syncwarp();
+      continue;
     }
-
-    const bool last = tile + gridDim.x >= p.n_tiles;
-    if (sh.q_count > (unsigned)(kPfQcap / 2) || last || (t1 - qb) > 0xF0000000ull) drain_queue();
+    // exclusive prefix sum of cnt across the warp
+    uint32_t pre = cnt;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, pre, dlt);
+      if (lane >= dlt) pre += t;
+    }
+    uint32_t slot = qlen + pre - cnt;
+    const uint32_t rel = (uint32_t)(blk - chunk_lo);
+    while (mask) {
+      const int o = __ffs(mask) - 1;
+      mask &= mask - 1;
+      q[slot++] = rel + o;
+    }
+    qlen += total;
+    if (qlen >= 64) drain();
   }
-  if (tid == 0 && sh.cand_total) atomicAdd(p.counter + 1, sh.cand_total);
+  if (qlen) drain();
+  if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
 }
 
 // ---- chain resolution ---------------------------------------------------------
@@ -280,7 +276,7 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfMcap) * 12 + size_t(kPfQcap) * 4 + bitmap_bytes;
+  const size_t smem = size_t(kPfWarps) * kPfQw * 4 + bitmap_bytes;
   auto kern = p.mode == 0 ? prefilter_kernel<0> : prefilter_kernel<1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -289,7 +285,8 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sm_count * per_sm;
-  if (grid > p.n_tiles) grid = p.n_tiles ? p.n_tiles : 1;
+  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + 8191) / 8192;  // one CTA step = 16 warps x 512 B
+  if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
   kern<<<(unsigned)grid, kPfThreads, smem, s>>>(dfa, p);
   return cudaGetLastError();
 }

@@ -125,6 +125,8 @@ def main():
     ap.add_argument("--hay-gib", type=float, default=4.0, help="haystack GiB per GPU (weak scaling)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 walk, 2 prefilter")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -147,7 +149,7 @@ def main():
     n_bytes -= n_bytes % 4096
     goff = rank * n_bytes  # weak scaling: every rank owns its own slice of the global stream
     pats = W.make_patterns(5000, W.CONFIGS["cfg2"]["pattern_seed"])
-    ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats)
+    ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats).set_engine(args.engine)
     d_hay = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
     planted = W.torch_fill_config("cfg2", d_hay, pats, global_offset=goff)
     torch.cuda.synchronize()
@@ -195,15 +197,16 @@ def main():
     h_hay = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
     h_hay.copy_(d_hay[:e2e_bytes])
     h_np = h_hay.numpy()
-    for _ in range(2):
+    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
+    r = []
+    for _ in range(0 if args.no_e2e else 2):
         r = ac.try_find_overlapping_iter_np(h_np)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 5))
     for _ in range(e2e_steps):
         r = ac.try_find_overlapping_iter_np(h_np)
     barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = (time.perf_counter() - t0) / max(e2e_steps, 1)
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -228,6 +231,8 @@ def main():
                    "engine": int(stats["engine"]), "table_bytes": ac.memory_usage(),
                    "states": ac.state_len()},
         "matches": total_matches, "matches_per_s": total_matches * args.steps / dev_s,
+        "candidates": int(stats["candidates"]), "scan_ms": sum(scan_ms) / len(scan_ms),
+        "order_ms": float(stats["order_ms"]),
         "wall_ms_per_step": wall / args.steps * 1e3,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": which,
