@@ -60,7 +60,7 @@ struct Workspace {
 // works for DFAs adopted through acg_dfa_create).
 struct PrefilterPlan {
   bool supported = false;
-  uint32_t k = 0, kmask = 0, fold = 0, mult = 1, mult2 = 0, shift = 0, log_bits = 0;
+  uint32_t k = 0, kmask = 0, fold = 0, mult = 1, shift = 0, log_bits = 0;
   bool brute = false;
   uint32_t dup_shift = 0;
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
@@ -96,6 +96,16 @@ int bits_for(uint64_t v) {
   int b = 0;
   while (v) { ++b; v >>= 1; }
   return b;
+}
+
+// second Bloom hash; must match bloom_hash2() in acb_prefilter.cu
+uint32_t bloom_hash2(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
 
 void derive_metadata(acg_dfa* a) {
@@ -179,32 +189,39 @@ void derive_metadata(acg_dfa* a) {
     folded.erase(std::unique(folded.begin(), folded.end()), folded.end());
     const bool use_fold = folded.size() * 3 < raw.size() * 2;
     const std::vector<uint32_t>& set = use_fold ? folded : raw;
-    uint32_t log_bits, mult, mult2, shift;
-    if (k <= 2) { log_bits = 8 * k; mult = 1; mult2 = 0; shift = 0; }   // exact direct index
-    else {
-      // Bloom bitmap with two multiplicative hashes; the second is probed only on a first hit
-      log_bits = uint32_t(std::min(19, std::max(13, bits_for(uint64_t(set.size()) * 128 - 1))));
-      mult = 0x9E3779B1u;
-      mult2 = 0x85EBCA77u;
-      shift = 32 - log_bits;
-    }
+    // Bloom bitmap with two hashes (a single multiply for the per-position probe, a full mix
+    // for the second probe that only first-probe hits pay for).  Bit position of a hash h: word
+    // from the top (log_bits-5) bits, bit inside the word from the low 5 bits.
+    const uint32_t log_bits = uint32_t(std::min(19, std::max(13, bits_for(uint64_t(set.size()) * 128 - 1))));
+    const uint32_t mult = 0x9E3779B1u;
+    const uint32_t shift = 35 - log_bits;
     const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
     std::vector<uint32_t> bm(size_t(1) << (log_bits - 5), 0u);
     uint64_t set_bits = 0;
-    auto set_bit = [&](uint32_t idx) {
-      uint32_t& wd = bm[idx >> 5];
-      if (!(wd >> (idx & 31) & 1)) { wd |= 1u << (idx & 31); ++set_bits; }
+    auto set_hash = [&](uint32_t hsh) {
+      uint32_t& wd = bm[hsh >> (37 - log_bits)];
+      if (!(wd >> (hsh & 31) & 1)) { wd |= 1u << (hsh & 31); ++set_bits; }
     };
     for (uint32_t g : set) {
-      set_bit(uint32_t((g & kmask) * mult) >> shift);
-      if (mult2) set_bit(uint32_t((g & kmask) * mult2) >> shift);
+      set_hash((g & kmask) * mult);
+      set_hash(bloom_hash2(g & kmask));
     }
     double fill = double(set_bits) / double(uint64_t(1) << log_bits);
-    if (mult2) fill = fill * fill;  // both probes must hit
+    fill = fill * fill;  // both probes must hit
+    // expected candidate rate on text drawn from the patterns' own alphabet: Bloom false positives
+    // plus genuine k-gram prefix hits (n_grams / prod_j |bytes seen at position j|)
+    double space = 1.0;
+    for (uint32_t j = 0; j < k; ++j) {
+      bool seen[256] = {false};
+      unsigned distinct = 0;
+      for (uint32_t g : set) { const uint32_t b = (g >> (8 * j)) & 0xFF; if (!seen[b]) { seen[b] = true; ++distinct; } }
+      space *= double(std::max(distinct, 1u));
+    }
+    fill += std::min(1.0, double(set.size()) / space);
     if (fill <= best_fill) {
       best_fill = fill;
       pf.k = k; pf.kmask = kmask; pf.fold = use_fold ? (0x20202020u & kmask) : 0u;
-      pf.mult = mult; pf.mult2 = mult2; pf.shift = shift; pf.log_bits = log_bits;
+      pf.mult = mult; pf.shift = shift; pf.log_bits = log_bits;
       pf.fill = fill; pf.n_grams = set.size();
       pf.bitmap.swap(bm);
     }
@@ -446,7 +463,6 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t hay_len, uint
     p.kmask = pf.kmask;
     p.fold = pf.fold;
     p.mult = pf.mult;
-    p.mult2 = pf.mult2;
     p.shift = pf.shift;
     p.brute = pf.brute ? 1 : 0;
     p.mode = mode;

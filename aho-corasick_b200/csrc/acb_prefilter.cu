@@ -22,7 +22,8 @@ namespace {
 
 constexpr int kPfThreads = 512;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfQw = 256;      // candidate queue entries per warp
+constexpr int kPfQw = 256;      // first-probe hit queue entries per warp
+constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 v;
@@ -30,6 +31,17 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
   return v;
+}
+
+// Second Bloom hash: a full avalanche mix (evaluated only for first-probe hits, so its cost is
+// irrelevant); the first probe is a single multiply.  Must match bloom_hash2() in acb_api.cu.
+__device__ __forceinline__ uint32_t bloom_hash2(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
 }
 
 struct Emitter {
@@ -90,17 +102,29 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
   if (MODE == 1 && best_len) em.emit(((s - p.span_start) << kTieBits) | best_len, best_pid);
 }
 
+// Bit position of a 32-bit hash in the Bloom bitmap: the word comes from the top (log_bits-5)
+// bits, the bit inside the word from the low 5 bits (a rotate by the raw hash selects it without
+// an extra mask).  Must match bloom_bit() in acb_api.cu.
+__device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h, uint32_t wshift) {
+  const uint32_t woff = (h >> wshift) & ~3u;  // byte offset of the word
+  const uint32_t word = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_bitmap) + woff);
+  return (__funnelshift_r(word, word, h) & 1u) != 0;
+}
+
 // One CTA owns a contiguous chunk of the filter region; each warp streams 512 B of it per step
-// (16 B per lane, coalesced), probes the k-gram Bloom bitmap once per position (second probe only
-// for first-probe hits), appends survivors to its own shared-memory queue and verifies them 32 at
-// a time.  There is no block-wide barrier in the steady state: a warp that is waiting on the
-// dependent loads of a verification overlaps with the other warps' fingerprint work.
-template <int MODE>
+// (16 B per lane, coalesced) and probes the k-gram Bloom bitmap once per position.  First-probe
+// hits are appended to the warp's shared-memory queue; when the queue fills, the warp applies the
+// second Bloom probe to 32 queued fingerprints at a time and compacts the survivors into a second
+// queue that is verified 32 at a time, so the dependent DFA walks always run with full warps.
+// There is no block-wide barrier in the steady state: a warp waiting on a verification overlaps
+// with the other warps' fingerprint work.
+template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(kPfThreads, 2)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw);          // [kPfWarps][kPfQw]
-  uint32_t* s_bitmap = s_queue + kPfWarps * kPfQw;
+  uint2* s_queue = reinterpret_cast<uint2*>(smem_raw);                      // [kPfWarps][kPfQw] (rel, gram)
+  uint32_t* s_queue2 = reinterpret_cast<uint32_t*>(s_queue + kPfWarps * kPfQw);  // [kPfWarps][kPfQ2]
+  uint32_t* s_bitmap = s_queue2 + kPfWarps * kPfQ2;
   __shared__ uint8_t s_cls[256];
 
   const int tid = threadIdx.x;
@@ -138,14 +162,36 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     return;
   }
 
-  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, mult2 = p.mult2, shift = p.shift;
-  uint32_t* q = s_queue + warp * kPfQw;
-  uint32_t qlen = 0;  // warp-uniform
+  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, wshift = p.shift;
+  uint2* q = s_queue + warp * kPfQw;
+  uint32_t* q2 = s_queue2 + warp * kPfQ2;
+  uint32_t qlen = 0, q2len = 0;  // warp-uniform
 
-  auto drain = [&]() {
+  auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
     __syncwarp();
-    for (uint32_t i = lane; i < qlen; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q[i], em);
-    cand_total += qlen;
+    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2[i], em);
+    cand_total += q2len;
+    q2len = 0;
+    __syncwarp();
+  };
+  auto drain = [&]() {  // second Bloom probe over the queued first-probe hits, 32 at a time
+    __syncwarp();
+    for (uint32_t base = 0; base < qlen; base += 32) {
+      const uint32_t i = base + lane;
+      bool pass = false;
+      uint32_t rel = 0;
+      if (i < qlen) {
+        const uint2 e = q[i];
+        rel = e.x;
+        pass = bloom_test(s_bitmap, bloom_hash2(e.y), wshift);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if (bal) {
+        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = rel;
+        q2len += __popc(bal);
+        if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+      }
+    }
     qlen = 0;
     __syncwarp();
   };
@@ -163,34 +209,22 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
     if (active && (lane == 31 || blk + 16 >= chunk_hi)) nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + 16));
     const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = nx;
-    uint32_t mask = 0;
-#define ACB_PROBE(o, lo, hi)                                                              \
-  do {                                                                                    \
-    const uint32_t win = ((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo);       \
-    const uint32_t idx = (((win | fold) & kmask) * mult) >> shift;                        \
-    const uint32_t word = s_bitmap[idx >> 5];                                             \
-    mask |= ((word >> (idx & 31)) & 1u) << (o);                                           \
+    uint32_t mask = 0;  // after 16 probes: bit 16+o <=> position blk+o passed the first probe
+#define ACB_GRAM(o, lo, hi) (MASKED ? (((((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)) | fold) & kmask) \
+                                    : (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)))
+#define ACB_PROBE(o, lo, hi)                                                                  \
+  do {                                                                                        \
+    const uint32_t h = ACB_GRAM(o, lo, hi) * mult;                                            \
+    const uint32_t woff = (h >> wshift) & ~3u;                                                \
+    const uint32_t word = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_bitmap) + woff); \
+    mask = __funnelshift_r(mask, __funnelshift_r(word, word, h), 1);                          \
   } while (0)
     ACB_PROBE(0, w0, w1); ACB_PROBE(1, w0, w1); ACB_PROBE(2, w0, w1); ACB_PROBE(3, w0, w1);
     ACB_PROBE(4, w1, w2); ACB_PROBE(5, w1, w2); ACB_PROBE(6, w1, w2); ACB_PROBE(7, w1, w2);
     ACB_PROBE(8, w2, w3); ACB_PROBE(9, w2, w3); ACB_PROBE(10, w2, w3); ACB_PROBE(11, w2, w3);
     ACB_PROBE(12, w3, w4); ACB_PROBE(13, w3, w4); ACB_PROBE(14, w3, w4); ACB_PROBE(15, w3, w4);
 #undef ACB_PROBE
-    if (!active) mask = 0;
-    if (mask && mult2) {
-      // second Bloom probe, only for positions that passed the first
-      uint32_t m = mask;
-      while (m) {
-        const int o = __ffs(m) - 1;
-        m &= m - 1;
-        const int wi = o >> 2;
-        const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-        const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : w4;
-        const uint32_t win = __funnelshift_r(lo, hi, (o & 3) * 8);
-        const uint32_t idx = (((win | fold) & kmask) * mult2) >> shift;
-        if (!((s_bitmap[idx >> 5] >> (idx & 31)) & 1u)) mask &= ~(1u << o);
-      }
-    }
+    mask = active ? (mask >> 16) : 0u;
     const uint32_t cnt = __popc(mask);
     const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
     if (total == 0) continue;
@@ -218,12 +252,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     while (mask) {
       const int o = __ffs(mask) - 1;
       mask &= mask - 1;
-      q[slot++] = rel + o;
+      const int wi = o >> 2;
+      const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+      const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : w4;
+      uint32_t gram = __funnelshift_r(lo, hi, (o & 3) * 8);
+      if (MASKED) gram = (gram | fold) & kmask;
+      q[slot++] = make_uint2(rel + o, gram);
     }
     qlen += total;
-    if (qlen >= 64) drain();
   }
+#undef ACB_GRAM
   if (qlen) drain();
+  if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
 }
 
@@ -276,8 +316,10 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfWarps) * kPfQw * 4 + bitmap_bytes;
-  auto kern = p.mode == 0 ? prefilter_kernel<0> : prefilter_kernel<1>;
+  const size_t smem = size_t(kPfWarps) * (kPfQw * 8 + kPfQ2 * 4) + bitmap_bytes;
+  const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
+  auto kern = p.mode == 0 ? (masked ? prefilter_kernel<0, true> : prefilter_kernel<0, false>)
+                          : (masked ? prefilter_kernel<1, true> : prefilter_kernel<1, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
