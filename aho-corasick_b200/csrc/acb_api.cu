@@ -190,17 +190,18 @@ void derive_metadata(acg_dfa* a) {
     const bool use_fold = folded.size() * 3 < raw.size() * 2;
     const std::vector<uint32_t>& set = use_fold ? folded : raw;
     // Bloom bitmap with two hashes (a single multiply for the per-position probe, a full mix
-    // for the second probe that only first-probe hits pay for).  Bit position of a hash h: word
-    // from the top (log_bits-5) bits, bit inside the word from the low 5 bits.
+    // for the second probe that only first-probe hits pay for).  Bit position of a hash h: byte
+    // from the top (log_bits-3) bits, bit inside the byte from the low 3 bits (little-endian words).
     const uint32_t log_bits = uint32_t(std::min(19, std::max(13, bits_for(uint64_t(set.size()) * 128 - 1))));
     const uint32_t mult = 0x9E3779B1u;
     const uint32_t shift = 35 - log_bits;
     const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
     std::vector<uint32_t> bm(size_t(1) << (log_bits - 5), 0u);
     uint64_t set_bits = 0;
-    auto set_hash = [&](uint32_t hsh) {
-      uint32_t& wd = bm[hsh >> (37 - log_bits)];
-      if (!(wd >> (hsh & 31) & 1)) { wd |= 1u << (hsh & 31); ++set_bits; }
+    auto set_hash = [&](uint32_t hsh) {  // byte (hsh >> shift), bit (hsh & 7); see bloom_test()
+      const uint32_t byte = hsh >> shift, bit = byte * 8 + (hsh & 7);
+      uint32_t& wd = bm[bit >> 5];
+      if (!(wd >> (bit & 31) & 1)) { wd |= 1u << (bit & 31); ++set_bits; }
     };
     for (uint32_t g : set) {
       set_hash((g & kmask) * mult);

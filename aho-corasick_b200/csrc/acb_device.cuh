@@ -80,7 +80,7 @@ struct PrefilterLaunch {
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult
-  uint32_t shift;               // (hash >> shift) & ~3 = byte offset of the bitmap word (= 35 - log_bits)
+  uint32_t shift;               // hash >> shift = byte offset into the bitmap (= 35 - log_bits)
   int brute;                    // 1: skip the bitmap, every position is a candidate
   int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)
   uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break

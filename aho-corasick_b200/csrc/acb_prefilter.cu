@@ -102,13 +102,16 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
   if (MODE == 1 && best_len) em.emit(((s - p.span_start) << kTieBits) | best_len, best_pid);
 }
 
-// Bit position of a 32-bit hash in the Bloom bitmap: the word comes from the top (log_bits-5)
-// bits, the bit inside the word from the low 5 bits (a rotate by the raw hash selects it without
-// an extra mask).  Must match bloom_bit() in acb_api.cu.
-__device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h, uint32_t wshift) {
-  const uint32_t woff = (h >> wshift) & ~3u;  // byte offset of the word
-  const uint32_t word = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_bitmap) + woff);
-  return (__funnelshift_r(word, word, h) & 1u) != 0;
+// Bit position of a 32-bit hash in the Bloom bitmap: the byte comes from the top (log_bits-3)
+// bits, the bit inside the byte from the low 3 bits.  The probe loads that byte, replicates it
+// into all four byte lanes with a multiply (FMA pipe) and rotates by the raw hash (the hardware
+// uses the shift amount mod 32), which puts bit (h & 7) of the byte at bit 0 -- one shift, one
+// byte load, one multiply and one rotate per position, no masking.  Must match set_hash() in
+// acb_api.cu.
+__device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h, uint32_t bshift) {
+  const uint32_t byte = reinterpret_cast<const uint8_t*>(s_bitmap)[h >> bshift];
+  const uint32_t rep = byte * 0x01010101u;  // the rotate below then finds bit (h & 7) at bit 0
+  return (__funnelshift_r(rep, rep, h) & 1u) != 0;
 }
 
 // One CTA owns a contiguous chunk of the filter region; each warp streams 512 B of it per step
@@ -162,7 +165,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     return;
   }
 
-  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, wshift = p.shift;
+  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
+  const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   uint2* q = s_queue + warp * kPfQw;
   uint32_t* q2 = s_queue2 + warp * kPfQ2;
   uint32_t qlen = 0, q2len = 0;  // warp-uniform
@@ -183,7 +187,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       if (i < qlen) {
         const uint2 e = q[i];
         rel = e.x;
-        pass = bloom_test(s_bitmap, bloom_hash2(e.y), wshift);
+        pass = bloom_test(s_bitmap, bloom_hash2(e.y), bshift);
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, pass);
       if (bal) {
@@ -196,35 +200,43 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     __syncwarp();
   };
 
-  const uint64_t wstride = (uint64_t)kPfWarps * 512;
-  uint64_t wbase = chunk_lo + (uint64_t)warp * 512;
-  uint4 v_next = make_uint4(0, 0, 0, 0);
-  if (wbase + (uint64_t)lane * 16 < chunk_hi) v_next = ld_stream_u4(p.hay + wbase + (uint64_t)lane * 16);
+  // each lane owns 32 consecutive positions (two 16-byte loads) per step: 1 KiB per warp step
+  const uint64_t wstride = (uint64_t)kPfWarps * 1024;
+  uint64_t wbase = chunk_lo + (uint64_t)warp * 1024;
+  uint4 va_next = make_uint4(0, 0, 0, 0), vb_next = make_uint4(0, 0, 0, 0);
+  {
+    const uint64_t blk = wbase + (uint64_t)lane * 32;
+    if (blk < chunk_hi) va_next = ld_stream_u4(p.hay + blk);
+    if (blk + 16 < chunk_hi) vb_next = ld_stream_u4(p.hay + blk + 16);
+  }
   for (; wbase < chunk_hi; wbase += wstride) {
-    const uint64_t blk = wbase + (uint64_t)lane * 16;
-    const bool active = blk < chunk_hi;
-    const uint4 v = v_next;
-    // software prefetch of the next step's 16 bytes: keeps two loads in flight per lane
-    if (blk + wstride < chunk_hi) v_next = ld_stream_u4(p.hay + blk + wstride);
-    uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);
-    if (active && (lane == 31 || blk + 16 >= chunk_hi)) nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + 16));
-    const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w, w4 = nx;
-    uint32_t mask = 0;  // after 16 probes: bit 16+o <=> position blk+o passed the first probe
+    const uint64_t blk = wbase + (uint64_t)lane * 32;
+    // number of valid positions of this lane in this step (chunk sizes are multiples of 16)
+    const uint32_t nvalid = blk >= chunk_hi ? 0u : (blk + 16 >= chunk_hi ? 16u : 32u);
+    const uint4 va = va_next, vb = vb_next;
+    // software prefetch of the next step: keeps four 16-byte loads in flight per lane
+    if (blk + wstride < chunk_hi) va_next = ld_stream_u4(p.hay + blk + wstride);
+    if (blk + wstride + 16 < chunk_hi) vb_next = ld_stream_u4(p.hay + blk + wstride + 16);
+    uint32_t nx = __shfl_down_sync(0xffffffffu, va.x, 1);
+    if (nvalid && (lane == 31 || blk + 32 >= chunk_hi))
+      nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + nvalid));
+    const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w;
+    const uint32_t w4 = nvalid == 16 ? nx : vb.x, w5 = vb.y, w6 = vb.z, w7 = vb.w, w8 = nx;
+    uint32_t mask = 0;  // after 32 probes: bit o <=> position blk+o passed the first probe
 #define ACB_GRAM(o, lo, hi) (MASKED ? (((((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)) | fold) & kmask) \
                                     : (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)))
 #define ACB_PROBE(o, lo, hi)                                                                  \
   do {                                                                                        \
     const uint32_t h = ACB_GRAM(o, lo, hi) * mult;                                            \
-    const uint32_t woff = (h >> wshift) & ~3u;                                                \
-    const uint32_t word = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_bitmap) + woff); \
-    mask = __funnelshift_r(mask, __funnelshift_r(word, word, h), 1);                          \
+    const uint32_t rep = (uint32_t)s_bytes[h >> bshift] * 0x01010101u;                        \
+    mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, h), 1);                            \
   } while (0)
-    ACB_PROBE(0, w0, w1); ACB_PROBE(1, w0, w1); ACB_PROBE(2, w0, w1); ACB_PROBE(3, w0, w1);
-    ACB_PROBE(4, w1, w2); ACB_PROBE(5, w1, w2); ACB_PROBE(6, w1, w2); ACB_PROBE(7, w1, w2);
-    ACB_PROBE(8, w2, w3); ACB_PROBE(9, w2, w3); ACB_PROBE(10, w2, w3); ACB_PROBE(11, w2, w3);
-    ACB_PROBE(12, w3, w4); ACB_PROBE(13, w3, w4); ACB_PROBE(14, w3, w4); ACB_PROBE(15, w3, w4);
+#define ACB_PROBE4(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 1, lo, hi); ACB_PROBE(o + 2, lo, hi); ACB_PROBE(o + 3, lo, hi)
+    ACB_PROBE4(0, w0, w1); ACB_PROBE4(4, w1, w2); ACB_PROBE4(8, w2, w3); ACB_PROBE4(12, w3, w4);
+    ACB_PROBE4(16, w4, w5); ACB_PROBE4(20, w5, w6); ACB_PROBE4(24, w6, w7); ACB_PROBE4(28, w7, w8);
+#undef ACB_PROBE4
 #undef ACB_PROBE
-    mask = active ? (mask >> 16) : 0u;
+    mask = nvalid == 32 ? mask : (nvalid == 16 ? (mask & 0xFFFFu) : 0u);
     const uint32_t cnt = __popc(mask);
     const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
     if (total == 0) continue;
@@ -253,8 +265,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       const int o = __ffs(mask) - 1;
       mask &= mask - 1;
       const int wi = o >> 2;
-      const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-      const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : w4;
+      const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : wi == 3 ? w3 : wi == 4 ? w4 : wi == 5 ? w5 : wi == 6 ? w6 : w7;
+      const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : wi == 3 ? w4 : wi == 4 ? w5 : wi == 5 ? w6 : wi == 6 ? w7 : w8;
       uint32_t gram = __funnelshift_r(lo, hi, (o & 3) * 8);
       if (MASKED) gram = (gram | fold) & kmask;
       q[slot++] = make_uint2(rel + o, gram);
@@ -327,7 +339,7 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sm_count * per_sm;
-  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + 8191) / 8192;  // one CTA step = 16 warps x 512 B
+  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + 16383) / 16384;  // one CTA step = 16 warps x 1 KiB
   if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
   kern<<<(unsigned)grid, kPfThreads, smem, s>>>(dfa, p);
   return cudaGetLastError();
