@@ -22,7 +22,7 @@ namespace {
 
 constexpr int kPfThreads = 512;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfQw = 256;      // first-probe hit queue entries per warp
+constexpr int kPfQw = 512;      // first-probe hit queue entries per warp
 constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
@@ -125,8 +125,8 @@ template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(kPfThreads, 2)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint2* s_queue = reinterpret_cast<uint2*>(smem_raw);                      // [kPfWarps][kPfQw] (rel, gram)
-  uint32_t* s_queue2 = reinterpret_cast<uint32_t*>(s_queue + kPfWarps * kPfQw);  // [kPfWarps][kPfQ2]
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw);          // [kPfWarps][kPfQw] offsets
+  uint32_t* s_queue2 = s_queue + kPfWarps * kPfQw;                    // [kPfWarps][kPfQ2]
   uint32_t* s_bitmap = s_queue2 + kPfWarps * kPfQ2;
   __shared__ uint8_t s_cls[256];
 
@@ -167,7 +167,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 
   const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
-  uint2* q = s_queue + warp * kPfQw;
+  uint32_t* q = s_queue + warp * kPfQw;
   uint32_t* q2 = s_queue2 + warp * kPfQ2;
   uint32_t qlen = 0, q2len = 0;  // warp-uniform
 
@@ -185,9 +185,15 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       bool pass = false;
       uint32_t rel = 0;
       if (i < qlen) {
-        const uint2 e = q[i];
-        rel = e.x;
-        pass = bloom_test(s_bitmap, bloom_hash2(e.y), bshift);
+        rel = q[i];
+        // re-read the fingerprint (L2 hit: the bytes were streamed a moment ago); cheaper than
+        // carrying it through the queue from the divergent append loop
+        const uint8_t* a = p.hay + chunk_lo + rel;
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
+        uint32_t gram = __funnelshift_r(__ldg(aw), __ldg(aw + 1), sh);
+        if (MASKED) gram = (gram | fold) & kmask;
+        pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, pass);
       if (bal) {
@@ -264,12 +270,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     while (mask) {
       const int o = __ffs(mask) - 1;
       mask &= mask - 1;
-      const int wi = o >> 2;
-      const uint32_t lo = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : wi == 3 ? w3 : wi == 4 ? w4 : wi == 5 ? w5 : wi == 6 ? w6 : w7;
-      const uint32_t hi = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : wi == 3 ? w4 : wi == 4 ? w5 : wi == 5 ? w6 : wi == 6 ? w7 : w8;
-      uint32_t gram = __funnelshift_r(lo, hi, (o & 3) * 8);
-      if (MASKED) gram = (gram | fold) & kmask;
-      q[slot++] = make_uint2(rel + o, gram);
+      q[slot++] = rel + o;
     }
     qlen += total;
   }
@@ -328,7 +329,7 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfWarps) * (kPfQw * 8 + kPfQ2 * 4) + bitmap_bytes;
+  const size_t smem = size_t(kPfWarps) * (kPfQw * 4 + kPfQ2 * 4) + bitmap_bytes;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   auto kern = p.mode == 0 ? (masked ? prefilter_kernel<0, true> : prefilter_kernel<0, false>)
                           : (masked ? prefilter_kernel<1, true> : prefilter_kernel<1, false>);
