@@ -22,7 +22,7 @@ namespace {
 
 constexpr int kPfThreads = 512;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfQw = 512;      // first-probe hit queue entries per warp
+constexpr int kPfSlots = 256;   // first-probe hits of one warp step handled by the compacted second probe
 constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
@@ -115,20 +115,22 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 }
 
 // One CTA owns a contiguous chunk of the filter region; each warp streams 512 B of it per step
-// (16 B per lane, coalesced) and probes the k-gram Bloom bitmap once per position.  First-probe
-// hits are appended to the warp's shared-memory queue; when the queue fills, the warp applies the
-// second Bloom probe to 32 queued fingerprints at a time and compacts the survivors into a second
-// queue that is verified 32 at a time, so the dependent DFA walks always run with full warps.
-// There is no block-wide barrier in the steady state: a warp waiting on a verification overlaps
-// with the other warps' fingerprint work.
+// (32 B per lane, coalesced) and probes the k-gram Bloom bitmap once per position.  The hits of
+// a step are compacted (lane t takes hit t), re-probed with the second Bloom hash out of a
+// per-warp shared-memory copy of the step's bytes, and the survivors go to a per-warp queue that
+// is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
+// block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
+// other warps' fingerprint work.
 template <int MODE, bool MASKED>
 __global__ void __launch_bounds__(kPfThreads, 2)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem_raw);          // [kPfWarps][kPfQw] offsets
-  uint32_t* s_queue2 = s_queue + kPfWarps * kPfQw;                    // [kPfWarps][kPfQ2]
-  uint32_t* s_bitmap = s_queue2 + kPfWarps * kPfQ2;
+  uint32_t* s_scratch = reinterpret_cast<uint32_t*>(smem_raw);        // [kPfWarps][32 lanes][9 words]
+  uint32_t* s_queue2 = s_scratch + kPfWarps * 32 * 9;                 // [kPfWarps][kPfQ2] verified offsets
+  uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
+  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
   __shared__ uint8_t s_cls[256];
+  __shared__ uint32_t s_cnt[kPfWarps];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -136,6 +138,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint32_t bitmap_words = p.brute ? 0u : (1u << (p.log_bits - 5));
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
+  if (tid < kPfWarps) s_cnt[tid] = 0;
   __syncthreads();
 
   Emitter em{p.keys, p.pids, p.counter, p.cap};
@@ -167,42 +170,16 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 
   const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
-  uint32_t* q = s_queue + warp * kPfQw;
+  uint32_t* scratch = s_scratch + warp * (32 * 9);
+  uint16_t* slots = s_slots + warp * kPfSlots;
   uint32_t* q2 = s_queue2 + warp * kPfQ2;
-  uint32_t qlen = 0, q2len = 0;  // warp-uniform
+  uint32_t q2len = 0;  // warp-uniform
 
   auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
     __syncwarp();
     for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2[i], em);
     cand_total += q2len;
     q2len = 0;
-    __syncwarp();
-  };
-  auto drain = [&]() {  // second Bloom probe over the queued first-probe hits, 32 at a time
-    __syncwarp();
-    for (uint32_t base = 0; base < qlen; base += 32) {
-      const uint32_t i = base + lane;
-      bool pass = false;
-      uint32_t rel = 0;
-      if (i < qlen) {
-        rel = q[i];
-        // re-read the fingerprint (L2 hit: the bytes were streamed a moment ago); cheaper than
-        // carrying it through the queue from the divergent append loop
-        const uint8_t* a = p.hay + chunk_lo + rel;
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
-        uint32_t gram = __funnelshift_r(__ldg(aw), __ldg(aw + 1), sh);
-        if (MASKED) gram = (gram | fold) & kmask;
-        pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-      if (bal) {
-        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = rel;
-        q2len += __popc(bal);
-        if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
-      }
-    }
-    qlen = 0;
     __syncwarp();
   };
 
@@ -228,6 +205,12 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + nvalid));
     const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w;
     const uint32_t w4 = nvalid == 16 ? nx : vb.x, w5 = vb.y, w6 = vb.z, w7 = vb.w, w8 = nx;
+    // park the lane's 36-byte window in shared memory (stride 9 words: conflict free) so that the
+    // second probe can fetch any fingerprint of this step without touching global memory
+    {
+      uint32_t* sc = scratch + lane * 9;
+      sc[0] = w0; sc[1] = w1; sc[2] = w2; sc[3] = w3; sc[4] = w4; sc[5] = w5; sc[6] = w6; sc[7] = w7; sc[8] = w8;
+    }
     uint32_t mask = 0;  // after 32 probes: bit o <=> position blk+o passed the first probe
 #define ACB_GRAM(o, lo, hi) (MASKED ? (((((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)) | fold) & kmask) \
                                     : (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)))
@@ -242,12 +225,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     ACB_PROBE4(16, w4, w5); ACB_PROBE4(20, w5, w6); ACB_PROBE4(24, w6, w7); ACB_PROBE4(28, w7, w8);
 #undef ACB_PROBE4
 #undef ACB_PROBE
+#undef ACB_GRAM
     mask = nvalid == 32 ? mask : (nvalid == 16 ? (mask & 0xFFFFu) : 0u);
+    // slot allocation for this step's first-probe hits: one shared-memory atomic per lane with hits
     const uint32_t cnt = __popc(mask);
-    const uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+    uint32_t slot = 0;
+    if (cnt) slot = atomicAdd(&s_cnt[warp], cnt);
+    __syncwarp();
+    const uint32_t total = s_cnt[warp];
     if (total == 0) continue;
-    if (qlen + total > (uint32_t)kPfQw) drain();
-    if (total > (uint32_t)kPfQw) {
+    __syncwarp();
+    if (lane == 0) s_cnt[warp] = 0;
+    if (total > (uint32_t)kPfSlots) {
       // fingerprints not selective here: verify this step's hits in place
       while (mask) {
         const int o = __ffs(mask) - 1;
@@ -258,24 +247,34 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       __syncwarp();
       continue;
     }
-    // exclusive prefix sum of cnt across the warp
-    uint32_t pre = cnt;
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, pre, dlt);
-      if (lane >= dlt) pre += t;
-    }
-    uint32_t slot = qlen + pre - cnt;
-    const uint32_t rel = (uint32_t)(blk - chunk_lo);
     while (mask) {
       const int o = __ffs(mask) - 1;
       mask &= mask - 1;
-      q[slot++] = rel + o;
+      slots[slot++] = (uint16_t)(lane * 32 + o);
     }
-    qlen += total;
+    __syncwarp();
+    // second Bloom probe, compacted: lane t handles hit t of this step
+    const uint32_t wrel = (uint32_t)(wbase - chunk_lo);
+    for (uint32_t base = 0; base < total; base += 32) {
+      const uint32_t t = base + lane;
+      bool pass = false;
+      uint32_t e = 0;
+      if (t < total) {
+        e = slots[t];
+        const uint32_t* sc = scratch + (e >> 5) * 9 + ((e & 31) >> 2);
+        uint32_t gram = __funnelshift_r(sc[0], sc[1], (e & 3) * 8);
+        if (MASKED) gram = (gram | fold) & kmask;
+        pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if (bal) {
+        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+        q2len += __popc(bal);
+        if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+      }
+    }
+    __syncwarp();  // scratch / slots are rewritten by the next step
   }
-#undef ACB_GRAM
-  if (qlen) drain();
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
 }
@@ -329,7 +328,7 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfWarps) * (kPfQw * 4 + kPfQ2 * 4) + bitmap_bytes;
+  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * 4 + kPfSlots * 2) + bitmap_bytes;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   auto kern = p.mode == 0 ? (masked ? prefilter_kernel<0, true> : prefilter_kernel<0, false>)
                           : (masked ? prefilter_kernel<1, true> : prefilter_kernel<1, false>);
