@@ -428,84 +428,129 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   return ACG_E_NOMEM;
 }
 
-// K3/K3b (+ K4): prefilter engine on a device-resident haystack.  mode 0 leaves all occurrences
-// ordered like find_overlapping_iter; mode 1 leaves the best match per start offset ordered by
-// start (input of the chain resolution).
-int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t hay_len, uint64_t span_start,
-                  uint64_t span_end, int mode, TupleResult* res) {
+// Enqueue one K3/K3b launch covering the start offsets [scan_lo, scan_hi) of the span.
+int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable,
+                            uint64_t span_start, uint64_t span_end, uint64_t scan_lo,
+                            uint64_t scan_hi, int mode, int dev_sms) {
   Workspace& w = a->ws;
   const PrefilterPlan& pf = a->pf;
+  // 16-byte aligned filter region whose 4-byte look-ahead stays inside the readable bytes
+  const uintptr_t base = reinterpret_cast<uintptr_t>(d_hay);
+  uint64_t lo = scan_lo + ((16 - ((base + scan_lo) & 15)) & 15);
+  const uint64_t limit = std::min<uint64_t>(scan_hi, readable >= 20 ? readable - 20 : 0);
+  uint64_t hi = lo;
+  if (limit > lo) hi = lo + ((limit - lo) & ~15ull);
+  if (lo > scan_hi) { lo = scan_hi; hi = scan_hi; }
+  acb::PrefilterLaunch p;
+  p.hay = d_hay;
+  p.hay_len = readable;
+  p.span_start = span_start;
+  p.span_end = span_end;
+  p.bitmap = a->d_bitmap;
+  p.log_bits = pf.log_bits;
+  p.k = pf.k;
+  p.kmask = pf.kmask;
+  p.fold = pf.fold;
+  p.mult = pf.mult;
+  p.shift = pf.shift;
+  p.brute = pf.brute ? 1 : 0;
+  p.mode = mode;
+  p.dup_shift = pf.dup_shift;
+  p.scan_lo = scan_lo;
+  p.scan_hi = scan_hi;
+  p.region_lo = lo;
+  p.region_hi = hi;
+  p.tile_bytes = 0;
+  p.n_tiles = 0;
+  p.keys = w.d_keys[0];
+  p.pids = w.d_pids[0];
+  p.counter = w.d_counter;
+  p.cap = w.cap;
+  CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
+  a->stats.launches += 1;
+  return ACG_OK;
+}
+
+// K4: order the appended tuples; `want` tuples sit in buffer 0.
+int order_tuples(const acg_dfa* a, uint64_t want, uint64_t n_bytes, TupleResult* res) {
+  Workspace& w = a->ws;
+  res->n = want;
+  a->stats.raw_matches = want;
+  if (want > 1) {
+    size_t tb = w.temp_bytes;
+    const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
+    float ms = 0;
+    CK(cudaEventRecord(w.ev2, w.stream));
+    CK(acb::sort_pairs(w.d_temp, tb, w.d_keys[0], w.d_keys[1], w.d_pids[0], w.d_pids[1], want, end_bit,
+                       w.stream));
+    CK(cudaEventRecord(w.ev3, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    cudaEventElapsedTime(&ms, w.ev2, w.ev3);
+    a->stats.order_ms = ms;
+    a->stats.launches += 8;  // radix passes (library code, upper bound)
+    res->sorted_buf = 1;
+  } else {
+    res->sorted_buf = 0;
+  }
+  return ACG_OK;
+}
+
+// K3/K3b (+ K4): prefilter engine.  mode 0 leaves all occurrences ordered like
+// find_overlapping_iter; mode 1 leaves the best match per start offset ordered by start (input of
+// the chain resolution).  When `h_hay` is given the span is first copied from (pinned) host
+// memory in chunks on the copy stream, and each chunk is scanned as soon as it has landed, so the
+// H2D copy and the scan overlap.
+int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uint64_t span_start,
+                  uint64_t span_end, int mode, TupleResult* res, const uint8_t* h_hay = nullptr) {
+  Workspace& w = a->ws;
   const uint64_t n_bytes = span_end - span_start;
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
-  // 16-byte aligned filter region whose 4-byte look-ahead stays inside the haystack allocation
-  const uintptr_t base = reinterpret_cast<uintptr_t>(d_hay);
-  uint64_t lo = span_start + ((16 - ((base + span_start) & 15)) & 15);
-  uint64_t limit = std::min<uint64_t>(span_end, hay_len >= 20 ? hay_len - 20 : 0);
-  uint64_t hi = lo;
-  if (limit > lo) hi = lo + ((limit - lo) & ~15ull);
-  if (lo > span_end) { lo = span_end; hi = span_end; }
-  const uint64_t tile_bytes = 16 * 1024;
-  const uint64_t n_tiles = (hi - lo + tile_bytes - 1) / tile_bytes;
   uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 64));
+  bool copied = h_hay == nullptr;
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
     if (rc) return rc;
     CK(cudaMemsetAsync(w.d_counter, 0, 16, w.stream));
-    acb::PrefilterLaunch p;
-    p.hay = d_hay;
-    p.hay_len = hay_len;
-    p.span_start = span_start;
-    p.span_end = span_end;
-    p.bitmap = a->d_bitmap;
-    p.log_bits = pf.log_bits;
-    p.k = pf.k;
-    p.kmask = pf.kmask;
-    p.fold = pf.fold;
-    p.mult = pf.mult;
-    p.shift = pf.shift;
-    p.brute = pf.brute ? 1 : 0;
-    p.mode = mode;
-    p.dup_shift = pf.dup_shift;
-    p.region_lo = lo;
-    p.region_hi = hi;
-    p.tile_bytes = tile_bytes;
-    p.n_tiles = n_tiles;
-    p.keys = w.d_keys[0];
-    p.pids = w.d_pids[0];
-    p.counter = w.d_counter;
-    p.cap = w.cap;
     CK(cudaEventRecord(w.ev0, w.stream));
-    CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
+    if (copied) {
+      if ((rc = enqueue_prefilter_range(a, d_hay, readable, span_start, span_end, span_start, span_end,
+                                        mode, dev_sms)))
+        return rc;
+    } else {
+      // chunked H2D on the copy stream; a chunk's start offsets are scanned once the bytes a
+      // verification can touch (max_pattern_len + fingerprint look-ahead) have landed
+      const uint64_t chunk = 64ull << 20;
+      const uint64_t tail = std::min<uint64_t>(a->h.max_pattern_len, 1u << 30) + 64;
+      uint64_t scanned = span_start;
+      CK(cudaEventRecord(w.ev2, w.copy_stream));
+      for (uint64_t c0 = span_start; c0 < span_end; c0 += chunk) {
+        const uint64_t c1 = std::min(span_end, c0 + chunk);
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(d_hay) + c0, h_hay + c0, c1 - c0, cudaMemcpyHostToDevice,
+                           w.copy_stream));
+        CK(cudaEventRecord(w.ev3, w.copy_stream));
+        CK(cudaStreamWaitEvent(w.stream, w.ev3, 0));
+        const uint64_t upto = c1 == span_end ? span_end : (c1 > scanned + tail ? c1 - tail : scanned);
+        if (upto > scanned || c1 == span_end) {
+          if ((rc = enqueue_prefilter_range(a, d_hay, c1 == span_end ? readable : c1, span_start, span_end,
+                                            scanned, upto, mode, dev_sms)))
+            return rc;
+          scanned = upto;
+        }
+      }
+      copied = true;
+    }
     CK(cudaEventRecord(w.ev1, w.stream));
     CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 16, cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
-    a->stats.launches += 1;
     const uint64_t want = w.h_counter[0];
     a->stats.candidates = w.h_counter[1];
-    if (want > w.cap) { cap = want + want / 8 + 1024; continue; }
-    res->n = want;
-    a->stats.raw_matches = want;
     float ms = 0;
     cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-    a->stats.scan_ms = ms;
-    if (want > 1) {
-      size_t tb = w.temp_bytes;
-      const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
-      CK(cudaEventRecord(w.ev2, w.stream));
-      CK(acb::sort_pairs(w.d_temp, tb, w.d_keys[0], w.d_keys[1], w.d_pids[0], w.d_pids[1], want, end_bit,
-                         w.stream));
-      CK(cudaEventRecord(w.ev3, w.stream));
-      CK(cudaStreamSynchronize(w.stream));
-      cudaEventElapsedTime(&ms, w.ev2, w.ev3);
-      a->stats.order_ms = ms;
-      a->stats.launches += 8;
-      res->sorted_buf = 1;
-    } else {
-      res->sorted_buf = 0;
-    }
-    return ACG_OK;
+    a->stats.scan_ms = ms;  // with a host haystack this is the overlapped copy+scan time
+    if (want > w.cap) { cap = want + want / 8 + 1024; continue; }
+    return order_tuples(a, want, n_bytes, res);
   }
   return ACG_E_NOMEM;
 }
@@ -662,13 +707,15 @@ int run_seq(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start, uint64_
 // Stage [span_start, span_end) of a host haystack on the device; returns a
 // pointer that can be indexed with ABSOLUTE haystack offsets in that range.
 int stage_host_span(const acg_dfa* a, const uint8_t* hay, uint64_t span_start, uint64_t span_end,
-                    const uint8_t** d_base) {
+                    const uint8_t** d_base, bool alloc_only = false) {
   Workspace& w = a->ws;
   // keep the 16-byte phase of the host offsets so vector loads stay aligned
   const uint64_t lead = span_start & 15;
   const uint64_t bytes = span_end - span_start;
   int rc = ensure_hay(w, bytes + lead + 64);
   if (rc) return rc;
+  *d_base = w.d_hay + lead - span_start;  // never dereferenced outside [span_start, span_end + slack)
+  if (alloc_only) return ACG_OK;
   CK(cudaEventRecord(w.ev0, w.stream));
   if (bytes)
     CK(cudaMemcpyAsync(w.d_hay + lead, hay + span_start, bytes, cudaMemcpyHostToDevice, w.stream));
@@ -725,12 +772,14 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   a->stats.engine = engine;
   const uint8_t* d_base = hay;
   uint64_t readable = hay_len;
+  const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
   if (!hay_on_device) {
-    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base, pipelined))) return rc;
     readable = span_end + 32;  // the staging buffer has slack behind the span
   }
   TupleResult r;
-  if (engine == ACG_ENGINE_PREFILTER) rc = run_prefilter(a, d_base, readable, span_start, span_end, 0, &r);
+  if (engine == ACG_ENGINE_PREFILTER)
+    rc = run_prefilter(a, d_base, readable, span_start, span_end, 0, &r, pipelined ? hay : nullptr);
   else rc = run_walk_overlapping(a, d_base, span_start, span_end, &r);
   if (rc) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
@@ -757,8 +806,9 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   a->stats.engine = engine;
   const uint8_t* d_base = hay;
   uint64_t readable = hay_len;
+  const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
   if (!hay_on_device) {
-    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base, pipelined))) return rc;
     readable = span_end + 32;
   }
   if (engine == ACG_ENGINE_SEQUENTIAL) {
@@ -770,7 +820,8 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   // leftmost kinds: best match per start offset ordered by start, then the same greedy choice.
   const int mode = a->h.match_kind == ACG_STANDARD ? 0 : 1;
   TupleResult r;
-  if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode, &r))) return rc;
+  if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode, &r, pipelined ? hay : nullptr)))
+    return rc;
   if ((rc = run_chain(a, mode, &r))) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
   return drain_tuples(a, r, span_start, out, cap, n_out, nullptr, mode);

@@ -146,10 +146,10 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 
   // head / tail positions outside the aligned filter region are unconditional candidates
   if (blockIdx.x == 0) {
-    const uint64_t head_n = p.region_lo - p.span_start;
-    const uint64_t tail_n = p.span_end > p.region_hi ? p.span_end - p.region_hi : 0;
+    const uint64_t head_n = p.region_lo - p.scan_lo;
+    const uint64_t tail_n = p.scan_hi > p.region_hi ? p.scan_hi - p.region_hi : 0;
     for (uint64_t i = tid; i < head_n + tail_n; i += kPfThreads) {
-      const uint64_t s = i < head_n ? p.span_start + i : p.region_hi + (i - head_n);
+      const uint64_t s = i < head_n ? p.scan_lo + i : p.region_hi + (i - head_n);
       verify_at<MODE>(d, p, s_cls, s, em);
     }
   }

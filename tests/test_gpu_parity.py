@@ -252,3 +252,27 @@ def test_config2_reduced_full_tuple_parity(engine):
     sub, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), hay.size, span=(s, e))
     keep = (want["start"] >= s) & (want["end"] <= e)
     assert_np_equal(sub, want[keep])
+
+
+def test_pipelined_host_path_multi_chunk():
+    """Host haystacks larger than one 64 MiB staging chunk are copied and scanned chunk by chunk
+    (copy and scan overlap); the stream must equal the one-shot device-resident scan."""
+    import torch
+    pats = W.make_patterns(5000, W.CONFIGS["cfg2"]["pattern_seed"])
+    t = torch.empty(200 << 20, dtype=torch.uint8)
+    W.torch_fill_config("cfg2", t, pats, chunk=1 << 24)
+    hay = t.numpy()
+    d = t.cuda()
+    for kind, overlapping in ((0, True), (0, False), (1, False)):
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA)
+        if overlapping:
+            want, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), hay.size)
+            got = ac.try_find_overlapping_iter_np(hay)
+            sub = ac.try_find_overlapping_iter_np(hay, span=(70 << 20 | 5, (190 << 20) + 3))
+            keep = (want["start"] >= (70 << 20 | 5)) & (want["end"] <= (190 << 20) + 3)
+            assert_np_equal(sub, want[keep])
+        else:
+            want, _ = ac.find_iter_dev_np(d.data_ptr(), hay.size)
+            got = ac.try_find_iter_np(hay)
+        assert len(want) > 40000
+        assert_np_equal(got, want, (kind, overlapping))
