@@ -142,6 +142,8 @@ _lib.acg_find_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64,
 _lib.acg_find_iter_dev.argtypes = _lib.acg_find_overlapping_dev.argtypes
 _lib.acg_count_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64),
                                            C.POINTER(C.c_float)]
+_lib.acg_find_overlapping_devout.argtypes = [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _u64,
+                                             C.POINTER(_u64), C.POINTER(C.c_float)]
 _lib.acg_device_count.argtypes = []
 
 
@@ -269,11 +271,15 @@ class AhoCorasick:
 
     def __init__(self, handle):
         self._h = handle
+        self._cap_hint = 4096  # output-buffer sizing for the two-call overflow protocol
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            _lib.acg_dfa_free(h)
+        if h and _lib is not None:
+            try:
+                _lib.acg_dfa_free(h)
+            except Exception:
+                pass
             self._h = None
 
     @staticmethod
@@ -396,13 +402,14 @@ class AhoCorasick:
     def _collect(self, fn, hay, span, anchored):
         keep, ptr, n = _hay_ptr(hay)
         s, e = _span(span, n)
-        cap = 4096
+        cap = self._cap_hint
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = np.empty(cap, MATCH_DTYPE)
             cnt = _u64()
             rc = fn(self._h, ptr, n, s, e, int(anchored), out.ctypes.data, cap, C.byref(cnt))
-            if rc == E_OVERFLOW:
-                cap = int(cnt.value)
+            if rc == E_OVERFLOW:  # the call reports the required count: retry once with room to spare
+                cap = int(cnt.value) + int(cnt.value) // 8 + 64
+                self._cap_hint = max(self._cap_hint, cap)
                 continue
             if rc:
                 self._raise(rc)
@@ -445,14 +452,15 @@ class AhoCorasick:
     # ---- device-resident haystack (torch tensor / raw pointer), for the roofline measurement ----
     def find_overlapping_iter_dev_np(self, dev_ptr, hay_len, span=None):
         s, e = _span(span, hay_len)
-        cap = 1 << 16
+        cap = max(self._cap_hint, 1 << 16)
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = np.empty(cap, MATCH_DTYPE)
             cnt, ms = _u64(), C.c_float()
             rc = _lib.acg_find_overlapping_dev(self._h, dev_ptr, hay_len, s, e, out.ctypes.data, cap,
                                                C.byref(cnt), C.byref(ms))
             if rc == E_OVERFLOW:
-                cap = int(cnt.value)
+                cap = int(cnt.value) + int(cnt.value) // 8 + 64
+                self._cap_hint = max(self._cap_hint, cap)
                 continue
             if rc:
                 self._raise(rc)
@@ -460,18 +468,32 @@ class AhoCorasick:
 
     def find_iter_dev_np(self, dev_ptr, hay_len, span=None):
         s, e = _span(span, hay_len)
-        cap = 1 << 16
+        cap = max(self._cap_hint, 1 << 16)
         while True:
-            out = np.zeros(cap, MATCH_DTYPE)
+            out = np.empty(cap, MATCH_DTYPE)
             cnt, ms = _u64(), C.c_float()
             rc = _lib.acg_find_iter_dev(self._h, dev_ptr, hay_len, s, e, out.ctypes.data, cap,
                                         C.byref(cnt), C.byref(ms))
             if rc == E_OVERFLOW:
-                cap = int(cnt.value)
+                cap = int(cnt.value) + int(cnt.value) // 8 + 64
+                self._cap_hint = max(self._cap_hint, cap)
                 continue
             if rc:
                 self._raise(rc)
             return out[: cnt.value], ms.value
+
+    def find_overlapping_devout(self, dev_ptr, hay_len, span, min_end, offset_add, out_ptr, cap):
+        """Ordered matches stay on the device (acg_match records at out_ptr). Returns (n, kernel_ms);
+        raises OverflowError(needed) if cap is too small."""
+        s, e = _span(span, hay_len)
+        cnt, ms = _u64(), C.c_float()
+        rc = _lib.acg_find_overlapping_devout(self._h, dev_ptr, hay_len, s, e, min_end, offset_add,
+                                              out_ptr, cap, C.byref(cnt), C.byref(ms))
+        if rc == E_OVERFLOW:
+            raise OverflowError(int(cnt.value))
+        if rc:
+            self._raise(rc)
+        return int(cnt.value), ms.value
 
     def count_overlapping_dev(self, dev_ptr, hay_len, span=None):
         s, e = _span(span, hay_len)

@@ -748,9 +748,16 @@ int validate_common(const acg_dfa* a, uint64_t hay_len, uint64_t s, uint64_t e, 
   return ACG_OK;
 }
 
+struct DevOut {
+  void* d_out = nullptr;
+  uint64_t min_end = 0;
+  uint64_t offset_add = 0;
+};
+
 int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
                      uint64_t span_start, uint64_t span_end, int anchored, acg_match* out,
-                     uint64_t cap, uint64_t* n_out, uint64_t* fnv, float* kernel_ms) {
+                     uint64_t cap, uint64_t* n_out, uint64_t* fnv, float* kernel_ms,
+                     const DevOut* devout = nullptr) {
   if (!n_out) return ACG_E_INVALID_ARG;
   *n_out = 0;
   int rc = validate_common(a, hay_len, span_start, span_end, anchored);
@@ -783,6 +790,34 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   else rc = run_walk_overlapping(a, d_base, span_start, span_end, &r);
   if (rc) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
+  if (devout) {
+    // keep the matches on the device: drop ends <= min_end (owned by the previous shard), expand
+    Workspace& w = a->ws;
+    uint64_t first = 0;
+    if (r.n && devout->min_end > span_start) {
+      const uint64_t bound_key = (devout->min_end - span_start + 1) << acb::kTieBits;  // first key with end > min_end
+      CK(acb::launch_lower_bound(w.d_keys[r.sorted_buf], r.n, bound_key, w.d_counter, w.stream));
+      CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
+      CK(cudaStreamSynchronize(w.stream));
+      first = *w.h_counter;
+    }
+    const uint64_t kept = r.n - first;
+    *n_out = kept;
+    if (kept > cap) return ACG_E_OVERFLOW;
+    acb::ExpandLaunch e;
+    e.keys = w.d_keys[r.sorted_buf];
+    e.pids = w.d_pids[r.sorted_buf];
+    e.pattern_lens = a->d_plens;
+    e.n = r.n;
+    e.first = first;
+    e.span_start = span_start;
+    e.offset_add = devout->offset_add;
+    e.out = static_cast<uint64_t*>(devout->d_out);
+    CK(acb::launch_expand(e, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    a->stats.launches += 2;
+    return ACG_OK;
+  }
   return drain_tuples(a, r, span_start, out, cap, n_out, fnv);
 }
 
@@ -1013,6 +1048,18 @@ int acg_find_overlapping_dev(const acg_dfa* a, const void* d_hay, uint64_t hay_l
                              uint64_t* n_out, float* kernel_ms) {
   return overlapping_impl(a, static_cast<const uint8_t*>(d_hay), true, hay_len, span_start, span_end,
                           0, out, cap, n_out, nullptr, kernel_ms);
+}
+int acg_find_overlapping_devout(const acg_dfa* a, const void* d_hay, uint64_t hay_len,
+                                uint64_t span_start, uint64_t span_end, uint64_t min_end,
+                                uint64_t offset_add, void* d_out, uint64_t cap, uint64_t* n_out,
+                                float* kernel_ms) {
+  if (!d_out && cap) return ACG_E_INVALID_ARG;
+  DevOut dv;
+  dv.d_out = d_out;
+  dv.min_end = min_end;
+  dv.offset_add = offset_add;
+  return overlapping_impl(a, static_cast<const uint8_t*>(d_hay), true, hay_len, span_start, span_end, 0,
+                          nullptr, cap, n_out, nullptr, kernel_ms, &dv);
 }
 int acg_count_overlapping_dev(const acg_dfa* a, const void* d_hay, uint64_t hay_len,
                               uint64_t span_start, uint64_t span_end, uint64_t* n_out, uint64_t* fnv,

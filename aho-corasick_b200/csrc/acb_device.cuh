@@ -114,6 +114,24 @@ cudaError_t select_flagged(void* d_temp, size_t& temp_bytes, const uint64_t* key
                            const uint8_t* flags, uint64_t* keys_out, uint32_t* pids_out,
                            unsigned long long* d_num_out, uint64_t n, cudaStream_t s);
 
+// Expand ordered (end_rel << 24 | tie, pid) tuples into 24-byte match records on the device,
+// keeping only ends > min_end (writes compacted output; order preserved because kept tuples are a
+// suffix of the end-sorted list).
+struct ExpandLaunch {
+  const uint64_t* keys;
+  const uint32_t* pids;
+  const uint32_t* pattern_lens;
+  uint64_t n;
+  uint64_t first;        // index of the first kept tuple (host-side binary search result)
+  uint64_t span_start;
+  uint64_t offset_add;
+  uint64_t* out;         // [ (n-first) * 3 ] as (pid, start, end) u64 triples == acg_match layout
+};
+cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s);
+// number of leading tuples whose end_rel <= bound (keys sorted ascending)
+cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_key,
+                               unsigned long long* d_result, cudaStream_t s);
+
 // key/pid pair sort (K4). temp storage is queried with d_temp == nullptr.
 cudaError_t sort_pairs(void* d_temp, size_t& temp_bytes, const uint64_t* keys_in, uint64_t* keys_out,
                        const uint32_t* vals_in, uint32_t* vals_out, uint64_t n, int end_bit,

@@ -182,7 +182,43 @@ __global__ void seq_find_kernel(DfaDev d, SeqLaunch p) {
   *p.counter = n;
 }
 
+__global__ void expand_kernel(ExpandLaunch e) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e.first + i >= e.n) return;
+  const uint64_t key = e.keys[e.first + i];
+  const uint32_t pid = e.pids[e.first + i];
+  const uint64_t end = e.span_start + (key >> kTieBits) + e.offset_add;
+  // acg_match { u32 pid; u32 pad; u64 start; u64 end; }
+  e.out[i * 3 + 0] = (uint64_t)pid;
+  e.out[i * 3 + 1] = end - e.pattern_lens[pid];
+  e.out[i * 3 + 2] = end;
+}
+
+// keys are sorted: count the tuples with key < bound_key (single block, strided binary chunks)
+__global__ void lower_bound_kernel(const uint64_t* keys, uint64_t n, uint64_t bound_key,
+                                   unsigned long long* result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (keys[mid] < bound_key) lo = mid + 1; else hi = mid;
+  }
+  *result = lo;
+}
+
 }  // namespace
+
+cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s) {
+  const uint64_t m = e.n - e.first;
+  if (m == 0) return cudaSuccess;
+  expand_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(e);
+  return cudaGetLastError();
+}
+cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_key,
+                               unsigned long long* d_result, cudaStream_t s) {
+  lower_bound_kernel<<<1, 32, 0, s>>>(keys, n, bound_key, d_result);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s) {
   const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;

@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 walk, 2 prefilter")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -136,25 +137,43 @@ def main():
     import torch.distributed as dist
 
     import aho_corasick_b200 as ab
+    from aho_corasick_b200 import sharded as S
     from aho_corasick_b200 import workload as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
-    n_bytes = int(args.hay_gib * GIB)
-    n_bytes -= n_bytes % 4096
-    goff = rank * n_bytes  # weak scaling: every rank owns its own slice of the global stream
-    pats = W.make_patterns(5000, W.CONFIGS["cfg2"]["pattern_seed"])
-    ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats).set_engine(args.engine)
-    d_hay = torch.empty(n_bytes, dtype=torch.uint8, device="cuda")
-    planted = W.torch_fill_config("cfg2", d_hay, pats, global_offset=goff)
+    cfg = W.CONFIGS[args.workload]
+    per_gpu = int(args.hay_gib * GIB)
+    per_gpu -= per_gpu % 4096
+    total = per_gpu * world  # weak scaling: the global haystack grows with the number of GPUs
+    pats = W.make_patterns(cfg["n_patterns"], cfg["pattern_seed"], alphabet=cfg["alphabet"])
+    overlapping = args.workload in ("cfg2", "cfg5")
+    b = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA)
+    if args.workload == "cfg3":
+        b.ascii_case_insensitive(True).match_kind(ab.MatchKind.LeftmostFirst)
+    if args.workload == "cfg4":
+        b.match_kind(ab.MatchKind.LeftmostFirst)
+    t0 = time.perf_counter()
+    ac = b.build(pats).set_engine(args.engine)
+    build_s = time.perf_counter() - t0
+    # haystack slicing: this rank owns ends in (own_lo, own_hi] and reads from read_lo
+    own_lo, own_hi, read_lo = S.slice_plan(0, total, world, ac.max_pattern_len())[rank]
+    gen_lo = read_lo - read_lo % 4096
+    n_local = own_hi - gen_lo
+    n_local += (-n_local) % 8
+    d_hay = torch.empty(n_local, dtype=torch.uint8, device=dev)
+    W.torch_fill_config(args.workload, d_hay, pats, global_offset=gen_lo)
     torch.cuda.synchronize()
-    # rank r additionally sees max_pattern_len-1 bytes before its slice? The slices are independent
-    # haystack slices here (each rank scans its own 4 GiB cold), matches carry global offsets.
+    span = (read_lo - gen_lo, own_hi - gen_lo)
+    n_bytes = own_hi - own_lo  # bytes this rank is credited with (overlap re-reads are not)
+    cap = max(1 << 20, n_bytes // 512)
+    d_out = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -162,55 +181,87 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_dev():
-        return ac.count_overlapping_dev(d_hay.data_ptr(), n_bytes)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        """One pass of the hot path over this rank's slice, matches left on the device in global
+        offsets; for N > 1 followed by the NCCL gather of the match buffers to rank 0."""
+        nonlocal cap, d_out
+        while True:
+            try:
+                if overlapping:
+                    n, ms = ac.find_overlapping_devout(d_hay.data_ptr(), n_local, span, own_lo - gen_lo, gen_lo,
+                                                       d_out.data_ptr(), cap)
+                else:
+                    r, ms = ac.find_iter_dev_np(d_hay.data_ptr(), n_local, span)
+                    n = len(r)
+                break
+            except OverflowError as e:
+                cap = int(e.args[0]) * 9 // 8 + 1024
+                d_out = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
+        gms = 0.0
+        gathered = None
+        if world > 1 and overlapping:
+            ev0.record()
+            gathered = S.gather_to_rank0(d_out[: n * 24], dist)
+            ev1.record()
+            ev1.synchronize()
+            gms = ev0.elapsed_time(ev1)
+        return n, ms, gms, gathered
 
     # ---- device-resident throughput (inputs already in HBM) ----
     for _ in range(args.warmup):
-        step_dev()
+        step()
     barrier()
-    kernel_ms, scan_ms = [], []
+    kernel_ms, scan_ms, gather_ms = [], [], []
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cnt, fnv, ms = step_dev()
+            cnt, ms, gms, gathered = step()
             st = ac.last_stats()
             kernel_ms.append(ms)
             scan_ms.append(st["scan_ms"])
+            gather_ms.append(gms)
         barrier()
         wall = time.perf_counter() - t0
     stats = ac.last_stats()
-    # device time of the K steps = sum of per-step CUDA-event times of the library's kernels
-    dev_s = sum(kernel_ms) / 1e3
-    t = torch.tensor([dev_s, wall], dtype=torch.float64, device="cuda")
+    dev_s = (sum(kernel_ms) + sum(gather_ms)) / 1e3
+    t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall = t.tolist()
-    value = world * n_bytes * args.steps / GIB / dev_s
-    matches = torch.tensor([cnt], dtype=torch.int64, device="cuda")
+    value = total * args.steps / GIB / dev_s
+    matches = torch.tensor([cnt], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(matches)
     total_matches = int(matches.item())
+    if world > 1 and rank == 0 and gathered is not None:
+        assert len(gathered) == total_matches and bool(np.all(np.diff(gathered["end"].astype(np.int64)) >= 0))
 
     # ---- end to end through the host-buffer C-ABI call (pinned host haystack, H2D inside) ----
-    e2e_bytes = min(n_bytes, 1 << 30)
-    h_hay = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
-    h_hay.copy_(d_hay[:e2e_bytes])
-    h_np = h_hay.numpy()
-    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
-    r = []
-    for _ in range(0 if args.no_e2e else 2):
-        r = ac.try_find_overlapping_iter_np(h_np)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = ac.try_find_overlapping_iter_np(h_np)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / max(e2e_steps, 1)
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * e2e_bytes / GIB / te.item()
+    e2e_val, e2e_bytes, d2h = None, 0, 0
+    if not args.no_e2e:
+        e2e_bytes = min(span[1] - span[0], 1 << 30)
+        h_hay = torch.empty(e2e_bytes, dtype=torch.uint8, pin_memory=True)
+        h_hay.copy_(d_hay[span[0]: span[0] + e2e_bytes])
+        h_np = h_hay.numpy()
+        call = ac.try_find_overlapping_iter_np if overlapping else ac.try_find_iter_np
+        for _ in range(2):
+            r = call(h_np)
+        barrier()
+        e2e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = call(h_np)
+            if world > 1:
+                S.gather_to_rank0(r, dist, device=dev)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_val = world * e2e_bytes / GIB / te.item()
+        d2h = int(len(r) * 12 + 16)
 
     if rank != 0:
         if world > 1:
@@ -219,40 +270,53 @@ def main():
     peak, which = peaks()
     scan_s = sum(scan_ms) / len(scan_ms) / 1e3
     achieved = n_bytes / scan_s / 1e9
+    kname = {1: "walk_overlapping_kernel", 2: "prefilter_kernel", 3: "seq_find_kernel"}[int(stats["engine"])]
+    traffic = None
+    tf = ROOT / "profiles" / "r01_dram_traffic.json"
+    if tf.exists():
+        rec = json.loads(tf.read_text()).get(f"{args.workload}:{kname}")
+        if rec:  # measured with `ncu --set full` on this kernel; scaled to this launch's bytes
+            traffic = rec["dram_bytes_per_haystack_byte"] * n_bytes
+    desc = {"cfg2": "5000 random 4-16B printable-ASCII patterns, DFA, MatchKind::Standard, find_overlapping_iter",
+            "cfg3": "5000 patterns, ascii_case_insensitive, DFA, MatchKind::LeftmostFirst, find_iter",
+            "cfg4": "50 literals (Teddy-active set), MatchKind::LeftmostFirst, find_iter",
+            "cfg5": "100000 patterns, DFA, MatchKind::Standard, find_overlapping_iter"}[args.workload]
     line = {
         "metric": "haystack_scan_throughput", "value": value, "unit": "GiB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "cfg2: 5000 random 4-16B printable-ASCII patterns, "
-                               f"{n_bytes / GIB:g} GiB synthetic ASCII haystack per GPU with ~1 planted pattern/4 KiB, "
-                               "DFA, MatchKind::Standard, find_overlapping_iter",
-                   "haystack_bytes_per_gpu": n_bytes, "l2": "input (>=1 GiB) is much larger than the 126 MB L2",
-                   "engine": int(stats["engine"]), "table_bytes": ac.memory_usage(),
-                   "states": ac.state_len()},
+        "config": {"workload": f"{args.workload}: {desc}; {per_gpu / GIB:g} GiB synthetic haystack per GPU, "
+                               "~1 planted pattern per 4 KiB",
+                   "haystack_bytes_per_gpu": per_gpu, "global_haystack_bytes": total,
+                   "l2": "input per launch is far larger than the 126 MB L2",
+                   "engine": kname, "table_bytes": ac.memory_usage(), "states": ac.state_len(),
+                   "sharding": "haystack slices, max_pattern_len-1 overlap, NCCL gather of match buffers to rank 0"
+                               if world > 1 else "single GPU"},
         "matches": total_matches, "matches_per_s": total_matches * args.steps / dev_s,
         "candidates": int(stats["candidates"]), "scan_ms": sum(scan_ms) / len(scan_ms),
-        "order_ms": float(stats["order_ms"]),
-        "wall_ms_per_step": wall / args.steps * 1e3,
+        "order_ms": float(stats["order_ms"]), "gather_ms": sum(gather_ms) / len(gather_ms),
+        "build_s": build_s, "wall_ms_per_step": wall / args.steps * 1e3,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": which,
-                     "kernel": "walk_overlapping_kernel" if stats["engine"] == 1 else "prefilter",
-                     "algorithmic_bytes_per_launch": n_bytes},
-        "e2e": {"value": e2e_val, "unit": "GiB/s", "h2d_bytes_per_step": e2e_bytes,
-                "d2h_bytes_per_step": int(len(r) * 12 + 8)},
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                     "kernel": kname, "algorithmic_bytes_per_launch": n_bytes},
         "gpu_launches": int(stats["launches"]) * args.steps,
         "clocks": clocks.summary(),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if e2e_val is not None:
+        line["e2e"] = {"value": e2e_val, "unit": "GiB/s", "h2d_bytes_per_step": e2e_bytes,
+                       "d2h_bytes_per_step": d2h}
+    if not args.no_cpu_baseline and world == 1 and overlapping:
         import oracle_py as O
-        sample = 64 << 20
+        sample = min(64 << 20, e2e_bytes or (64 << 20))
         o = O.Oracle(pats, kind=O.KIND_DFA)
-        h = h_np[:sample]
+        h = (h_np if not args.no_e2e else d_hay[span[0]: span[0] + sample].cpu().numpy())[:sample]
         t0 = time.perf_counter()
-        c1 = o.scan_overlapping_count(h)
+        o.scan_overlapping_count(h)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": sample / GIB / dt, "unit": "GiB/s", "cores": 1, "kind": "port",
-                                "sample": "first 64 MiB of the same haystack, scalar DFA loop, 1 thread"}
+                                "sample": f"first {sample >> 20} MiB of the same haystack, scalar DFA loop "
+                                          "(src/automaton.rs:1491-1534 restated in oracle/), 1 thread"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

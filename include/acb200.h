@@ -166,6 +166,14 @@ int acg_find_overlapping_dev(const acg_dfa* dfa, const void* d_hay, uint64_t hay
 int acg_find_iter_dev(const acg_dfa* dfa, const void* d_hay, uint64_t hay_len,
                       uint64_t span_start, uint64_t span_end,
                       acg_match* out, uint64_t cap, uint64_t* n_out, float* kernel_ms);
+/* Same as acg_find_overlapping_dev but the ordered matches stay on the device: d_out is a device
+ * array of acg_match (cap entries); only matches with end > min_end are kept (shard ownership
+ * by end offset) and `offset_add` is added to start/end (global offsets of
+ * a sliced haystack).  *n_out receives the number written.  Feeds the NCCL gather directly. */
+int acg_find_overlapping_devout(const acg_dfa* dfa, const void* d_hay, uint64_t hay_len,
+                                uint64_t span_start, uint64_t span_end, uint64_t min_end,
+                                uint64_t offset_add, void* d_out, uint64_t cap, uint64_t* n_out,
+                                float* kernel_ms);
 /* Count-only variants: scan + order on the device, return the number of matches
  * and an FNV-1a checksum of the ordered (pid,start,end) stream computed on the
  * device-ordered tuples (host side folds it).  `d_out`/cap may be 0/NULL. */
