@@ -61,3 +61,35 @@ def gather_to_rank0(local, dist, device=None):
         return None
     parts = [b[:c].cpu().numpy().view(MATCH_DTYPE) for b, c in zip(bufs, counts)]
     return np.concatenate(parts) if parts else np.zeros(0, MATCH_DTYPE)
+
+
+class MatchGatherer:
+    """Persistent-buffer version of gather_to_rank0 for the bench loop: match buffers stay on the
+    device (rank 0 ends up with every rank's acg_match records in rank order), one small
+    all_gather for the counts and one gather for the payload per call, no host round trips other
+    than reading the counts."""
+
+    def __init__(self, dist, device, cap_bytes):
+        import torch
+        self.dist, self.device = dist, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.cap = int(cap_bytes)
+        self._torch = torch
+        self.count = torch.zeros(1, dtype=torch.int64, device=device)
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=device)
+        self.recv = ([torch.empty(self.cap, dtype=torch.uint8, device=device) for _ in range(self.world)]
+                     if self.rank == 0 else None)
+
+    def gather(self, local_buf, n_bytes):
+        """local_buf: uint8 CUDA tensor of capacity >= cap (only the first n_bytes are meaningful)."""
+        assert local_buf.numel() >= self.cap and n_bytes <= self.cap
+        self.count.fill_(n_bytes)
+        self.dist.all_gather_into_tensor(self.counts, self.count)
+        self.dist.gather(local_buf[: self.cap], self.recv, dst=0)
+        return self.counts
+
+    def result_numpy(self):
+        """(rank 0) concatenated matches as a host array -- outside any timed region."""
+        counts = self.counts.tolist()
+        parts = [b[:c].cpu().numpy().view(MATCH_DTYPE) for b, c in zip(self.recv, counts)]
+        return np.concatenate(parts)

@@ -182,6 +182,7 @@ def main():
             torch.cuda.synchronize()
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gatherer = None
 
     def step():
         """One pass of the hot path over this rank's slice, matches left on the device in global
@@ -199,15 +200,27 @@ def main():
             except OverflowError as e:
                 cap = int(e.args[0]) * 9 // 8 + 1024
                 d_out = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
+        nonlocal gatherer
         gms = 0.0
-        gathered = None
         if world > 1 and overlapping:
+            # every rank must use the same payload width: agree on the capacity once (and again
+            # only if some rank had to grow its buffer)
+            capt = torch.tensor([cap], dtype=torch.int64, device=dev)
+            if gatherer is None or gatherer.cap < cap * 24:
+                dist.all_reduce(capt, op=dist.ReduceOp.MAX)
+                gcap = int(capt.item())
+                if gcap > cap:
+                    cap = gcap
+                    grown = torch.empty(cap * 24, dtype=torch.uint8, device=dev)
+                    grown[: n * 24] = d_out[: n * 24]
+                    d_out = grown
+                gatherer = S.MatchGatherer(dist, dev, cap * 24)
             ev0.record()
-            gathered = S.gather_to_rank0(d_out[: n * 24], dist)
+            gatherer.gather(d_out, n * 24)
             ev1.record()
             ev1.synchronize()
             gms = ev0.elapsed_time(ev1)
-        return n, ms, gms, gathered
+        return n, ms, gms, None
 
     # ---- device-resident throughput (inputs already in HBM) ----
     for _ in range(args.warmup):
@@ -235,7 +248,8 @@ def main():
     if world > 1:
         dist.all_reduce(matches)
     total_matches = int(matches.item())
-    if world > 1 and rank == 0 and gathered is not None:
+    if world > 1 and rank == 0 and gatherer is not None:
+        gathered = gatherer.result_numpy()  # outside the timed region: check the gathered stream
         assert len(gathered) == total_matches and bool(np.all(np.diff(gathered["end"].astype(np.int64)) >= 0))
 
     # ---- end to end through the host-buffer C-ABI call (pinned host haystack, H2D inside) ----
