@@ -146,6 +146,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = W.CONFIGS[args.workload]
