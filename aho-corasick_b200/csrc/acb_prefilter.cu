@@ -20,9 +20,9 @@
 namespace acb {
 namespace {
 
-constexpr int kPfThreads = 512;
+constexpr int kPfThreads = 1024;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfSlots = 256;   // first-probe hits of one warp step handled by the compacted second probe
+constexpr int kPfSlots = 512;   // first-probe hits of one warp step handled by the compacted second probe
 constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
@@ -122,7 +122,7 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
 template <int MODE, bool MASKED>
-__global__ void __launch_bounds__(kPfThreads, 2)
+__global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_scratch = reinterpret_cast<uint32_t*>(smem_raw);        // [kPfWarps][32 lanes][9 words]
