@@ -66,6 +66,9 @@ struct PrefilterPlan {
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
   uint64_t n_grams = 0;
   std::vector<uint32_t> bitmap;
+  // third level (dense pattern sets only): single-hash bitmap of 2^glog bits kept in global memory
+  std::vector<uint32_t> gbitmap;
+  uint32_t glog = 0;
 };
 
 struct acg_dfa {
@@ -73,6 +76,7 @@ struct acg_dfa {
   std::vector<uint16_t> depth16;
   PrefilterPlan pf;
   uint32_t* d_bitmap = nullptr;
+  uint32_t* d_gbitmap = nullptr;
   bool has_empty = false;
   uint32_t max_list_len = 0;
   bool on_device = false;
@@ -105,6 +109,16 @@ uint32_t bloom_hash2(uint32_t x) {
   x ^= x >> 15;
   x *= 0x846ca68bu;
   x ^= x >> 16;
+  return x;
+}
+
+// third-level hash; must match bloom_hash3() in acb_prefilter.cu
+uint32_t bloom_hash3(uint32_t x) {
+  x ^= x >> 15;
+  x *= 0x2c1b3c6du;
+  x ^= x >> 12;
+  x *= 0x297a2d39u;
+  x ^= x >> 15;
   return x;
 }
 
@@ -180,7 +194,8 @@ void derive_metadata(acg_dfa* a) {
     if (cur.size() > (64u << 20)) break;  // pathological fan-out: give up on longer fingerprints
   }
   // pick the fingerprint length with the sparsest bitmap (ties -> longer)
-  double best_fill = 2.0;
+  double best_fill = 2.0, best_fp = 0.0;
+  std::vector<uint32_t> best_set;
   for (uint32_t k = 1; k <= kmax; ++k) {
     if (grams[k].empty()) continue;
     std::vector<uint32_t> raw = grams[k], folded = grams[k];
@@ -209,6 +224,7 @@ void derive_metadata(acg_dfa* a) {
     }
     double fill = double(set_bits) / double(uint64_t(1) << log_bits);
     fill = fill * fill;  // both probes must hit
+    const double fp_only = fill;
     // expected candidate rate on text drawn from the patterns' own alphabet: Bloom false positives
     // plus genuine k-gram prefix hits (n_grams / prod_j |bytes seen at position j|)
     double space = 1.0;
@@ -225,11 +241,24 @@ void derive_metadata(acg_dfa* a) {
       pf.mult = mult; pf.shift = shift; pf.log_bits = log_bits;
       pf.fill = fill; pf.n_grams = set.size();
       pf.bitmap.swap(bm);
+      best_fp = fp_only;
+      best_set = set;
+      for (uint32_t& g : best_set) g &= kmask;
     }
   }
   if (pf.k == 0) return;
   pf.brute = pf.fill > 0.25;
   pf.supported = true;
+  if (!pf.brute && best_fp > 1e-3) {
+    // the shared-memory Bloom filter lets through more than 0.1 % false positives (many
+    // patterns): add a large single-hash bitmap that lives in L2 and is probed only by survivors
+    pf.glog = uint32_t(std::min(28, std::max(20, bits_for(uint64_t(best_set.size()) * 512 - 1))));
+    pf.gbitmap.assign(size_t(1) << (pf.glog - 5), 0u);
+    for (uint32_t g : best_set) {
+      const uint32_t hsh = bloom_hash3(g);
+      pf.gbitmap[hsh >> (37 - pf.glog)] |= 1u << (hsh & 31);
+    }
+  }
 }
 
 int upload(acg_dfa* a) {
@@ -253,6 +282,7 @@ int upload(acg_dfa* a) {
   CK(up(&a->d_plens, h.pattern_lens.data(), h.pattern_lens.size() * 4));
   CK(up(&a->d_depth16, a->depth16.data(), a->depth16.size() * 2));
   if (a->pf.supported && !a->pf.bitmap.empty()) CK(up(&a->d_bitmap, a->pf.bitmap.data(), a->pf.bitmap.size() * 4));
+  if (a->pf.supported && !a->pf.gbitmap.empty()) CK(up(&a->d_gbitmap, a->pf.gbitmap.data(), a->pf.gbitmap.size() * 4));
   DfaDev& d = a->dev;
   d.trans = a->d_trans;
   d.classes = a->d_classes;
@@ -453,6 +483,8 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.fold = pf.fold;
   p.mult = pf.mult;
   p.shift = pf.shift;
+  p.gbitmap = a->d_gbitmap;
+  p.gshift = pf.glog ? 37 - pf.glog : 0;
   p.brute = pf.brute ? 1 : 0;
   p.mode = mode;
   p.dup_shift = pf.dup_shift;
@@ -962,7 +994,7 @@ void acg_dfa_free(acg_dfa* a) {
     Workspace& w = a->ws;
     if (w.stream) cudaStreamSynchronize(w.stream);
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
-    cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap);
+    cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_gbitmap);
     for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
     cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
     cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);

@@ -81,6 +81,8 @@ struct PrefilterLaunch {
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult
   uint32_t shift;               // hash >> shift = byte offset into the bitmap (= 35 - log_bits)
+  const uint32_t* gbitmap;      // optional third-level bitmap in global memory (nullptr: unused)
+  uint32_t gshift;              // word index = hash3 >> gshift
   int brute;                    // 1: skip the bitmap, every position is a candidate
   int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)
   uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break

@@ -44,6 +44,17 @@ __device__ __forceinline__ uint32_t bloom_hash2(uint32_t x) {
   return x;
 }
 
+// Third-level fingerprint hash (global-memory bitmap, only for automata with many patterns).
+// Must match bloom_hash3() in acb_api.cu.
+__device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
+  x ^= x >> 15;
+  x *= 0x2c1b3c6du;
+  x ^= x >> 12;
+  x *= 0x297a2d39u;
+  x ^= x >> 15;
+  return x;
+}
+
 struct Emitter {
   uint64_t* g_keys;
   uint32_t* g_pids;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_scratch = reinterpret_cast<uint32_t*>(smem_raw);        // [kPfWarps][32 lanes][9 words]
-  uint32_t* s_queue2 = s_scratch + kPfWarps * 32 * 9;                 // [kPfWarps][kPfQ2] verified offsets
+  uint2* s_queue2 = reinterpret_cast<uint2*>(s_scratch + kPfWarps * 32 * 9);  // [kPfWarps][kPfQ2] (offset, gram)
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
   __shared__ uint8_t s_cls[256];
@@ -172,12 +183,34 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   uint32_t* scratch = s_scratch + warp * (32 * 9);
   uint16_t* slots = s_slots + warp * kPfSlots;
-  uint32_t* q2 = s_queue2 + warp * kPfQ2;
+  uint2* q2 = s_queue2 + warp * kPfQ2;
+  const uint32_t* __restrict__ gbits = p.gbitmap;  // optional third-level bitmap in global memory (L2)
+  const uint32_t gshift = p.gshift;
   uint32_t q2len = 0;  // warp-uniform
 
   auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
     __syncwarp();
-    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2[i], em);
+    if (gbits) {
+      // dense pattern sets: one more fingerprint probe against a large L2-resident bitmap, the
+      // survivors are compacted in place so that the DFA walks still run with full warps
+      uint32_t w = 0;
+      for (uint32_t base = 0; base < q2len; base += 32) {
+        const uint32_t i = base + lane;
+        bool pass = false;
+        uint2 e = make_uint2(0, 0);
+        if (i < q2len) {
+          e = q2[i];
+          const uint32_t h = bloom_hash3(e.y);
+          pass = (__ldg(gbits + (h >> gshift)) >> (h & 31)) & 1u;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) q2[w + __popc(bal & ((1u << lane) - 1))] = e;
+        w += __popc(bal);
+        __syncwarp();
+      }
+      q2len = w;
+    }
+    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2[i].x, em);
     cand_total += q2len;
     q2len = 0;
     __syncwarp();
@@ -258,17 +291,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     for (uint32_t base = 0; base < total; base += 32) {
       const uint32_t t = base + lane;
       bool pass = false;
-      uint32_t e = 0;
+      uint32_t e = 0, gram_keep = 0;
       if (t < total) {
         e = slots[t];
         const uint32_t* sc = scratch + (e >> 5) * 9 + ((e & 31) >> 2);
         uint32_t gram = __funnelshift_r(sc[0], sc[1], (e & 3) * 8);
         if (MASKED) gram = (gram | fold) & kmask;
+        gram_keep = gram;
         pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, pass);
       if (bal) {
-        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
         q2len += __popc(bal);
         if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
       }
@@ -328,7 +362,7 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * 4 + kPfSlots * 2) + bitmap_bytes;
+  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * 8 + kPfSlots * 2) + bitmap_bytes;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   auto kern = p.mode == 0 ? (masked ? prefilter_kernel<0, true> : prefilter_kernel<0, false>)
                           : (masked ? prefilter_kernel<1, true> : prefilter_kernel<1, false>);
