@@ -14,6 +14,8 @@
 // of patterns that are a prefix of the haystack at that offset.
 #include "acb_device.cuh"
 
+#include <type_traits>
+
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 
@@ -22,8 +24,9 @@ namespace {
 
 constexpr int kPfThreads = 1024;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfSlots = 512;   // first-probe hits of one warp step handled by the compacted second probe
 constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
+// first-probe hits of one warp step handled by the compacted second probe (more for dense sets)
+template <bool DENSE> struct PfCfg { static constexpr int kSlots = DENSE ? 512 : 256; };
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 v;
@@ -132,12 +135,14 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-template <int MODE, bool MASKED>
+template <int MODE, bool MASKED, bool DENSE>
 __global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
+  constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
+  using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* s_scratch = reinterpret_cast<uint32_t*>(smem_raw);        // [kPfWarps][32 lanes][9 words]
-  uint2* s_queue2 = reinterpret_cast<uint2*>(s_scratch + kPfWarps * 32 * 9);  // [kPfWarps][kPfQ2] (offset, gram)
+  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_scratch + kPfWarps * 32 * 9);  // [kPfWarps][kPfQ2]
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
   __shared__ uint8_t s_cls[256];
@@ -183,14 +188,17 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   uint32_t* scratch = s_scratch + warp * (32 * 9);
   uint16_t* slots = s_slots + warp * kPfSlots;
-  uint2* q2 = s_queue2 + warp * kPfQ2;
+  Q2Entry* q2 = s_queue2 + warp * kPfQ2;
   const uint32_t* __restrict__ gbits = p.gbitmap;  // optional third-level bitmap in global memory (L2)
   const uint32_t gshift = p.gshift;
   uint32_t q2len = 0;  // warp-uniform
 
+  auto q2_off = [](const Q2Entry& e) -> uint32_t {
+    if constexpr (DENSE) return e.x; else return e;
+  };
   auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
     __syncwarp();
-    if (gbits) {
+    if constexpr (DENSE) {
       // dense pattern sets: one more fingerprint probe against a large L2-resident bitmap, the
       // survivors are compacted in place so that the DFA walks still run with full warps
       uint32_t w = 0;
@@ -210,7 +218,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       }
       q2len = w;
     }
-    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2[i].x, em);
+    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2_off(q2[i]), em);
     cand_total += q2len;
     q2len = 0;
     __syncwarp();
@@ -302,7 +310,10 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, pass);
       if (bal) {
-        if (pass) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
+        if (pass) {
+          if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
+          else q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+        }
         q2len += __popc(bal);
         if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
       }
@@ -362,10 +373,17 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * 8 + kPfSlots * 2) + bitmap_bytes;
+  const bool dense = p.gbitmap != nullptr;
+  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * (dense ? 8 : 4) +
+                                          (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
-  auto kern = p.mode == 0 ? (masked ? prefilter_kernel<0, true> : prefilter_kernel<0, false>)
-                          : (masked ? prefilter_kernel<1, true> : prefilter_kernel<1, false>);
+  using KernT = void (*)(DfaDev, PrefilterLaunch);
+  static const KernT table[2][2][2] = {
+      {{prefilter_kernel<0, false, false>, prefilter_kernel<0, false, true>},
+       {prefilter_kernel<0, true, false>, prefilter_kernel<0, true, true>}},
+      {{prefilter_kernel<1, false, false>, prefilter_kernel<1, false, true>},
+       {prefilter_kernel<1, true, false>, prefilter_kernel<1, true, true>}}};
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][dense ? 1 : 0];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
