@@ -447,7 +447,11 @@ class AhoCorasick:
     find = try_find  # :404
 
     def is_match(self, hay, span=None):  # :311
-        return self.try_find(hay, span, earliest=True) is not None
+        # The reference asks for the earliest match; only existence is reported, and a match exists
+        # under `earliest` iff one exists without it, so leftmost automata stay on the windowed
+        # device scan instead of the single-lane engine.
+        earliest = self.match_kind() == MatchKind.Standard
+        return self.try_find(hay, span, earliest=earliest) is not None
 
     # ---- device-resident haystack (torch tensor / raw pointer), for the roofline measurement ----
     def find_overlapping_iter_dev_np(self, dev_ptr, hay_len, span=None):

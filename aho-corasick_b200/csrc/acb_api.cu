@@ -533,13 +533,15 @@ int order_tuples(const acg_dfa* a, uint64_t want, uint64_t n_bytes, TupleResult*
 // memory in chunks on the copy stream, and each chunk is scanned as soon as it has landed, so the
 // H2D copy and the scan overlap.
 int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uint64_t span_start,
-                  uint64_t span_end, int mode, TupleResult* res, const uint8_t* h_hay = nullptr) {
+                  uint64_t span_end, int mode, TupleResult* res, const uint8_t* h_hay = nullptr,
+                  uint64_t scan_lo = UINT64_MAX, uint64_t scan_hi = UINT64_MAX) {
+  if (scan_lo == UINT64_MAX) { scan_lo = span_start; scan_hi = span_end; }
   Workspace& w = a->ws;
   const uint64_t n_bytes = span_end - span_start;
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
-  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 64));
+  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, (scan_hi - scan_lo) / 64));
   bool copied = h_hay == nullptr;
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
@@ -547,8 +549,8 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
     CK(cudaMemsetAsync(w.d_counter, 0, 16, w.stream));
     CK(cudaEventRecord(w.ev0, w.stream));
     if (copied) {
-      if ((rc = enqueue_prefilter_range(a, d_hay, readable, span_start, span_end, span_start, span_end,
-                                        mode, dev_sms)))
+      if ((rc = enqueue_prefilter_range(a, d_hay, readable, span_start, span_end, scan_lo, scan_hi, mode,
+                                        dev_sms)))
         return rc;
     } else {
       // chunked H2D on the copy stream; a chunk's start offsets are scanned once the bytes a
@@ -1125,13 +1127,91 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
   std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
   a->stats = acg_stats{};
-  a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+  Workspace& w = a->ws;
+  // `earliest` on a leftmost automaton reports the first match STATE entered (src/automaton.rs
+  // :1381-1383), which the per-start formulation does not model: sequential engine.
+  const bool use_pf = a->pf.supported && !anchored && a->engine_override != ACG_ENGINE_SEQUENTIAL &&
+                      !(earliest && a->h.match_kind != ACG_STANDARD);
   const uint8_t* d_base = nullptr;
-  if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
-  uint64_t n = 0;
-  rc = run_seq(a, d_base, span_start, span_end, anchored, earliest, 1, out, 1, &n);
-  if (rc == ACG_OK && n) *found = 1;
-  return rc;
+  if (!use_pf) {
+    a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+    if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
+    uint64_t n = 0;
+    rc = run_seq(a, d_base, span_start, span_end, anchored, earliest, 1, out, 1, &n);
+    if (rc == ACG_OK && n) *found = 1;
+    return rc;
+  }
+  // The reference's try_find is lazy (it stops reading at the first match, SURVEY.md section
+  // 7h); the eager device scan therefore works through geometrically growing windows of start
+  // offsets (1 MiB, 16 MiB, 256 MiB, ...), copying only what a window needs.
+  a->stats.engine = ACG_ENGINE_PREFILTER;
+  if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base, true))) return rc;
+  const int mode = a->h.match_kind == ACG_STANDARD ? 0 : 1;
+  const uint64_t look = a->h.max_pattern_len + 64;
+  uint64_t copied_hi = span_start;
+  auto ensure_copied = [&](uint64_t upto) -> int {
+    upto = std::min(upto, span_end);
+    if (upto > copied_hi) {
+      CK(cudaMemcpyAsync(const_cast<uint8_t*>(d_base) + copied_hi, hay + copied_hi, upto - copied_hi,
+                         cudaMemcpyHostToDevice, w.stream));
+      copied_hi = upto;
+    }
+    return ACG_OK;
+  };
+  auto first_tuple = [&](const TupleResult& r, uint64_t* key, uint32_t* pid) -> int {
+    CK(cudaMemcpyAsync(w.h_counter, w.d_keys[r.sorted_buf], 8, cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaMemcpyAsync(w.h_counter + 1, w.d_pids[r.sorted_buf], 4, cudaMemcpyDeviceToHost, w.stream));
+    CK(cudaStreamSynchronize(w.stream));
+    *key = w.h_counter[0];
+    *pid = uint32_t(w.h_counter[1]);
+    return ACG_OK;
+  };
+  auto decode = [&](uint64_t key, uint32_t pid) {
+    out->pid = pid;
+    out->_pad = 0;
+    if (mode == 1) {
+      out->start = span_start + (key >> acb::kTieBits);
+      out->end = out->start + (key & acb::kTieMask);
+    } else {
+      out->end = span_start + (key >> acb::kTieBits);
+      out->start = out->end - a->h.pattern_lens[pid];
+    }
+  };
+  uint64_t lo = span_start, win = 1ull << 20;
+  while (lo < span_end) {
+    const uint64_t hi = std::min(span_end, lo + win);
+    if ((rc = ensure_copied(hi + look))) return rc;
+    TupleResult r;
+    if ((rc = run_prefilter(a, d_base, copied_hi == span_end ? span_end + 32 : copied_hi, span_start,
+                            span_end, mode, &r, nullptr, lo, hi)))
+      return rc;
+    if (r.n) {
+      uint64_t key;
+      uint32_t pid;
+      if ((rc = first_tuple(r, &key, &pid))) return rc;
+      decode(key, pid);
+      if (mode == 0 && out->end > hi && hi < span_end) {
+        // Standard: a match that starts in [hi, end) could still end earlier -- scan those starts
+        const uint64_t hi2 = std::min(span_end, uint64_t(out->end));
+        if ((rc = ensure_copied(hi2 + look))) return rc;
+        TupleResult r2;
+        if ((rc = run_prefilter(a, d_base, copied_hi == span_end ? span_end + 32 : copied_hi, span_start,
+                                span_end, mode, &r2, nullptr, hi, hi2)))
+          return rc;
+        if (r2.n) {
+          uint64_t key2;
+          uint32_t pid2;
+          if ((rc = first_tuple(r2, &key2, &pid2))) return rc;
+          if (key2 < key) decode(key2, pid2);
+        }
+      }
+      *found = 1;
+      return ACG_OK;
+    }
+    lo = hi;
+    win = std::min<uint64_t>(win * 16, 1ull << 30);
+  }
+  return ACG_OK;
 }
 
 const char* acg_strerror(int code) {

@@ -276,3 +276,82 @@ def test_pipelined_host_path_multi_chunk():
             got = ac.try_find_iter_np(hay)
         assert len(want) > 40000
         assert_np_equal(got, want, (kind, overlapping))
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at its full size (4 GiB, device-generated).  The oracle cannot scan 4 GiB
+    in test time, so parity is carried by size-independent properties: (1) the two independent
+    engines (sharded state-transition walk vs. prefilter + verify) produce the same ordered stream
+    (count + FNV of every tuple); (2) a checksum of checksums: the stream over the whole haystack
+    equals the concatenation of the streams over two half spans plus the matches that straddle the
+    cut; (3) every planted pattern is reported; (4) the oracle agrees on sampled 8 MiB windows."""
+    import torch
+    n = 4 << 30
+    pats = W.make_patterns(5000, W.CONFIGS["cfg2"]["pattern_seed"])
+    try:
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    except RuntimeError:
+        pytest.skip("not enough device memory for the 4 GiB haystack")
+    planted = W.torch_fill_config("cfg2", d, pats)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    cnt_p, fnv_p, _ = ac.count_overlapping_dev(d.data_ptr(), n)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    ac.set_engine(ab.Engine.Walk)
+    cnt_w, fnv_w, _ = ac.count_overlapping_dev(d.data_ptr(), n)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
+    assert (cnt_p, fnv_p) == (cnt_w, fnv_w)
+    assert cnt_p >= planted
+    ac.set_engine(ab.Engine.Auto)
+    full, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n)
+    assert len(full) == cnt_p
+    cut = (2 << 30) + 12345
+    left, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n, span=(0, cut))
+    right, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n, span=(cut, n))
+    straddle = full[(full["start"] < cut) & (full["end"] > cut)]
+    assert len(left) + len(right) + len(straddle) == len(full)
+    assert_np_equal(left, full[full["end"] <= cut])
+    assert_np_equal(right, full[full["start"] >= cut])
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    for off in (0, (1 << 30) + 4096 * 7 + 3, n - (8 << 20)):
+        w = d[off: off + (8 << 20)].cpu().numpy()
+        want = o.find_overlapping_iter_np(w)
+        got = full[(full["start"] >= off) & (full["end"] <= off + (8 << 20))]
+        assert len(got) == len(want)
+        assert np.array_equal(got["pid"], want["pid"]) and np.array_equal(got["start"] - off, want["start"]) \
+            and np.array_equal(got["end"] - off, want["end"])
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_find_single_vs_oracle(kind):
+    """AhoCorasick::try_find (src/ahocorasick.rs:1021): windowed device scan vs the oracle."""
+    rng = random.Random(0xF1D0 + kind)
+    for it in range(80):
+        pats, hay, span, ci = rand_case(rng, it, allow_empty=(it % 5 == 0))
+        kw = {"ascii_case_insensitive": ci}
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA, **kw)
+        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA, prefilter=False, **kw)
+        for earliest in (False, True):
+            got = ac.try_find(hay, span, earliest=earliest)
+            want = o.try_find(hay, span, earliest=earliest)
+            assert (got.as_tuple() if got else None) == want, (it, pats[:4], hay.size, span, earliest)
+        assert ac.is_match(hay, span) == (o.try_find(hay, span, earliest=True) is not None)
+
+
+def test_find_far_match_multi_window():
+    """The first match sits behind several scan windows (1 MiB, 16 MiB, ...)."""
+    hay = np.full(40 << 20, ord("x"), dtype=np.uint8)
+    hay[(30 << 20) + 5: (30 << 20) + 11] = np.frombuffer(b"needle", dtype=np.uint8)
+    hay[(1 << 20) - 2: (1 << 20) + 1] = np.frombuffer(b"nee", dtype=np.uint8)   # near miss on a window edge
+    for kind in (0, 1, 2):
+        ac = build([b"needle", b"need", b"zzz"], kind, kind=ab.AhoCorasickKind.DFA)
+        o = O.Oracle([b"needle", b"need", b"zzz"], match_kind=kind, kind=O.KIND_DFA)
+        assert ac.try_find(hay).as_tuple() == o.try_find(hay)
+        assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+        assert ac.try_find(hay, span=(0, (30 << 20) + 8)) is None
+        assert ac.is_match(hay) and not ac.is_match(hay[: 30 << 20])
+    # Standard semantics across a window edge: the earliest END wins even if it starts later
+    pats = [b"a" + b"b" * 15, b"bb"]
+    hay = np.full(3 << 20, ord("x"), dtype=np.uint8)
+    hay[(1 << 20) - 3: (1 << 20) + 13] = np.frombuffer(pats[0], dtype=np.uint8)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    assert ac.try_find(hay).as_tuple() == O.Oracle(pats, kind=O.KIND_DFA).try_find(hay)
