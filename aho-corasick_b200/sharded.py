@@ -85,7 +85,12 @@ class MatchGatherer:
         assert local_buf.numel() >= self.cap and n_bytes <= self.cap
         self.count.fill_(n_bytes)
         self.dist.all_gather_into_tensor(self.counts, self.count)
-        self.dist.gather(local_buf[: self.cap], self.recv, dst=0)
+        # ship only what the fullest rank needs (one small host read of the counts), not the capacity
+        width = int(self.counts.max().item())
+        width = min(self.cap, (width + 4095) // 4096 * 4096)
+        if width:
+            recv = [b[:width] for b in self.recv] if self.rank == 0 else None
+            self.dist.gather(local_buf[:width], recv, dst=0)
         return self.counts
 
     def result_numpy(self):
