@@ -207,7 +207,11 @@ void derive_metadata(acg_dfa* a) {
     // Bloom bitmap with two hashes (a single multiply for the per-position probe, a full mix
     // for the second probe that only first-probe hits pay for).  Bit position of a hash h: byte
     // from the top (log_bits-3) bits, bit inside the byte from the low 3 bits (little-endian words).
-    const uint32_t log_bits = uint32_t(std::min(20, std::max(13, bits_for(uint64_t(set.size()) * 256 - 1))));
+    // more than 8192 fingerprints: a 64 KiB shared bitmap plus the third-level bitmap in L2
+    // (the larger queues of the dense variant need the shared memory); otherwise 128 KiB
+    const bool dense_set = set.size() > 8192;
+    const uint32_t log_bits =
+        uint32_t(std::min(dense_set ? 19 : 20, std::max(13, bits_for(uint64_t(set.size()) * 256 - 1))));
     const uint32_t mult = 0x9E3779B1u;
     const uint32_t shift = 35 - log_bits;
     const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
@@ -249,7 +253,8 @@ void derive_metadata(acg_dfa* a) {
   if (pf.k == 0) return;
   pf.brute = pf.fill > 0.25;
   pf.supported = true;
-  if (!pf.brute && best_fp > 1e-3) {
+  (void)best_fp;
+  if (!pf.brute && best_set.size() > 8192) {
     // the shared-memory Bloom filter lets through more than 0.1 % false positives (many
     // patterns): add a large single-hash bitmap that lives in L2 and is probed only by survivors
     pf.glog = uint32_t(std::min(28, std::max(20, bits_for(uint64_t(best_set.size()) * 512 - 1))));

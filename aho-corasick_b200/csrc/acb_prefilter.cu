@@ -58,6 +58,40 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
   return x;
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared staging of the haystack ----
+constexpr int kPfStages = 2;            // ring depth per warp
+constexpr int kPfTile = 1024;           // haystack bytes per warp step
+constexpr int kPfStageBytes = kPfTile + 16;  // + fingerprint look-ahead
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// cp.async.bulk (TMA, SASS UBLKCP): `bytes` (multiple of 16) from 16-byte aligned global memory
+// into shared memory, completion signalled on the mbarrier as transaction bytes.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct Emitter {
   uint64_t* g_keys;
   uint32_t* g_pids;
@@ -129,9 +163,10 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 }
 
 // One CTA owns a contiguous chunk of the filter region; each warp streams 512 B of it per step
-// (32 B per lane, coalesced) and probes the k-gram Bloom bitmap once per position.  The hits of
-// a step are compacted (lane t takes hit t), re-probed with the second Bloom hash out of a
-// per-warp shared-memory copy of the step's bytes, and the survivors go to a per-warp queue that
+// (a 1 KiB tile staged in shared memory by a TMA bulk copy, double buffered per warp) and probes
+// the k-gram Bloom bitmap once per position.  The hits of a step are compacted (lane t takes hit
+// t), re-probed with the second Bloom hash out of the staged tile, and the survivors go to a
+// per-warp queue that
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
@@ -140,9 +175,10 @@ __global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_scratch = reinterpret_cast<uint32_t*>(smem_raw);        // [kPfWarps][32 lanes][9 words]
-  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_scratch + kPfWarps * 32 * 9);  // [kPfWarps][kPfQ2]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
+  uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
+  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_bars + kPfWarps * kPfStages);  // [kPfWarps][kPfQ2]
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
   __shared__ uint8_t s_cls[256];
@@ -155,6 +191,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
   if (tid < kPfWarps) s_cnt[tid] = 0;
+  if (tid < kPfWarps * kPfStages) mbar_init(&s_bars[tid], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_proxy_async();
   __syncthreads();
 
   Emitter em{p.keys, p.pids, p.counter, p.cap};
@@ -186,10 +225,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 
   const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
-  uint32_t* scratch = s_scratch + warp * (32 * 9);
+  unsigned char* ring = s_ring + warp * (kPfStages * kPfStageBytes);
+  uint64_t* bars = s_bars + warp * kPfStages;
   uint16_t* slots = s_slots + warp * kPfSlots;
   Q2Entry* q2 = s_queue2 + warp * kPfQ2;
-  const uint32_t* __restrict__ gbits = p.gbitmap;  // optional third-level bitmap in global memory (L2)
+  const uint32_t* __restrict__ gbits = p.gbitmap;  // third-level bitmap in global memory (DENSE only)
   const uint32_t gshift = p.gshift;
   uint32_t q2len = 0;  // warp-uniform
 
@@ -224,35 +264,44 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     __syncwarp();
   };
 
-  // each lane owns 32 consecutive positions (two 16-byte loads) per step: 1 KiB per warp step
-  const uint64_t wstride = (uint64_t)kPfWarps * 1024;
-  uint64_t wbase = chunk_lo + (uint64_t)warp * 1024;
-  uint4 va_next = make_uint4(0, 0, 0, 0), vb_next = make_uint4(0, 0, 0, 0);
-  {
-    const uint64_t blk = wbase + (uint64_t)lane * 32;
-    if (blk < chunk_hi) va_next = ld_stream_u4(p.hay + blk);
-    if (blk + 16 < chunk_hi) vb_next = ld_stream_u4(p.hay + blk + 16);
+  // ---- K3 main loop.  Each warp streams its share of the chunk through a two-stage ring of
+  // 1 KiB tiles (+16 B look-ahead) filled by TMA bulk copies (cp.async.bulk, completion on an
+  // mbarrier): no load instructions or address arithmetic per lane, and the next tile is in
+  // flight while the current one is probed.  Lane L owns positions [16L,16L+16) and
+  // [512+16L,512+16L+16) of the tile, so its two 16-byte shared-memory reads are conflict free.
+  const uint64_t wstride = (uint64_t)kPfWarps * kPfTile;
+  const uint64_t wfirst = chunk_lo + (uint64_t)warp * kPfTile;
+  auto issue = [&](uint64_t wb, int stage) {  // lane 0 only
+    const uint32_t valid = (uint32_t)min((uint64_t)kPfTile, chunk_hi - wb);
+    fence_proxy_async();
+    mbar_expect_tx(&bars[stage], valid + 16);
+    tma_load_1d(ring + stage * kPfStageBytes, p.hay + wb, valid + 16, &bars[stage]);
+  };
+  if (lane == 0) {
+    if (wfirst < chunk_hi) issue(wfirst, 0);
+    if (wfirst + wstride < chunk_hi) issue(wfirst + wstride, 1);
   }
-  for (; wbase < chunk_hi; wbase += wstride) {
-    const uint64_t blk = wbase + (uint64_t)lane * 32;
-    // number of valid positions of this lane in this step (chunk sizes are multiples of 16)
-    const uint32_t nvalid = blk >= chunk_hi ? 0u : (blk + 16 >= chunk_hi ? 16u : 32u);
-    const uint4 va = va_next, vb = vb_next;
-    // software prefetch of the next step: keeps four 16-byte loads in flight per lane
-    if (blk + wstride < chunk_hi) va_next = ld_stream_u4(p.hay + blk + wstride);
-    if (blk + wstride + 16 < chunk_hi) vb_next = ld_stream_u4(p.hay + blk + wstride + 16);
-    uint32_t nx = __shfl_down_sync(0xffffffffu, va.x, 1);
-    if (nvalid && (lane == 31 || blk + 32 >= chunk_hi))
-      nx = __ldg(reinterpret_cast<const uint32_t*>(p.hay + blk + nvalid));
-    const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w;
-    const uint32_t w4 = nvalid == 16 ? nx : vb.x, w5 = vb.y, w6 = vb.z, w7 = vb.w, w8 = nx;
-    // park the lane's 36-byte window in shared memory (stride 9 words: conflict free) so that the
-    // second probe can fetch any fingerprint of this step without touching global memory
-    {
-      uint32_t* sc = scratch + lane * 9;
-      sc[0] = w0; sc[1] = w1; sc[2] = w2; sc[3] = w3; sc[4] = w4; sc[5] = w5; sc[6] = w6; sc[7] = w7; sc[8] = w8;
+  uint32_t it = 0;
+  for (uint64_t wbase = wfirst; wbase < chunk_hi; wbase += wstride, ++it) {
+    const int stage = it & 1;
+    const uint32_t parity = (it >> 1) & 1;
+    while (!mbar_try_wait(&bars[stage], parity)) {}
+    const unsigned char* tile = ring + stage * kPfStageBytes;
+    const uint32_t valid = (uint32_t)min((uint64_t)kPfTile, chunk_hi - wbase);  // multiple of 16
+    const bool va_ok = (uint32_t)lane * 16 < valid, vb_ok = 512u + (uint32_t)lane * 16 < valid;
+    const uint4 va = *reinterpret_cast<const uint4*>(tile + lane * 16);
+    const uint4 vb = *reinterpret_cast<const uint4*>(tile + 512 + lane * 16);
+    // look-ahead words: the next lane's first word; lane 31 continues at byte 512 / 1024
+    uint32_t nxa = __shfl_down_sync(0xffffffffu, va.x, 1);
+    uint32_t nxb = __shfl_down_sync(0xffffffffu, vb.x, 1);
+    const uint32_t vb0 = __shfl_sync(0xffffffffu, vb.x, 0);
+    if (lane == 31) {
+      nxa = vb0;
+      nxb = *reinterpret_cast<const uint32_t*>(tile + kPfTile);
     }
-    uint32_t mask = 0;  // after 32 probes: bit o <=> position blk+o passed the first probe
+    const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = nxa;
+    const uint32_t x0 = vb.x, x1 = vb.y, x2 = vb.z, x3 = vb.w, x4 = nxb;
+    uint32_t mask = 0;  // bit o (<16): position 16L+o; bit 16+o: position 512+16L+o of the tile
 #define ACB_GRAM(o, lo, hi) (MASKED ? (((((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)) | fold) & kmask) \
                                     : (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)))
 #define ACB_PROBE(o, lo, hi)                                                                  \
@@ -263,62 +312,64 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   } while (0)
 #define ACB_PROBE4(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 1, lo, hi); ACB_PROBE(o + 2, lo, hi); ACB_PROBE(o + 3, lo, hi)
     ACB_PROBE4(0, w0, w1); ACB_PROBE4(4, w1, w2); ACB_PROBE4(8, w2, w3); ACB_PROBE4(12, w3, w4);
-    ACB_PROBE4(16, w4, w5); ACB_PROBE4(20, w5, w6); ACB_PROBE4(24, w6, w7); ACB_PROBE4(28, w7, w8);
+    ACB_PROBE4(16, x0, x1); ACB_PROBE4(20, x1, x2); ACB_PROBE4(24, x2, x3); ACB_PROBE4(28, x3, x4);
 #undef ACB_PROBE4
 #undef ACB_PROBE
 #undef ACB_GRAM
-    mask = nvalid == 32 ? mask : (nvalid == 16 ? (mask & 0xFFFFu) : 0u);
+    mask &= (va_ok ? 0x0000FFFFu : 0u) | (vb_ok ? 0xFFFF0000u : 0u);
     // slot allocation for this step's first-probe hits: one shared-memory atomic per lane with hits
     const uint32_t cnt = __popc(mask);
     uint32_t slot = 0;
     if (cnt) slot = atomicAdd(&s_cnt[warp], cnt);
     __syncwarp();
     const uint32_t total = s_cnt[warp];
-    if (total == 0) continue;
-    __syncwarp();
-    if (lane == 0) s_cnt[warp] = 0;
-    if (total > (uint32_t)kPfSlots) {
-      // fingerprints not selective here: verify this step's hits in place
-      while (mask) {
-        const int o = __ffs(mask) - 1;
-        mask &= mask - 1;
-        verify_at<MODE>(d, p, s_cls, blk + o, em);
-      }
-      cand_total += total;
+    if (total) {
       __syncwarp();
-      continue;
-    }
-    while (mask) {
-      const int o = __ffs(mask) - 1;
-      mask &= mask - 1;
-      slots[slot++] = (uint16_t)(lane * 32 + o);
-    }
-    __syncwarp();
-    // second Bloom probe, compacted: lane t handles hit t of this step
-    const uint32_t wrel = (uint32_t)(wbase - chunk_lo);
-    for (uint32_t base = 0; base < total; base += 32) {
-      const uint32_t t = base + lane;
-      bool pass = false;
-      uint32_t e = 0, gram_keep = 0;
-      if (t < total) {
-        e = slots[t];
-        const uint32_t* sc = scratch + (e >> 5) * 9 + ((e & 31) >> 2);
-        uint32_t gram = __funnelshift_r(sc[0], sc[1], (e & 3) * 8);
-        if (MASKED) gram = (gram | fold) & kmask;
-        gram_keep = gram;
-        pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-      if (bal) {
-        if (pass) {
-          if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
-          else q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+      if (lane == 0) s_cnt[warp] = 0;
+      if (total > (uint32_t)kPfSlots) {
+        // fingerprints not selective here: verify this step's hits in place
+        while (mask) {
+          const int o = __ffs(mask) - 1;
+          mask &= mask - 1;
+          verify_at<MODE>(d, p, s_cls, wbase + (o < 16 ? lane * 16 + o : 512 + lane * 16 + (o - 16)), em);
         }
-        q2len += __popc(bal);
-        if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+        cand_total += total;
+      } else {
+        while (mask) {
+          const int o = __ffs(mask) - 1;
+          mask &= mask - 1;
+          slots[slot++] = (uint16_t)(o < 16 ? lane * 16 + o : 512 + lane * 16 + (o - 16));
+        }
+        __syncwarp();
+        // second Bloom probe, compacted: lane t handles hit t of this step; the fingerprint is
+        // re-read from the staged tile
+        const uint32_t wrel = (uint32_t)(wbase - chunk_lo);
+        for (uint32_t base = 0; base < total; base += 32) {
+          const uint32_t t = base + lane;
+          bool pass = false;
+          uint32_t e = 0, gram_keep = 0;
+          if (t < total) {
+            e = slots[t];
+            const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (e & ~3u));
+            uint32_t gram = __funnelshift_r(sc[0], sc[1], (e & 3) * 8);
+            if (MASKED) gram = (gram | fold) & kmask;
+            gram_keep = gram;
+            pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+          if (bal) {
+            if (pass) {
+              if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
+              else q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+            }
+            q2len += __popc(bal);
+            if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+          }
+        }
       }
     }
-    __syncwarp();  // scratch / slots are rewritten by the next step
+    __syncwarp();  // every lane is done with this stage: refill it with the tile two steps ahead
+    if (lane == 0 && wbase + 2 * wstride < chunk_hi) issue(wbase + 2 * wstride, stage);
   }
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
@@ -374,8 +425,9 @@ struct MaxOp {
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const bool dense = p.gbitmap != nullptr;
-  const size_t smem = size_t(kPfWarps) * (32 * 9 * 4 + kPfQ2 * (dense ? 8 : 4) +
+  const size_t smem = size_t(kPfWarps) * (kPfStages * kPfStageBytes + kPfStages * 8 + kPfQ2 * (dense ? 8 : 4) +
                                           (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
   static const KernT table[2][2][2] = {
@@ -391,7 +443,7 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sm_count * per_sm;
-  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + 16383) / 16384;  // one CTA step = 16 warps x 1 KiB
+  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + (kPfWarps * kPfTile - 1)) / (kPfWarps * kPfTile);
   if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
   kern<<<(unsigned)grid, kPfThreads, smem, s>>>(dfa, p);
   return cudaGetLastError();
