@@ -24,9 +24,13 @@ namespace {
 
 constexpr int kPfThreads = 1024;
 constexpr int kPfWarps = kPfThreads / 32;
-constexpr int kPfQ2 = 96;       // verified-candidate queue entries per warp
-// first-probe hits of one warp step handled by the compacted second probe (more for dense sets)
-template <bool DENSE> struct PfCfg { static constexpr int kSlots = DENSE ? 512 : 256; };
+// per-warp queue sizes: first-probe hits of one step handled by the compacted second probe, and
+// verified-candidate entries (the dense variant stores 8-byte entries, so fewer of them fit
+// beside the 128 KiB bitmap)
+template <bool DENSE> struct PfCfg {
+  static constexpr int kSlots = 256;
+  static constexpr int kQ2 = DENSE ? 64 : 96;
+};
 
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
   uint4 v;
@@ -174,6 +178,7 @@ template <int MODE, bool MASKED, bool DENSE>
 __global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
+  constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
@@ -425,7 +430,8 @@ struct MaxOp {
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const bool dense = p.gbitmap != nullptr;
-  const size_t smem = size_t(kPfWarps) * (kPfStages * kPfStageBytes + kPfStages * 8 + kPfQ2 * (dense ? 8 : 4) +
+  const size_t smem = size_t(kPfWarps) * (kPfStages * kPfStageBytes + kPfStages * 8 +
+                                          (dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4) +
                                           (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
