@@ -187,7 +187,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
   __shared__ uint8_t s_cls[256];
-  __shared__ uint32_t s_cnt[kPfWarps];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -195,7 +194,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint32_t bitmap_words = p.brute ? 0u : (1u << (p.log_bits - 5));
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
-  if (tid < kPfWarps) s_cnt[tid] = 0;
   if (tid < kPfWarps * kPfStages) mbar_init(&s_bars[tid], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_proxy_async();
@@ -322,15 +320,21 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 #undef ACB_PROBE
 #undef ACB_GRAM
     mask &= (va_ok ? 0x0000FFFFu : 0u) | (vb_ok ? 0xFFFF0000u : 0u);
-    // slot allocation for this step's first-probe hits: one shared-memory atomic per lane with hits
+    // slot allocation for this step's first-probe hits without touching shared memory: the
+    // per-lane counts (almost always < 8) are summed across the warp bit plane by bit plane with
+    // ballots; a lane with more hits than the planes cover sends the step down the unselective path
     const uint32_t cnt = __popc(mask);
-    uint32_t slot = 0;
-    if (cnt) slot = atomicAdd(&s_cnt[warp], cnt);
-    __syncwarp();
-    const uint32_t total = s_cnt[warp];
+    const uint32_t lt = (1u << lane) - 1;
+    constexpr int kPlanes = DENSE ? 6 : 3;  // dense sets: up to 32 hits per lane are normal
+    uint32_t slot = 0, total = 0;
+#pragma unroll
+    for (int b = 0; b < kPlanes; ++b) {
+      const uint32_t bl = __ballot_sync(0xffffffffu, (cnt >> b) & 1u);
+      slot += __popc(bl & lt) << b;
+      total += __popc(bl) << b;
+    }
+    if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
-      __syncwarp();
-      if (lane == 0) s_cnt[warp] = 0;
       if (total > (uint32_t)kPfSlots) {
         // fingerprints not selective here: verify this step's hits in place
         while (mask) {
@@ -338,7 +342,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
           mask &= mask - 1;
           verify_at<MODE>(d, p, s_cls, wbase + (o < 16 ? lane * 16 + o : 512 + lane * 16 + (o - 16)), em);
         }
-        cand_total += total;
+        cand_total += __reduce_add_sync(0xffffffffu, cnt);
       } else {
         while (mask) {
           const int o = __ffs(mask) - 1;
