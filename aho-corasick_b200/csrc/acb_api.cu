@@ -411,7 +411,7 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   // shard starts are placed so that (d_hay + span_start + k*seg_len) keeps the 16-byte
   // phase of the first shard; the kernel handles the unaligned head per lane.
   const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
-  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 64));
+  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 256));
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
     if (rc) return rc;
@@ -493,8 +493,6 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.scan_hi = scan_hi;
   p.region_lo = lo;
   p.region_hi = hi;
-  p.tile_bytes = 0;
-  p.n_tiles = 0;
   p.keys = w.d_keys[0];
   p.pids = w.d_pids[0];
   p.counter = w.d_counter;
@@ -542,7 +540,9 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
-  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, (scan_hi - scan_lo) / 64));
+  // one tuple per 256 haystack bytes to start with (the BASELINE workloads have one per 4 KiB);
+  // denser outputs are detected through the counter and the scan is repeated with room
+  uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, (scan_hi - scan_lo) / 256));
   bool copied = h_hay == nullptr;
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);

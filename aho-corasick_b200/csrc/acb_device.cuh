@@ -88,7 +88,6 @@ struct PrefilterLaunch {
   uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break
   uint64_t scan_lo, scan_hi;      // start offsets this launch is responsible for (within the span)
   uint64_t region_lo, region_hi;  // 16-byte aligned filter region inside [scan_lo, scan_hi)
-  uint64_t tile_bytes, n_tiles;
   uint64_t* keys;
   uint32_t* pids;
   unsigned long long* counter;  // [0] tuples, [1] candidates
