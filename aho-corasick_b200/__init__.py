@@ -453,6 +453,84 @@ class AhoCorasick:
         earliest = self.match_kind() == MatchKind.Standard
         return self.try_find(hay, span, earliest=earliest) is not None
 
+    # ---- replace / stream: host-side glue over find_iter, as in the reference -------------------
+    def try_replace_all_with(self, hay, dst: bytearray, replace_with):
+        """`try_replace_all_with_bytes`, src/automaton.rs:498-550: `replace_with(match, matched
+        bytes, dst) -> bool`; returning False stops the replacement after that match."""
+        keep, ptr, n = _hay_ptr(hay)
+        view = memoryview(keep).cast("B") if n else b""
+        last = 0
+        for m in self.try_find_iter(keep):
+            dst += bytes(view[last:m.start()])
+            last = m.end()
+            if not replace_with(m, bytes(view[m.start():m.end()]), dst):
+                break
+        dst += bytes(view[last:])
+
+    def try_replace_all_bytes(self, hay, replace_with):  # src/automaton.rs:457-480
+        if len(replace_with) != self.patterns_len():
+            raise ValueError("replace_all requires a replacement for every pattern in the automaton")
+        reps = [r.encode() if isinstance(r, str) else bytes(r) for r in replace_with]
+        dst = bytearray()
+
+        def put(m, _, out):
+            out += reps[m.pattern()]
+            return True
+        self.try_replace_all_with(hay, dst, put)
+        return bytes(dst)
+
+    def try_replace_all(self, hay: str, replace_with):  # src/automaton.rs:433-455
+        return self.try_replace_all_bytes(hay.encode(), replace_with).decode()
+
+    replace_all = try_replace_all                # src/ahocorasick.rs:651
+    replace_all_bytes = try_replace_all_bytes    # :693
+    replace_all_with = try_replace_all_with      # :834 (bytes flavour)
+
+    def try_stream_find_iter(self, rdr, chunk_bytes=64 << 20):
+        """`try_stream_find_iter`, src/ahocorasick.rs:1677 -> src/automaton.rs:1059-1256: matches of
+        a byte stream (anything with .read(n)), offsets relative to the start of the stream.  Like
+        the reference it is limited to MatchKind::Standard without empty patterns, and like the
+        reference's 64 KB roll buffer (src/util/buffer.rs) only max_pattern_len-1 bytes are carried
+        from one device scan to the next."""
+        if self.match_kind() != MatchKind.Standard:
+            raise MatchError(-12)
+        if self.patterns_len() and self.min_pattern_len() == 0:
+            raise MatchError(-14)
+        back = max(self.max_pattern_len() - 1, 0)
+        carry = b""
+        base = 0          # stream offset of carry[0]
+        cursor = 0        # stream offset where the iterator restarts
+        while True:
+            block = rdr.read(chunk_bytes)
+            if not block:
+                break
+            buf = np.frombuffer(carry + bytes(block), dtype=np.uint8)
+            r = self.try_find_iter_np(buf, span=(cursor - base, buf.size))
+            for pid, s, e in zip(r["pid"].tolist(), r["start"].tolist(), r["end"].tolist()):
+                yield Match(pid, base + s, base + e)
+            if len(r):
+                cursor = base + int(r["end"][-1])
+            # a match that straddles the block boundary starts no earlier than end-(max_len-1)
+            keep_from = max(cursor, base + buf.size - back)
+            carry = buf[keep_from - base:].tobytes()
+            base = keep_from
+            cursor = max(cursor, base)
+
+    stream_find_iter = try_stream_find_iter      # :906
+
+    def try_stream_replace_all(self, rdr, wtr, replace_with, chunk_bytes=64 << 20):  # :1751
+        if len(replace_with) != self.patterns_len():
+            raise ValueError("stream_replace_all requires a replacement for every pattern in the automaton")
+        reps = [r.encode() if isinstance(r, str) else bytes(r) for r in replace_with]
+        data = rdr.read()   # replacement needs the unmatched bytes as well; kept simple: one read
+        last = 0
+        import io
+        for m in self.try_stream_find_iter(io.BytesIO(data), chunk_bytes):
+            wtr.write(data[last:m.start()])
+            wtr.write(reps[m.pattern()])
+            last = m.end()
+        wtr.write(data[last:])
+
     # ---- device-resident haystack (torch tensor / raw pointer), for the roofline measurement ----
     def find_overlapping_iter_dev_np(self, dev_ptr, hay_len, span=None):
         s, e = _span(span, hay_len)

@@ -1,0 +1,293 @@
+// acb200.hpp -- header-only C++ facade over the C ABI (acb200.h).
+//
+// Mirrors the search surface of BurntSushi/aho-corasick 1.1.3 (the reference is Rust; there is no
+// Rust toolchain in the build image, so the host side above the C ABI is C++):
+//
+//   reference (src/ahocorasick.rs)                        here
+//   ---------------------------------------------------  -----------------------------------------
+//   AhoCorasick::new(patterns)                    :243   acb200::AhoCorasick::create(patterns)
+//   AhoCorasick::builder()                        :268   acb200::AhoCorasick::builder()
+//   AhoCorasickBuilder::{match_kind, start_kind,          acb200::AhoCorasickBuilder (same knobs,
+//     ascii_case_insensitive, kind, prefilter,              same defaults)
+//     dense_depth, byte_classes, build}      :2171-2616
+//   find / try_find / is_match           :311, 404, 1021   find / try_find / is_match
+//   find_iter / try_find_iter                 :562, 1275   find_iter / try_find_iter
+//   find_overlapping_iter / try_...           :609, 1350   find_overlapping_iter / try_...
+//   kind, start_kind, match_kind, min/max_pattern_len,     same names
+//     patterns_len, memory_usage              :1867-2021
+//   Match { pattern(), start(), end(), span(), ... }       acb200::Match (src/util/search.rs:825-1000)
+//   Input { span, anchored, earliest }   search.rs:83-88   acb200::Input
+//   MatchError / BuildError          src/util/error.rs     acb200::MatchError / acb200::BuildError
+//
+// The `find_*` methods panic in the reference where the `try_*` methods return Err; here `find_*`
+// throw the same exception the `try_*` variants report through acb200::Result.  Iterators are
+// cursors over the materialised, already ordered match list (the device scan is eager; results are
+// identical to the reference's lazy iteration).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <utility>
+#include <vector>
+
+#include "acb200.h"
+
+namespace acb200 {
+
+enum class MatchKind : int { Standard = ACG_STANDARD, LeftmostFirst = ACG_LEFTMOST_FIRST, LeftmostLongest = ACG_LEFTMOST_LONGEST };
+enum class StartKind : int { Unanchored = ACG_START_UNANCHORED, Anchored = ACG_START_ANCHORED, Both = ACG_START_BOTH };
+enum class AhoCorasickKind : int { NoncontiguousNFA = ACG_KIND_NONCONTIGUOUS_NFA, ContiguousNFA = ACG_KIND_CONTIGUOUS_NFA, DFA = ACG_KIND_DFA };
+enum class Anchored : int { No = 0, Yes = 1 };
+
+// src/util/error.rs:23-49
+class BuildError : public std::runtime_error {
+ public:
+  explicit BuildError(int code) : std::runtime_error(acg_strerror(code)), code_(code) {}
+  int code() const { return code_; }
+ private:
+  int code_;
+};
+
+// src/util/error.rs:140-223
+enum class MatchErrorKind { InvalidInputAnchored, InvalidInputUnanchored, UnsupportedStream, UnsupportedOverlapping, UnsupportedEmpty, Boundary };
+class MatchError : public std::runtime_error {
+ public:
+  explicit MatchError(int code) : std::runtime_error(acg_strerror(code)), code_(code) {}
+  int code() const { return code_; }
+  MatchErrorKind kind() const {
+    switch (code_) {
+      case ACG_E_INVALID_INPUT_ANCHORED: return MatchErrorKind::InvalidInputAnchored;
+      case ACG_E_INVALID_INPUT_UNANCHORED: return MatchErrorKind::InvalidInputUnanchored;
+      case ACG_E_UNSUPPORTED_STREAM: return MatchErrorKind::UnsupportedStream;
+      case ACG_E_UNSUPPORTED_OVERLAPPING: return MatchErrorKind::UnsupportedOverlapping;
+      case ACG_E_UNSUPPORTED_EMPTY: return MatchErrorKind::UnsupportedEmpty;
+      default: return MatchErrorKind::Boundary;
+    }
+  }
+ private:
+  int code_;
+};
+// device / boundary failures (no CPU fallback exists)
+class DeviceError : public std::runtime_error {
+ public:
+  explicit DeviceError(int code) : std::runtime_error(acg_strerror(code)), code_(code) {}
+  int code() const { return code_; }
+ private:
+  int code_;
+};
+
+// `Match`, src/util/search.rs:825-1000
+class Match {
+ public:
+  Match() = default;
+  Match(uint32_t pid, uint64_t start, uint64_t end) : pid_(pid), start_(start), end_(end) {}
+  uint32_t pattern() const { return pid_; }
+  uint64_t start() const { return start_; }
+  uint64_t end() const { return end_; }
+  std::pair<uint64_t, uint64_t> span() const { return {start_, end_}; }
+  uint64_t len() const { return end_ - start_; }
+  bool is_empty() const { return start_ == end_; }
+  bool operator==(const Match& o) const { return pid_ == o.pid_ && start_ == o.start_ && end_ == o.end_; }
+ private:
+  uint32_t pid_ = 0;
+  uint64_t start_ = 0, end_ = 0;
+};
+
+// `Input`, src/util/search.rs:83-88, builder-style setters :148-330
+class Input {
+ public:
+  // implicit on purpose, like `impl<'h, H: AsRef<[u8]>> From<&'h H> for Input<'h>` (search.rs:656)
+  Input(std::string_view haystack) : hay_(haystack), start_(0), end_(haystack.size()) {}  // NOLINT
+  Input(const std::string& haystack) : Input(std::string_view(haystack)) {}                // NOLINT
+  Input(const char* haystack) : Input(std::string_view(haystack)) {}                       // NOLINT
+  Input(const uint8_t* p, size_t n) : hay_(reinterpret_cast<const char*>(p), n), start_(0), end_(n) {}
+  Input& span(uint64_t start, uint64_t end) { start_ = start; end_ = end; return *this; }
+  Input& range(uint64_t start, uint64_t end) { return span(start, end); }
+  Input& anchored(Anchored a) { anchored_ = a; return *this; }
+  Input& earliest(bool yes) { earliest_ = yes; return *this; }
+  std::string_view haystack() const { return hay_; }
+  uint64_t start() const { return start_; }
+  uint64_t end() const { return end_; }
+  Anchored get_anchored() const { return anchored_; }
+  bool get_earliest() const { return earliest_; }
+ private:
+  std::string_view hay_;
+  uint64_t start_, end_;
+  Anchored anchored_ = Anchored::No;
+  bool earliest_ = false;
+};
+
+template <class T>
+struct Result {  // Result<T, MatchError>
+  T value{};
+  int error = 0;
+  bool is_ok() const { return error == 0; }
+  bool is_err() const { return error != 0; }
+  T& unwrap() {
+    if (error) throw_error(error);
+    return value;
+  }
+  static void throw_error(int e) {
+    if (e <= ACG_E_INVALID_INPUT_ANCHORED && e >= ACG_E_UNSUPPORTED_EMPTY) throw MatchError(e);
+    if (e == ACG_E_INVALID_SPAN) throw std::out_of_range(acg_strerror(e));  // the reference panics
+    throw DeviceError(e);
+  }
+};
+
+// FindIter / FindOverlappingIter (src/automaton.rs:844-970): cursor over the ordered matches.
+class MatchIter {
+ public:
+  MatchIter() = default;
+  explicit MatchIter(std::vector<Match> m) : m_(std::move(m)) {}
+  // Iterator::next -> Option<Match>
+  bool next(Match* out) {
+    if (i_ >= m_.size()) return false;
+    *out = m_[i_++];
+    return true;
+  }
+  std::vector<Match>::const_iterator begin() const { return m_.begin(); }
+  std::vector<Match>::const_iterator end() const { return m_.end(); }
+  size_t count() const { return m_.size(); }
+  const std::vector<Match>& collect() const { return m_; }
+ private:
+  std::vector<Match> m_;
+  size_t i_ = 0;
+};
+using FindIter = MatchIter;
+using FindOverlappingIter = MatchIter;
+
+class AhoCorasick;
+
+// `AhoCorasickBuilder`, src/ahocorasick.rs:2135-2617
+class AhoCorasickBuilder {
+ public:
+  AhoCorasickBuilder() { acg_build_opts_default(&o_); }
+  AhoCorasickBuilder& match_kind(MatchKind k) { o_.match_kind = int(k); return *this; }
+  AhoCorasickBuilder& start_kind(StartKind k) { o_.start_kind = int(k); return *this; }
+  AhoCorasickBuilder& ascii_case_insensitive(bool yes) { o_.ascii_case_insensitive = yes; return *this; }
+  AhoCorasickBuilder& kind(AhoCorasickKind k) { o_.kind = int(k); return *this; }
+  AhoCorasickBuilder& kind_auto() { o_.kind = ACG_KIND_AUTO; return *this; }  // kind(None)
+  AhoCorasickBuilder& prefilter(bool yes) { o_.prefilter = yes; return *this; }
+  AhoCorasickBuilder& dense_depth(uint64_t d) { o_.dense_depth = int64_t(d); return *this; }
+  AhoCorasickBuilder& byte_classes(bool yes) { o_.byte_classes = yes; return *this; }
+  template <class Patterns>
+  AhoCorasick build(const Patterns& patterns) const;
+ private:
+  acg_build_opts o_;
+};
+
+// `AhoCorasick`, src/ahocorasick.rs:177-2082 (search surface)
+class AhoCorasick {
+ public:
+  AhoCorasick() = default;
+  AhoCorasick(AhoCorasick&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  AhoCorasick& operator=(AhoCorasick&& o) noexcept {
+    if (this != &o) { reset(); h_ = o.h_; o.h_ = nullptr; }
+    return *this;
+  }
+  AhoCorasick(const AhoCorasick&) = delete;
+  AhoCorasick& operator=(const AhoCorasick&) = delete;
+  ~AhoCorasick() { reset(); }
+
+  template <class Patterns>
+  static AhoCorasick create(const Patterns& patterns) { return AhoCorasickBuilder().build(patterns); }  // ::new
+  static AhoCorasickBuilder builder() { return AhoCorasickBuilder(); }
+
+  AhoCorasickKind kind() const { return AhoCorasickKind(acg_kind(h_)); }
+  StartKind start_kind() const { return StartKind(acg_start_kind(h_)); }
+  MatchKind match_kind() const { return MatchKind(acg_match_kind(h_)); }
+  uint64_t min_pattern_len() const { return acg_min_pattern_len(h_); }
+  uint64_t max_pattern_len() const { return acg_max_pattern_len(h_); }
+  uint64_t patterns_len() const { return acg_patterns_len(h_); }
+  uint64_t memory_usage() const { return acg_memory_usage(h_); }
+
+  // try_find, src/ahocorasick.rs:1021
+  Result<std::pair<bool, Match>> try_find(const Input& in) const {
+    Result<std::pair<bool, Match>> r;
+    acg_match m{};
+    int found = 0;
+    r.error = acg_find(h_, hay(in), in.haystack().size(), in.start(), in.end(), int(in.get_anchored()),
+                       in.get_earliest(), &m, &found);
+    r.value = {found != 0, Match(m.pid, m.start, m.end)};
+    return r;
+  }
+  // find, :404 (panics in the reference where this throws)
+  bool find(const Input& in, Match* out) const {
+    auto r = try_find(in).unwrap();
+    if (r.first && out) *out = r.second;
+    return r.first;
+  }
+  // is_match, :311
+  bool is_match(const Input& in) const {
+    Input e = in;
+    e.earliest(match_kind() == MatchKind::Standard);  // existence is all that is reported
+    return try_find(e).unwrap().first;
+  }
+  // try_find_iter, :1275
+  Result<FindIter> try_find_iter(const Input& in) const { return collect(acg_find_iter, in); }
+  FindIter find_iter(const Input& in) const { return std::move(try_find_iter(in).unwrap()); }  // :562
+  // try_find_overlapping_iter, :1350
+  Result<FindOverlappingIter> try_find_overlapping_iter(const Input& in) const {
+    return collect(acg_find_overlapping, in);
+  }
+  FindOverlappingIter find_overlapping_iter(const Input& in) const {  // :609
+    return std::move(try_find_overlapping_iter(in).unwrap());
+  }
+
+  acg_dfa* raw() const { return h_; }
+
+ private:
+  friend class AhoCorasickBuilder;
+  explicit AhoCorasick(acg_dfa* h) : h_(h) {}
+  void reset() {
+    if (h_) acg_dfa_free(h_);
+    h_ = nullptr;
+  }
+  static const uint8_t* hay(const Input& in) { return reinterpret_cast<const uint8_t*>(in.haystack().data()); }
+  using SearchFn = int (*)(const acg_dfa*, const uint8_t*, uint64_t, uint64_t, uint64_t, int, acg_match*, uint64_t, uint64_t*);
+  Result<MatchIter> collect(SearchFn fn, const Input& in) const {
+    Result<MatchIter> r;
+    std::vector<acg_match> buf(cap_hint_);
+    uint64_t n = 0;
+    for (;;) {
+      int rc = fn(h_, hay(in), in.haystack().size(), in.start(), in.end(), int(in.get_anchored()), buf.data(),
+                  buf.size(), &n);
+      if (rc == ACG_E_OVERFLOW) {  // two-call protocol: n is the required count
+        cap_hint_ = n + n / 8 + 64;
+        buf.resize(cap_hint_);
+        continue;
+      }
+      r.error = rc;
+      break;
+    }
+    if (r.error == 0) {
+      std::vector<Match> out;
+      out.reserve(n);
+      for (uint64_t i = 0; i < n; ++i) out.emplace_back(buf[i].pid, buf[i].start, buf[i].end);
+      r.value = MatchIter(std::move(out));
+    }
+    return r;
+  }
+  acg_dfa* h_ = nullptr;
+  mutable uint64_t cap_hint_ = 4096;
+};
+
+template <class Patterns>
+AhoCorasick AhoCorasickBuilder::build(const Patterns& patterns) const {
+  std::vector<const uint8_t*> ptrs;
+  std::vector<uint64_t> lens;
+  for (const auto& p : patterns) {
+    std::string_view v(p);
+    ptrs.push_back(reinterpret_cast<const uint8_t*>(v.data()));
+    lens.push_back(v.size());
+  }
+  acg_dfa* h = nullptr;
+  int rc = acg_build(ptrs.data(), lens.data(), ptrs.size(), &o_, &h);
+  if (rc == ACG_E_STATE_ID_OVERFLOW || rc == ACG_E_PATTERN_ID_OVERFLOW || rc == ACG_E_PATTERN_TOO_LONG)
+    throw BuildError(rc);
+  if (rc) throw DeviceError(rc);
+  return AhoCorasick(h);
+}
+
+}  // namespace acb200

@@ -355,3 +355,56 @@ def test_find_far_match_multi_window():
     hay[(1 << 20) - 3: (1 << 20) + 13] = np.frombuffer(pats[0], dtype=np.uint8)
     ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
     assert ac.try_find(hay).as_tuple() == O.Oracle(pats, kind=O.KIND_DFA).try_find(hay)
+
+
+def _apply(hay: bytes, matches, reps):
+    out, last = bytearray(), 0
+    for pid, s, e in matches:
+        out += hay[last:s] + reps[pid]
+        last = e
+    return bytes(out + hay[last:])
+
+
+def test_replace_all_and_stream():
+    """replace_all* / stream_find_iter are host glue over find_iter (SURVEY.md section 8f.3);
+    examples from src/ahocorasick.rs:651-760 and the stream rows of src/tests.rs:999-1036."""
+    import io
+    pats = [b"append", b"appendage", b"app"]
+    hay = b"append the app to the appendage"
+    assert build(pats, 1).replace_all(hay.decode(), ["x", "y", "z"]) == "x the z to the xage"
+    assert build(pats, 2).replace_all_bytes(hay, [b"x", b"y", b"z"]) == b"x the z to the yage"
+    ac = build(pats, 1)
+    dst = bytearray()
+    ac.replace_all_with(hay, dst, lambda m, txt, out: (out.extend(txt.upper()), m.pattern() != 2)[1])
+    assert bytes(dst) == b"APPEND the APP to the appendage"   # stops after the first "app"
+    with pytest.raises(ValueError):
+        ac.replace_all_bytes(hay, [b"x"])
+    # stream search == find_iter of the whole stream, for every Standard vector without empty patterns
+    for t in G.collection(AC, "AC_STANDARD_NON_OVERLAPPING"):
+        if any(len(p) == 0 for p in t["patterns"]):
+            continue
+        ac = build(t["patterns"], 0, kind=ab.AhoCorasickKind.DFA)
+        for chunk in (1, 2, 3, 7, 64 << 20):
+            got = [m.as_tuple() for m in ac.stream_find_iter(io.BytesIO(t["haystack"]), chunk_bytes=chunk)]
+            assert got == t["matches"], (t["name"], chunk)
+    # unsupported configurations, src/automaton.rs:1087-1103
+    with pytest.raises(ab.MatchError) as e:
+        list(build([b"a"], 1).stream_find_iter(io.BytesIO(b"a")))
+    assert e.value.kind == "UnsupportedStream"
+    with pytest.raises(ab.MatchError) as e:
+        list(build([b"a", b""], 0).stream_find_iter(io.BytesIO(b"a")))
+    assert e.value.kind == "UnsupportedEmpty"
+    # a larger stream with matches that straddle block boundaries, against the oracle
+    pats2 = W.make_patterns(200, 77)
+    t = np.empty(3 << 20, dtype=np.uint8)
+    W.fill_haystack(t, 99)
+    W.plant(t, pats2, 5, period=512, window=256)
+    o = O.Oracle(pats2, kind=O.KIND_DFA)
+    ac = build(pats2, 0, kind=ab.AhoCorasickKind.DFA)
+    want = o.find_iter(t)
+    got = [m.as_tuple() for m in ac.stream_find_iter(io.BytesIO(t.tobytes()), chunk_bytes=(1 << 18) + 13)]
+    assert got == want and len(want) > 5000
+    out = io.BytesIO()
+    reps = [b"<%d>" % i for i in range(len(pats2))]
+    ac.try_stream_replace_all(io.BytesIO(t.tobytes()), out, reps, chunk_bytes=1 << 19)
+    assert out.getvalue() == _apply(t.tobytes(), want, reps)
