@@ -408,3 +408,40 @@ def test_replace_all_and_stream():
     reps = [b"<%d>" % i for i in range(len(pats2))]
     ac.try_stream_replace_all(io.BytesIO(t.tobytes()), out, reps, chunk_bytes=1 << 19)
     assert out.getvalue() == _apply(t.tobytes(), want, reps)
+
+
+def test_dense_outputs_and_unselective_fingerprints():
+    """Stress the slow paths: (1) far more matches than the initial tuple capacity (counter
+    overflow -> regrow -> rescan), (2) pattern sets whose fingerprints cannot be selective (every
+    byte starts a pattern: the kernel verifies every position), (3) steps with more first-probe
+    hits than the compaction slots."""
+    # (1) 3 matches per position on 2 MiB of 'a'  => ~6.3 M tuples
+    pats = [b"a", b"aa", b"aaa"]
+    hay = np.full(2 << 20, ord("a"), dtype=np.uint8)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    for engine in OVERLAPPING_ENGINES:
+        ac = build(pats, 0, engine=engine, kind=ab.AhoCorasickKind.DFA)
+        got = ac.try_find_overlapping_iter_np(hay)
+        assert len(got) == 3 * hay.size - 3
+        assert_np_equal(got, o.find_overlapping_iter_np(hay), engine)
+    for kind in (0, 1, 2):
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA)
+        assert_np_equal(ac.try_find_iter_np(hay), O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA).find_iter_np(hay), kind)
+    # (2) all 256 single bytes + a few longer patterns
+    pats = [bytes([b]) for b in range(256)] + [b"abc", b"\x00\x01\x02\x03", b"zz"]
+    rng = np.random.default_rng(5)
+    hay = rng.integers(0, 256, size=300000, dtype=np.uint8)
+    hay[1000:1003] = np.frombuffer(b"abc", dtype=np.uint8)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    assert_np_equal(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay))
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    assert ac.last_stats()["candidates"] >= hay.size - 64   # every position was verified
+    for kind in (1, 2):
+        ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA)
+        assert_np_equal(ac.try_find_iter_np(hay), O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA).find_iter_np(hay))
+    # (3) 4-byte fingerprints that hit at every position of a periodic haystack
+    pats = [b"abababab", b"babababa", b"abab"]
+    hay = np.frombuffer(b"ab" * 200000, dtype=np.uint8)
+    ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
+    assert_np_equal(ac.try_find_overlapping_iter_np(hay), O.Oracle(pats, kind=O.KIND_DFA).find_overlapping_iter_np(hay))
