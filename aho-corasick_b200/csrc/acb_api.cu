@@ -61,6 +61,7 @@ struct Workspace {
 struct PrefilterPlan {
   bool supported = false;
   uint32_t k = 0, kmask = 0, fold = 0, mult = 1, shift = 0, log_bits = 0;
+  uint32_t stride = 1;
   bool brute = false;
   uint32_t dup_shift = 0;
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
@@ -249,6 +250,39 @@ void derive_metadata(acg_dfa* a) {
   if (pf.k == 0) return;
   pf.brute = pf.fill > 0.25;
   pf.supported = true;
+  // Stride-2 first stage: with 4-byte fingerprints and patterns of at least 4 bytes, probing only
+  // every other offset with the 3-byte fingerprints of pattern bytes [0,3) and [1,4) still sees
+  // every occurrence (a pattern that starts at an odd offset shows its second fingerprint at the
+  // next even one) and halves the per-position probe work.  Worth it while those 3-grams stay rare.
+  if (!pf.brute && pf.k == 4 && best_set.size() <= 8192) {
+    std::vector<uint32_t> g3;
+    g3.reserve(best_set.size() * 2);
+    const uint32_t f3 = pf.fold & 0x00FFFFFFu;
+    for (uint32_t g : best_set) {
+      g3.push_back((g & 0x00FFFFFFu) | f3);
+      g3.push_back((g >> 8) | f3);
+    }
+    std::sort(g3.begin(), g3.end());
+    g3.erase(std::unique(g3.begin(), g3.end()), g3.end());
+    double space = 1.0;
+    for (uint32_t j = 0; j < 3; ++j) {
+      bool seen[256] = {false};
+      unsigned distinct = 0;
+      for (uint32_t g : g3) { const uint32_t b = (g >> (8 * j)) & 0xFF; if (!seen[b]) { seen[b] = true; ++distinct; } }
+      space *= double(std::max(distinct, 1u));
+    }
+    const double bits = double(uint64_t(1) << pf.log_bits);
+    const double fill1 = (double(g3.size()) + 2.0 * double(best_set.size())) / bits;
+    const double pass1 = fill1 + double(g3.size()) / space;  // per probed offset
+    if (pass1 < 0.10) {
+      pf.stride = 2;
+      for (uint32_t g : g3) {
+        const uint32_t hsh = g * pf.mult;
+        const uint32_t byte = hsh >> pf.shift, bit = byte * 8 + (hsh & 7);
+        pf.bitmap[bit >> 5] |= 1u << (bit & 31);
+      }
+    }
+  }
   (void)best_fp;
   if (!pf.brute && best_set.size() > 8192) {
     // the shared-memory Bloom filter lets through more than 0.1 % false positives (many
@@ -480,6 +514,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.bitmap = a->d_bitmap;
   p.log_bits = pf.log_bits;
   p.k = pf.k;
+  p.stride = pf.stride;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;

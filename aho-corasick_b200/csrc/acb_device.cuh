@@ -77,6 +77,8 @@ struct PrefilterLaunch {
   const uint32_t* bitmap;       // global copy, staged into shared memory per CTA
   uint32_t log_bits;            // bitmap size = 1 << log_bits bits
   uint32_t k;                   // fingerprint length in bytes (1..4), <= min_pattern_len
+  uint32_t stride;              // 1: probe every offset with the k-gram; 2: probe even offsets with
+                                // 3-byte fingerprints of pattern bytes [0,3) and [1,4) (k == 4 only)
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult

@@ -174,9 +174,10 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-template <int MODE, bool MASKED, bool DENSE>
+template <int MODE, bool MASKED, bool DENSE, int STRIDE>
 __global__ void __launch_bounds__(kPfThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
+  static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
@@ -203,11 +204,14 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   unsigned long long cand_total = 0;
 
   // head / tail positions outside the aligned filter region are unconditional candidates
+  // (with stride 2 the last probe of the region is at region_hi-2 and covers the starts
+  // region_hi-3 and region_hi-2, so region_hi-1 joins the tail)
   if (blockIdx.x == 0) {
+    const uint64_t tail_lo = (p.region_hi > p.region_lo && !p.brute) ? p.region_hi - (STRIDE - 1) : p.region_hi;
     const uint64_t head_n = p.region_lo - p.scan_lo;
-    const uint64_t tail_n = p.scan_hi > p.region_hi ? p.scan_hi - p.region_hi : 0;
+    const uint64_t tail_n = p.scan_hi > tail_lo ? p.scan_hi - tail_lo : 0;
     for (uint64_t i = tid; i < head_n + tail_n; i += kPfThreads) {
-      const uint64_t s = i < head_n ? p.scan_lo + i : p.region_hi + (i - head_n);
+      const uint64_t s = i < head_n ? p.scan_lo + i : tail_lo + (i - head_n);
       verify_at<MODE>(d, p, s_cls, s, em);
     }
   }
@@ -227,6 +231,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   }
 
   const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
+  const uint32_t fold1 = p.fold & 0x00FFFFFFu;  // stride 2: the first stage fingerprints 3 bytes
+  // queue offsets are relative to chunk_base: a stride-2 probe at the first byte of the chunk
+  // also owns the start one byte before it
+  const uint64_t chunk_base = chunk_lo - (uint64_t)(STRIDE - 1) * (chunk_lo > 0 ? 1 : 0);
+  const uint32_t rel_bias = (uint32_t)(chunk_lo - chunk_base);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   unsigned char* ring = s_ring + warp * (kPfStages * kPfStageBytes);
   uint64_t* bars = s_bars + warp * kPfStages;
@@ -261,7 +270,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       }
       q2len = w;
     }
-    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_lo + q2_off(q2[i]), em);
+    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_base + q2_off(q2[i]), em);
     cand_total += q2len;
     q2len = 0;
     __syncwarp();
@@ -304,22 +313,42 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     }
     const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = nxa;
     const uint32_t x0 = vb.x, x1 = vb.y, x2 = vb.z, x3 = vb.w, x4 = nxb;
-    uint32_t mask = 0;  // bit o (<16): position 16L+o; bit 16+o: position 512+16L+o of the tile
-#define ACB_GRAM(o, lo, hi) (MASKED ? (((((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)) | fold) & kmask) \
-                                    : (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo)))
+    // hit mask of this lane.  Stride 1: bit o (<16) = position 16L+o, bit 16+o = position
+    // 512+16L+o of the tile.  Stride 2: only even offsets are probed (3-byte fingerprints of the
+    // pattern bytes [0,3) and [1,4): a pattern starting at an odd offset is caught by its second
+    // fingerprint at the next even offset); bit i (<8) = offset 2i of the first group, bit 8+i =
+    // offset 2i of the second group.
+    uint32_t mask = 0;
+#define ACB_WIN(o, lo, hi) (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo))
+#define ACB_GRAM(o, lo, hi) (STRIDE == 2 ? ((MASKED ? (ACB_WIN(o, lo, hi) | fold1) : ACB_WIN(o, lo, hi)) & 0x00FFFFFFu) \
+                                         : (MASKED ? ((ACB_WIN(o, lo, hi) | fold) & kmask) : ACB_WIN(o, lo, hi)))
 #define ACB_PROBE(o, lo, hi)                                                                  \
   do {                                                                                        \
     const uint32_t h = ACB_GRAM(o, lo, hi) * mult;                                            \
     const uint32_t rep = (uint32_t)s_bytes[h >> bshift] * 0x01010101u;                        \
     mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, h), 1);                            \
   } while (0)
+    if constexpr (STRIDE == 1) {
 #define ACB_PROBE4(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 1, lo, hi); ACB_PROBE(o + 2, lo, hi); ACB_PROBE(o + 3, lo, hi)
-    ACB_PROBE4(0, w0, w1); ACB_PROBE4(4, w1, w2); ACB_PROBE4(8, w2, w3); ACB_PROBE4(12, w3, w4);
-    ACB_PROBE4(16, x0, x1); ACB_PROBE4(20, x1, x2); ACB_PROBE4(24, x2, x3); ACB_PROBE4(28, x3, x4);
+      ACB_PROBE4(0, w0, w1); ACB_PROBE4(4, w1, w2); ACB_PROBE4(8, w2, w3); ACB_PROBE4(12, w3, w4);
+      ACB_PROBE4(16, x0, x1); ACB_PROBE4(20, x1, x2); ACB_PROBE4(24, x2, x3); ACB_PROBE4(28, x3, x4);
 #undef ACB_PROBE4
+      mask &= (va_ok ? 0x0000FFFFu : 0u) | (vb_ok ? 0xFFFF0000u : 0u);
+    } else {
+#define ACB_PROBE2(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 2, lo, hi)
+      ACB_PROBE2(0, w0, w1); ACB_PROBE2(4, w1, w2); ACB_PROBE2(8, w2, w3); ACB_PROBE2(12, w3, w4);
+      ACB_PROBE2(16, x0, x1); ACB_PROBE2(20, x1, x2); ACB_PROBE2(24, x2, x3); ACB_PROBE2(28, x3, x4);
+#undef ACB_PROBE2
+      mask = (mask >> 16) & ((va_ok ? 0x00FFu : 0u) | (vb_ok ? 0xFF00u : 0u));
+    }
 #undef ACB_PROBE
 #undef ACB_GRAM
-    mask &= (va_ok ? 0x0000FFFFu : 0u) | (vb_ok ? 0xFFFF0000u : 0u);
+#undef ACB_WIN
+    // tile offset of hit bit `b` of this lane
+    auto hit_offset = [&](int b) -> uint32_t {
+      if constexpr (STRIDE == 1) return b < 16 ? lane * 16 + b : 512 + lane * 16 + (b - 16);
+      else return b < 8 ? lane * 16 + 2 * b : 512 + lane * 16 + 2 * (b - 8);
+    };
     // slot allocation for this step's first-probe hits without touching shared memory: the
     // per-lane counts (almost always < 8) are summed across the warp bit plane by bit plane with
     // ballots; a lane with more hits than the planes cover sends the step down the unselective path
@@ -337,42 +366,60 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     if (total) {
       if (total > (uint32_t)kPfSlots) {
         // fingerprints not selective here: verify this step's hits in place
+        uint32_t nver = 0;
         while (mask) {
-          const int o = __ffs(mask) - 1;
+          const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          verify_at<MODE>(d, p, s_cls, wbase + (o < 16 ? lane * 16 + o : 512 + lane * 16 + (o - 16)), em);
+          const uint64_t e = wbase + hit_offset(b);
+#pragma unroll
+          for (int j = 0; j < STRIDE; ++j)
+            if (e >= p.region_lo + j) { verify_at<MODE>(d, p, s_cls, e - j, em); ++nver; }
         }
-        cand_total += __reduce_add_sync(0xffffffffu, cnt);
+        cand_total += __reduce_add_sync(0xffffffffu, nver);
       } else {
         while (mask) {
-          const int o = __ffs(mask) - 1;
+          const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          slots[slot++] = (uint16_t)(o < 16 ? lane * 16 + o : 512 + lane * 16 + (o - 16));
+          slots[slot++] = (uint16_t)hit_offset(b);
         }
         __syncwarp();
-        // second Bloom probe, compacted: lane t handles hit t of this step; the fingerprint is
-        // re-read from the staged tile
-        const uint32_t wrel = (uint32_t)(wbase - chunk_lo);
+        // second stage, compacted: lane t handles hit t of this step.  Every start offset the
+        // hit owns (the probed offset and, with stride 2, the one before it) is tested with two
+        // Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
+        const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
         for (uint32_t base = 0; base < total; base += 32) {
           const uint32_t t = base + lane;
-          bool pass = false;
-          uint32_t e = 0, gram_keep = 0;
-          if (t < total) {
-            e = slots[t];
-            const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (e & ~3u));
-            uint32_t gram = __funnelshift_r(sc[0], sc[1], (e & 3) * 8);
-            if (MASKED) gram = (gram | fold) & kmask;
-            gram_keep = gram;
-            pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
-          }
-          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-          if (bal) {
-            if (pass) {
-              if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(wrel + e, gram_keep);
-              else q2[q2len + __popc(bal & ((1u << lane) - 1))] = wrel + e;
+          const uint32_t e = t < total ? slots[t] : 0u;
+#pragma unroll
+          for (int j = 0; j < STRIDE; ++j) {
+            bool pass = false;
+            uint32_t gram_keep = 0;
+            if (t < total && wbase + e >= p.region_lo + j) {
+              uint32_t gram;
+              if (STRIDE == 1 || e >= (uint32_t)j) {
+                const uint32_t off = e - j;
+                const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (off & ~3u));
+                gram = __funnelshift_r(sc[0], sc[1], (off & 3) * 8);
+              } else {  // the start lies one byte before the tile: fetch from global memory
+                const uint8_t* a = p.hay + wbase + e - j;
+                gram = (uint32_t)__ldg(a) | ((uint32_t)__ldg(a + 1) << 8) | ((uint32_t)__ldg(a + 2) << 16) |
+                       ((uint32_t)__ldg(a + 3) << 24);
+              }
+              if (MASKED) gram = (gram | fold) & kmask;
+              gram_keep = gram;
+              pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
+              if (STRIDE == 2) pass = pass && bloom_test(s_bitmap, gram * mult, bshift);
             }
-            q2len += __popc(bal);
-            if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+              const uint32_t rel = wrel + e - j;
+              if (pass) {
+                if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(rel, gram_keep);
+                else q2[q2len + __popc(bal & ((1u << lane) - 1))] = rel;
+              }
+              q2len += __popc(bal);
+              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            }
           }
         }
       }
@@ -440,12 +487,14 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
-  static const KernT table[2][2][2] = {
-      {{prefilter_kernel<0, false, false>, prefilter_kernel<0, false, true>},
-       {prefilter_kernel<0, true, false>, prefilter_kernel<0, true, true>}},
-      {{prefilter_kernel<1, false, false>, prefilter_kernel<1, false, true>},
-       {prefilter_kernel<1, true, false>, prefilter_kernel<1, true, true>}}};
-  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][dense ? 1 : 0];
+  // [mode][masked][dense + 2*(stride==2)]; stride 2 is never combined with the dense variant
+  static const KernT table[2][2][3] = {
+      {{prefilter_kernel<0, false, false, 1>, prefilter_kernel<0, false, true, 1>, prefilter_kernel<0, false, false, 2>},
+       {prefilter_kernel<0, true, false, 1>, prefilter_kernel<0, true, true, 1>, prefilter_kernel<0, true, false, 2>}},
+      {{prefilter_kernel<1, false, false, 1>, prefilter_kernel<1, false, true, 1>, prefilter_kernel<1, false, false, 2>},
+       {prefilter_kernel<1, true, false, 1>, prefilter_kernel<1, true, true, 1>, prefilter_kernel<1, true, false, 2>}}};
+  if (p.stride == 2 && dense) return cudaErrorInvalidValue;
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.stride == 2 ? 2 : (dense ? 1 : 0)];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
