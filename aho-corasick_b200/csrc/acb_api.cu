@@ -274,7 +274,7 @@ void derive_metadata(acg_dfa* a) {
     const double bits = double(uint64_t(1) << pf.log_bits);
     const double fill1 = (double(g3.size()) + 2.0 * double(best_set.size())) / bits;
     const double pass1 = fill1 + double(g3.size()) / space;  // per probed offset
-    if (pass1 < 0.10) {
+    if (pass1 < 0.04) {
       pf.stride = 2;
       for (uint32_t g : g3) {
         const uint32_t hsh = g * pf.mult;
