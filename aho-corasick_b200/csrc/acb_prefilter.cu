@@ -303,14 +303,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     const bool va_ok = (uint32_t)lane * 16 < valid, vb_ok = 512u + (uint32_t)lane * 16 < valid;
     const uint4 va = *reinterpret_cast<const uint4*>(tile + lane * 16);
     const uint4 vb = *reinterpret_cast<const uint4*>(tile + 512 + lane * 16);
-    // look-ahead words: the next lane's first word; lane 31 continues at byte 512 / 1024
-    uint32_t nxa = __shfl_down_sync(0xffffffffu, va.x, 1);
-    uint32_t nxb = __shfl_down_sync(0xffffffffu, vb.x, 1);
-    const uint32_t vb0 = __shfl_sync(0xffffffffu, vb.x, 0);
-    if (lane == 31) {
-      nxa = vb0;
-      nxb = *reinterpret_cast<const uint32_t*>(tile + kPfTile);
-    }
+    // look-ahead words (the 4 bytes behind each 16-byte group) straight from the staged tile
+    const uint32_t nxa = *reinterpret_cast<const uint32_t*>(tile + lane * 16 + 16);
+    const uint32_t nxb = *reinterpret_cast<const uint32_t*>(tile + 512 + lane * 16 + 16);
     const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = nxa;
     const uint32_t x0 = vb.x, x1 = vb.y, x2 = vb.z, x3 = vb.w, x4 = nxb;
     // hit mask of this lane.  Stride 1: bit o (<16) = position 16L+o, bit 16+o = position
