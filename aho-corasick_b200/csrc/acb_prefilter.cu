@@ -22,8 +22,17 @@
 namespace acb {
 namespace {
 
-constexpr int kPfThreads = 1024;
-constexpr int kPfWarps = kPfThreads / 32;
+// Kernel geometry per fingerprint stride.  Both variants keep 32 hit bits per lane and step:
+//   stride 1: 1 024 threads, 1 KiB tile per warp step (2 x 16 positions per lane, 32 probes)
+//   stride 2:   512 threads, 2 KiB tile per warp step (4 x 16 positions per lane, 32 probes)
+// so the per-step bookkeeping of the stride-2 variant is spread over twice as many positions.
+template <int STRIDE> struct PfGeom {
+  static constexpr int kThreads = STRIDE == 2 ? 512 : 1024;
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kGroups = STRIDE == 2 ? 4 : 2;   // 16-byte groups per lane and step
+  static constexpr int kTile = kGroups * 512;           // haystack bytes per warp step
+  static constexpr int kStageBytes = kTile + 16;        // + fingerprint look-ahead
+};
 // per-warp queue sizes: first-probe hits of one step handled by the compacted second probe, and
 // verified-candidate entries (the dense variant stores 8-byte entries, so fewer of them fit
 // beside the 128 KiB bitmap)
@@ -64,8 +73,6 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
 
 // ---- TMA (bulk async copy) + mbarrier helpers: global -> shared staging of the haystack ----
 constexpr int kPfStages = 2;            // ring depth per warp
-constexpr int kPfTile = 1024;           // haystack bytes per warp step
-constexpr int kPfStageBytes = kPfTile + 16;  // + fingerprint look-ahead
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -175,9 +182,14 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
 template <int MODE, bool MASKED, bool DENSE, int STRIDE>
-__global__ void __launch_bounds__(kPfThreads, 1)
+__global__ void __launch_bounds__(PfGeom<STRIDE>::kThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
+  constexpr int kPfThreads = PfGeom<STRIDE>::kThreads;
+  constexpr int kPfWarps = PfGeom<STRIDE>::kWarps;
+  constexpr int kPfTile = PfGeom<STRIDE>::kTile;
+  constexpr int kPfStageBytes = PfGeom<STRIDE>::kStageBytes;
+  constexpr int kGroups = PfGeom<STRIDE>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
@@ -300,19 +312,22 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     while (!mbar_try_wait(&bars[stage], parity)) {}
     const unsigned char* tile = ring + stage * kPfStageBytes;
     const uint32_t valid = (uint32_t)min((uint64_t)kPfTile, chunk_hi - wbase);  // multiple of 16
-    const bool va_ok = (uint32_t)lane * 16 < valid, vb_ok = 512u + (uint32_t)lane * 16 < valid;
-    const uint4 va = *reinterpret_cast<const uint4*>(tile + lane * 16);
-    const uint4 vb = *reinterpret_cast<const uint4*>(tile + 512 + lane * 16);
-    // look-ahead words (the 4 bytes behind each 16-byte group) straight from the staged tile
-    const uint32_t nxa = *reinterpret_cast<const uint32_t*>(tile + lane * 16 + 16);
-    const uint32_t nxb = *reinterpret_cast<const uint32_t*>(tile + 512 + lane * 16 + 16);
-    const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w, w4 = nxa;
-    const uint32_t x0 = vb.x, x1 = vb.y, x2 = vb.z, x3 = vb.w, x4 = nxb;
-    // hit mask of this lane.  Stride 1: bit o (<16) = position 16L+o, bit 16+o = position
-    // 512+16L+o of the tile.  Stride 2: only even offsets are probed (3-byte fingerprints of the
-    // pattern bytes [0,3) and [1,4): a pattern starting at an odd offset is caught by its second
-    // fingerprint at the next even offset); bit i (<8) = offset 2i of the first group, bit 8+i =
-    // offset 2i of the second group.
+    // lane L owns the 16-byte groups at tile offsets g*512 + 16L (conflict-free 16-byte reads)
+    uint32_t wv[kGroups][5];
+    uint32_t ok_bits = 0;  // which of the lane's hit bits belong to valid positions
+    constexpr int kBitsPerGroup = 16 / STRIDE;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      const unsigned char* gp = tile + g * 512 + lane * 16;
+      const uint4 v = *reinterpret_cast<const uint4*>(gp);
+      wv[g][0] = v.x; wv[g][1] = v.y; wv[g][2] = v.z; wv[g][3] = v.w;
+      wv[g][4] = *reinterpret_cast<const uint32_t*>(gp + 16);  // look-ahead word behind the group
+      if ((uint32_t)(g * 512 + lane * 16) < valid) ok_bits |= ((1u << kBitsPerGroup) - 1) << (g * kBitsPerGroup);
+    }
+    // hit mask of this lane, kBitsPerGroup bits per group.  Stride 1: bit 16g+o = offset o of
+    // group g.  Stride 2: only even offsets are probed (3-byte fingerprints of the pattern bytes
+    // [0,3) and [1,4): a pattern starting at an odd offset is caught by its second fingerprint at
+    // the next even offset); bit 8g+i = offset 2i of group g.
     uint32_t mask = 0;
 #define ACB_WIN(o, lo, hi) (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo))
 #define ACB_GRAM(o, lo, hi) (STRIDE == 2 ? ((MASKED ? (ACB_WIN(o, lo, hi) | fold1) : ACB_WIN(o, lo, hi)) & 0x00FFFFFFu) \
@@ -323,26 +338,26 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     const uint32_t rep = (uint32_t)s_bytes[h >> bshift] * 0x01010101u;                        \
     mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, h), 1);                            \
   } while (0)
-    if constexpr (STRIDE == 1) {
-#define ACB_PROBE4(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 1, lo, hi); ACB_PROBE(o + 2, lo, hi); ACB_PROBE(o + 3, lo, hi)
-      ACB_PROBE4(0, w0, w1); ACB_PROBE4(4, w1, w2); ACB_PROBE4(8, w2, w3); ACB_PROBE4(12, w3, w4);
-      ACB_PROBE4(16, x0, x1); ACB_PROBE4(20, x1, x2); ACB_PROBE4(24, x2, x3); ACB_PROBE4(28, x3, x4);
-#undef ACB_PROBE4
-      mask &= (va_ok ? 0x0000FFFFu : 0u) | (vb_ok ? 0xFFFF0000u : 0u);
-    } else {
-#define ACB_PROBE2(o, lo, hi) ACB_PROBE(o, lo, hi); ACB_PROBE(o + 2, lo, hi)
-      ACB_PROBE2(0, w0, w1); ACB_PROBE2(4, w1, w2); ACB_PROBE2(8, w2, w3); ACB_PROBE2(12, w3, w4);
-      ACB_PROBE2(16, x0, x1); ACB_PROBE2(20, x1, x2); ACB_PROBE2(24, x2, x3); ACB_PROBE2(28, x3, x4);
-#undef ACB_PROBE2
-      mask = (mask >> 16) & ((va_ok ? 0x00FFu : 0u) | (vb_ok ? 0xFF00u : 0u));
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        if constexpr (STRIDE == 1) {
+          ACB_PROBE(0, wv[g][wi], wv[g][wi + 1]); ACB_PROBE(1, wv[g][wi], wv[g][wi + 1]);
+          ACB_PROBE(2, wv[g][wi], wv[g][wi + 1]); ACB_PROBE(3, wv[g][wi], wv[g][wi + 1]);
+        } else {
+          ACB_PROBE(0, wv[g][wi], wv[g][wi + 1]); ACB_PROBE(2, wv[g][wi], wv[g][wi + 1]);
+        }
+      }
     }
 #undef ACB_PROBE
 #undef ACB_GRAM
 #undef ACB_WIN
+    // 32 probes were funnelled in from the top: the first probe now sits at bit 0
+    mask &= ok_bits;
     // tile offset of hit bit `b` of this lane
     auto hit_offset = [&](int b) -> uint32_t {
-      if constexpr (STRIDE == 1) return b < 16 ? lane * 16 + b : 512 + lane * 16 + (b - 16);
-      else return b < 8 ? lane * 16 + 2 * b : 512 + lane * 16 + 2 * (b - 8);
+      return (uint32_t)((b / kBitsPerGroup) * 512 + lane * 16 + (b % kBitsPerGroup) * STRIDE);
     };
     // slot allocation for this step's first-probe hits without touching shared memory: the
     // per-lane counts (almost always < 8) are summed across the warp bit plane by bit plane with
@@ -476,9 +491,13 @@ struct MaxOp {
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const bool dense = p.gbitmap != nullptr;
-  const size_t smem = size_t(kPfWarps) * (kPfStages * kPfStageBytes + kPfStages * 8 +
-                                          (dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4) +
-                                          (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
+  const int threads = p.stride == 2 ? PfGeom<2>::kThreads : PfGeom<1>::kThreads;
+  const int warps = threads / 32;
+  const int stage_bytes = p.stride == 2 ? PfGeom<2>::kStageBytes : PfGeom<1>::kStageBytes;
+  const int tile = p.stride == 2 ? PfGeom<2>::kTile : PfGeom<1>::kTile;
+  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 +
+                                       (dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4) +
+                                       (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
@@ -493,13 +512,14 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPfThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   uint64_t grid = (uint64_t)sm_count * per_sm;
-  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + (kPfWarps * kPfTile - 1)) / (kPfWarps * kPfTile);
+  const uint64_t cta_step = uint64_t(warps) * tile;
+  const uint64_t warp_steps = ((p.region_hi - p.region_lo) + cta_step - 1) / cta_step;
   if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
-  kern<<<(unsigned)grid, kPfThreads, smem, s>>>(dfa, p);
+  kern<<<(unsigned)grid, threads, smem, s>>>(dfa, p);
   return cudaGetLastError();
 }
 
