@@ -62,6 +62,7 @@ struct PrefilterPlan {
   bool supported = false;
   uint32_t k = 0, kmask = 0, fold = 0, mult = 1, shift = 0, log_bits = 0;
   uint32_t stride = 1;
+  bool wide = false;
   bool brute = false;
   uint32_t dup_shift = 0;
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
@@ -276,6 +277,7 @@ void derive_metadata(acg_dfa* a) {
     const double pass1 = fill1 + double(g3.size()) / space;  // per probed offset
     if (pass1 < 0.04) {
       pf.stride = 2;
+      pf.wide = pass1 < 0.01;  // rare hits: amortise the per-step bookkeeping over 2 KiB tiles
       for (uint32_t g : g3) {
         const uint32_t hsh = g * pf.mult;
         const uint32_t byte = hsh >> pf.shift, bit = byte * 8 + (hsh & 7);
@@ -515,6 +517,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.log_bits = pf.log_bits;
   p.k = pf.k;
   p.stride = pf.stride;
+  p.wide = pf.wide ? 1 : 0;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;

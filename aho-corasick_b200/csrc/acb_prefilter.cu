@@ -22,14 +22,15 @@
 namespace acb {
 namespace {
 
-// Kernel geometry per fingerprint stride.  Both variants keep 32 hit bits per lane and step:
-//   stride 1: 1 024 threads, 1 KiB tile per warp step (2 x 16 positions per lane, 32 probes)
-//   stride 2:   512 threads, 2 KiB tile per warp step (4 x 16 positions per lane, 32 probes)
-// so the per-step bookkeeping of the stride-2 variant is spread over twice as many positions.
-template <int STRIDE> struct PfGeom {
-  static constexpr int kThreads = STRIDE == 2 ? 512 : 1024;
+// Kernel geometry.  NARROW: 1 024 threads, 1 KiB tile per warp step (2 x 16 positions per lane);
+// WIDE (stride 2 only): 512 threads, 2 KiB tile per warp step (4 x 16 positions per lane, 32
+// probes) -- the per-step bookkeeping is spread over twice as many positions, which pays when
+// first-stage hits are rare (few patterns); with frequent hits the 32 resident warps of the
+// narrow geometry hide the latency of the second stage and the verifier better.
+template <bool WIDE> struct PfGeom {
+  static constexpr int kThreads = WIDE ? 512 : 1024;
   static constexpr int kWarps = kThreads / 32;
-  static constexpr int kGroups = STRIDE == 2 ? 4 : 2;   // 16-byte groups per lane and step
+  static constexpr int kGroups = WIDE ? 4 : 2;          // 16-byte groups per lane and step
   static constexpr int kTile = kGroups * 512;           // haystack bytes per warp step
   static constexpr int kStageBytes = kTile + 16;        // + fingerprint look-ahead
 };
@@ -181,15 +182,16 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h,
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-template <int MODE, bool MASKED, bool DENSE, int STRIDE>
-__global__ void __launch_bounds__(PfGeom<STRIDE>::kThreads, 1)
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, bool WIDE>
+__global__ void __launch_bounds__(PfGeom<WIDE>::kThreads, 1)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
-  constexpr int kPfThreads = PfGeom<STRIDE>::kThreads;
-  constexpr int kPfWarps = PfGeom<STRIDE>::kWarps;
-  constexpr int kPfTile = PfGeom<STRIDE>::kTile;
-  constexpr int kPfStageBytes = PfGeom<STRIDE>::kStageBytes;
-  constexpr int kGroups = PfGeom<STRIDE>::kGroups;
+  static_assert(!WIDE || STRIDE == 2, "the wide geometry needs the stride-2 first stage (32 hit bits per lane)");
+  constexpr int kPfThreads = PfGeom<WIDE>::kThreads;
+  constexpr int kPfWarps = PfGeom<WIDE>::kWarps;
+  constexpr int kPfTile = PfGeom<WIDE>::kTile;
+  constexpr int kPfStageBytes = PfGeom<WIDE>::kStageBytes;
+  constexpr int kGroups = PfGeom<WIDE>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
@@ -353,7 +355,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 #undef ACB_PROBE
 #undef ACB_GRAM
 #undef ACB_WIN
-    // 32 probes were funnelled in from the top: the first probe now sits at bit 0
+    // the probes were funnelled in from the top: move the first one down to bit 0
+    constexpr int kHitBits = kGroups * kBitsPerGroup;
+    if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
     mask &= ok_bits;
     // tile offset of hit bit `b` of this lane
     auto hit_offset = [&](int b) -> uint32_t {
@@ -491,24 +495,31 @@ struct MaxOp {
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const bool dense = p.gbitmap != nullptr;
-  const int threads = p.stride == 2 ? PfGeom<2>::kThreads : PfGeom<1>::kThreads;
+  const bool wide_geom = p.stride == 2 && p.wide;
+  const int threads = wide_geom ? PfGeom<true>::kThreads : PfGeom<false>::kThreads;
   const int warps = threads / 32;
-  const int stage_bytes = p.stride == 2 ? PfGeom<2>::kStageBytes : PfGeom<1>::kStageBytes;
-  const int tile = p.stride == 2 ? PfGeom<2>::kTile : PfGeom<1>::kTile;
+  const int stage_bytes = wide_geom ? PfGeom<true>::kStageBytes : PfGeom<false>::kStageBytes;
+  const int tile = wide_geom ? PfGeom<true>::kTile : PfGeom<false>::kTile;
   const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 +
                                        (dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4) +
                                        (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
-  // [mode][masked][dense + 2*(stride==2)]; stride 2 is never combined with the dense variant
-  static const KernT table[2][2][3] = {
-      {{prefilter_kernel<0, false, false, 1>, prefilter_kernel<0, false, true, 1>, prefilter_kernel<0, false, false, 2>},
-       {prefilter_kernel<0, true, false, 1>, prefilter_kernel<0, true, true, 1>, prefilter_kernel<0, true, false, 2>}},
-      {{prefilter_kernel<1, false, false, 1>, prefilter_kernel<1, false, true, 1>, prefilter_kernel<1, false, false, 2>},
-       {prefilter_kernel<1, true, false, 1>, prefilter_kernel<1, true, true, 1>, prefilter_kernel<1, true, false, 2>}}};
+  // [mode][masked][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide
+  // (stride 2 is never combined with the dense variant)
+  static const KernT table[2][2][4] = {
+      {{prefilter_kernel<0, false, false, 1, false>, prefilter_kernel<0, false, true, 1, false>,
+        prefilter_kernel<0, false, false, 2, false>, prefilter_kernel<0, false, false, 2, true>},
+       {prefilter_kernel<0, true, false, 1, false>, prefilter_kernel<0, true, true, 1, false>,
+        prefilter_kernel<0, true, false, 2, false>, prefilter_kernel<0, true, false, 2, true>}},
+      {{prefilter_kernel<1, false, false, 1, false>, prefilter_kernel<1, false, true, 1, false>,
+        prefilter_kernel<1, false, false, 2, false>, prefilter_kernel<1, false, false, 2, true>},
+       {prefilter_kernel<1, true, false, 1, false>, prefilter_kernel<1, true, true, 1, false>,
+        prefilter_kernel<1, true, false, 2, false>, prefilter_kernel<1, true, false, 2, true>}}};
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
-  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.stride == 2 ? 2 : (dense ? 1 : 0)];
+  const bool wide = p.stride == 2 && p.wide;
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.stride == 2 ? (wide ? 3 : 2) : (dense ? 1 : 0)];
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
