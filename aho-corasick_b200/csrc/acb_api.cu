@@ -209,7 +209,7 @@ void derive_metadata(acg_dfa* a) {
     // Bloom bitmap with two hashes (a single multiply for the per-position probe, a full mix
     // for the second probe that only first-probe hits pay for).  Bit position of a hash h: byte
     // from the top (log_bits-3) bits, bit inside the byte from the low 3 bits (little-endian words).
-    const uint32_t log_bits = uint32_t(std::min(20, std::max(13, bits_for(uint64_t(set.size()) * 256 - 1))));
+    const uint32_t log_bits = uint32_t(std::min(20, std::max(17, bits_for(uint64_t(set.size()) * 256 - 1))));
     const uint32_t mult = 0x9E3779B1u;
     const uint32_t shift = 35 - log_bits;
     const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
