@@ -60,7 +60,7 @@ struct Workspace {
 // works for DFAs adopted through acg_dfa_create).
 struct PrefilterPlan {
   bool supported = false;
-  uint32_t k = 0, kmask = 0, fold = 0, mult = 1, shift = 0, log_bits = 0;
+  uint32_t k = 0, kmask = 0, fold = 0, mult = 1, mult3 = 1, shift = 0, log_bits = 0;
   uint32_t stride = 1;
   bool wide = false;
   bool brute = false;
@@ -209,7 +209,8 @@ void derive_metadata(acg_dfa* a) {
     // Bloom bitmap with two hashes (a single multiply for the per-position probe, a full mix
     // for the second probe that only first-probe hits pay for).  Bit position of a hash h: byte
     // from the top (log_bits-3) bits, bit inside the byte from the low 3 bits (little-endian words).
-    const uint32_t log_bits = uint32_t(std::min(20, std::max(17, bits_for(uint64_t(set.size()) * 256 - 1))));
+    // the kernel's bitmap size is a compile-time constant (kBloomLogBits in acb_prefilter.cu)
+    const uint32_t log_bits = 20;
     const uint32_t mult = 0x9E3779B1u;
     const uint32_t shift = 35 - log_bits;
     const uint32_t kmask = k == 4 ? 0xFFFFFFFFu : ((1u << (8 * k)) - 1);
@@ -272,15 +273,66 @@ void derive_metadata(acg_dfa* a) {
       for (uint32_t g : g3) { const uint32_t b = (g >> (8 * j)) & 0xFF; if (!seen[b]) { seen[b] = true; ++distinct; } }
       space *= double(std::max(distinct, 1u));
     }
-    const double bits = double(uint64_t(1) << pf.log_bits);
-    const double fill1 = (double(g3.size()) + 2.0 * double(best_set.size())) / bits;
-    const double pass1 = fill1 + double(g3.size()) / space;  // per probed offset
+    const double n_bits_set = double(g3.size()) + 2.0 * double(best_set.size());
+    const double true3 = double(g3.size()) / space;
+    const double pass1 = n_bits_set / double(uint64_t(1) << pf.log_bits) + true3;  // per probed offset
     if (pass1 < 0.04) {
       pf.stride = 2;
-      pf.wide = pass1 < 0.01;  // rare hits: amortise the per-step bookkeeping over 2 KiB tiles
+      // rare hits even with a 16 KiB bitmap: the wide geometry (2 KiB tiles, two CTAs per SM,
+      // PfBloom<true> in acb_prefilter.cu) amortises the per-step bookkeeping better
+      constexpr uint32_t kWideLogBits = 17;
+      pf.wide = n_bits_set / double(uint64_t(1) << kWideLogBits) + true3 < 0.01;
+      if (pf.wide) {
+        pf.log_bits = kWideLogBits;
+        pf.shift = 35 - kWideLogBits;
+        pf.bitmap.assign(size_t(1) << (kWideLogBits - 5), 0u);
+        auto set_hash = [&](uint32_t hsh) {
+          const uint32_t bit = (hsh >> pf.shift) * 8 + (hsh & 7);
+          pf.bitmap[bit >> 5] |= 1u << (bit & 31);
+        };
+        for (uint32_t g : best_set) {
+          set_hash(g * pf.mult);
+          set_hash(bloom_hash2(g));
+        }
+      }
+      // First-stage probe of the stride-2 kernel: byte index from the 3-byte fingerprint times
+      // (mult3 << 8) -- the shifted multiplier discards the fourth window byte -- and the bit inside
+      // the byte from the fingerprint's own low bits.  A multiplicative hash of such short keys is
+      // sensitive to the constant, so pick the candidate that lets through the fewest fingerprints
+      // drawn from the bytes the patterns use at each position.
+      static const uint32_t kCand[] = {0x1B873593u, 0x27D4EB2Fu, 0x165667B1u, 0x9E3779B1u, 0x2C1B3C6Du,
+                                       0xB5297A4Du, 0x85EBCA6Bu, 0x5BD1E995u, 0x7FEB352Du, 0xCC9E2D51u,
+                                       0x1B56C4E9u, 0xC2B2AE35u};
+      std::vector<uint8_t> alpha[3];
+      for (uint32_t j = 0; j < 3; ++j) {
+        bool seen[256] = {false};
+        for (uint32_t g : g3) seen[(g >> (8 * j)) & 0xFF] = true;
+        for (uint32_t b = 0; b < 256; ++b) if (seen[b]) alpha[j].push_back(uint8_t(b));
+      }
+      auto bit_of = [&](uint32_t g, uint32_t m) -> uint32_t {
+        return ((g * (m << 8)) >> pf.shift) * 8 + (g & 7);
+      };
+      uint32_t best_m = kCand[0];
+      uint64_t best_pass = UINT64_MAX;
+      std::vector<uint32_t> trial;
+      for (uint32_t m : kCand) {
+        trial = pf.bitmap;
+        for (uint32_t g : g3) { const uint32_t bit = bit_of(g, m); trial[bit >> 5] |= 1u << (bit & 31); }
+        uint64_t pass = 0, x = 0x9E3779B97F4A7C15ull;
+        for (int i = 0; i < 65536; ++i) {
+          x = x * 6364136223846793005ull + 1442695040888963407ull;
+          const uint32_t r = uint32_t(x >> 33);
+          const uint32_t g = uint32_t(alpha[0][r % alpha[0].size()]) |
+                             uint32_t(alpha[1][(r >> 10) % alpha[1].size()]) << 8 |
+                             uint32_t(alpha[2][(r >> 20) % alpha[2].size()]) << 16;
+          const uint32_t bit = bit_of(g, m);
+          pass += (trial[bit >> 5] >> (bit & 31)) & 1u;
+        }
+        if (pass < best_pass) { best_pass = pass; best_m = m; }
+      }
+      pf.mult3 = best_m;
       for (uint32_t g : g3) {
-        const uint32_t hsh = g * pf.mult;
-        const uint32_t byte = hsh >> pf.shift, bit = byte * 8 + (hsh & 7);
+        const uint32_t bit = bit_of(g, best_m);
         pf.bitmap[bit >> 5] |= 1u << (bit & 31);
       }
     }
@@ -521,6 +573,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
+  p.mult3 = pf.mult3;
   p.shift = pf.shift;
   p.gbitmap = a->d_gbitmap;
   p.gshift = pf.glog ? 37 - pf.glog : 0;

@@ -83,6 +83,7 @@ struct PrefilterLaunch {
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult
+  uint32_t mult3;               // stride 2: multiplier of the 3-byte first-stage fingerprint
   uint32_t shift;               // hash >> shift = byte offset into the bitmap (= 35 - log_bits)
   const uint32_t* gbitmap;      // optional third-level bitmap in global memory (nullptr: unused)
   uint32_t gshift;              // word index = hash3 >> gshift

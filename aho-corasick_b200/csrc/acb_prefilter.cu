@@ -162,14 +162,24 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
   if (MODE == 1 && best_len) em.emit(((s - p.span_start) << kTieBits) | best_len, best_pid);
 }
 
+// The size of the shared-memory Bloom bitmap is a compile-time property of the kernel geometry,
+// so that the byte index (hash >> shift) and the shared-memory base fold into one address
+// instruction: 2^20 bits (128 KiB) in general; 2^17 bits (16 KiB) for the wide geometry, which is
+// only chosen for small pattern sets and then leaves room for two CTAs per SM.
+template <bool WIDE> struct PfBloom {
+  static constexpr uint32_t kLogBits = WIDE ? 17 : 20;
+  static constexpr uint32_t kShift = 35 - kLogBits;
+};
+
 // Bit position of a 32-bit hash in the Bloom bitmap: the byte comes from the top (log_bits-3)
 // bits, the bit inside the byte from the low 3 bits.  The probe loads that byte, replicates it
 // into all four byte lanes with a multiply (FMA pipe) and rotates by the raw hash (the hardware
 // uses the shift amount mod 32), which puts bit (h & 7) of the byte at bit 0 -- one shift, one
 // byte load, one multiply and one rotate per position, no masking.  Must match set_hash() in
 // acb_api.cu.
-__device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h, uint32_t bshift) {
-  const uint32_t byte = reinterpret_cast<const uint8_t*>(s_bitmap)[h >> bshift];
+template <uint32_t SHIFT>
+__device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h) {
+  const uint32_t byte = reinterpret_cast<const uint8_t*>(s_bitmap)[h >> SHIFT];
   const uint32_t rep = byte * 0x01010101u;  // the rotate below then finds bit (h & 7) at bit 0
   return (__funnelshift_r(rep, rep, h) & 1u) != 0;
 }
@@ -194,6 +204,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   constexpr int kGroups = PfGeom<WIDE>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
+  constexpr uint32_t kBloomShift = PfBloom<WIDE>::kShift;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
@@ -244,8 +255,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     return;
   }
 
-  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult, bshift = p.shift;
+  const uint32_t kmask = p.kmask, fold = p.fold, mult = p.mult;
   const uint32_t fold1 = p.fold & 0x00FFFFFFu;  // stride 2: the first stage fingerprints 3 bytes
+  // stride 2: multiplying by (mult << 8) drops the window's fourth byte for free; the bit inside
+  // the bitmap byte then comes from the fingerprint's own low bits (the product's are zero)
+  const uint32_t mult8 = p.mult3 << 8;
   // queue offsets are relative to chunk_base: a stride-2 probe at the first byte of the chunk
   // also owns the start one byte before it
   const uint64_t chunk_base = chunk_lo - (uint64_t)(STRIDE - 1) * (chunk_lo > 0 ? 1 : 0);
@@ -291,40 +305,50 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   };
 
   // ---- K3 main loop.  Each warp streams its share of the chunk through a two-stage ring of
-  // 1 KiB tiles (+16 B look-ahead) filled by TMA bulk copies (cp.async.bulk, completion on an
+  // tiles (+16 B look-ahead) filled by TMA bulk copies (cp.async.bulk, completion on an
   // mbarrier): no load instructions or address arithmetic per lane, and the next tile is in
-  // flight while the current one is probed.  Lane L owns positions [16L,16L+16) and
-  // [512+16L,512+16L+16) of the tile, so its two 16-byte shared-memory reads are conflict free.
+  // flight while the current one is probed.  Lane L owns the 16-byte groups at tile offsets
+  // g*512 + 16L, so its 16-byte shared-memory reads are conflict free.
   const uint64_t wstride = (uint64_t)kPfWarps * kPfTile;
   const uint64_t wfirst = chunk_lo + (uint64_t)warp * kPfTile;
-  auto issue = [&](uint64_t wb, int stage) {  // lane 0 only
-    const uint32_t valid = (uint32_t)min((uint64_t)kPfTile, chunk_hi - wb);
-    fence_proxy_async();
-    mbar_expect_tx(&bars[stage], valid + 16);
-    tma_load_1d(ring + stage * kPfStageBytes, p.hay + wb, valid + 16, &bars[stage]);
+  // step i of this warp covers [wfirst + i*wstride, +kPfTile) cut at chunk_hi; only the last
+  // step can be short
+  const uint64_t wspan = chunk_hi > wfirst ? chunk_hi - wfirst : 0;
+  const uint32_t n_steps = wspan ? (uint32_t)((wspan - 1) / wstride) + 1 : 0;
+  const uint32_t last_valid = n_steps ? (uint32_t)min((uint64_t)kPfTile, wspan - (uint64_t)(n_steps - 1) * wstride) : 0;
+  const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
+  // Refilling a stage needs no proxy fence: every lane has consumed its shared-memory reads of the
+  // tile (their values fed the probes) before the __syncwarp that precedes the copy.
+  const uint8_t* next_src = p.hay + wfirst;  // source of the next tile to request
+  auto issue = [&](uint32_t step, uint32_t stage) {  // lane 0 only, steps in order
+    const uint32_t bytes = (step + 1 < n_steps ? (uint32_t)kPfTile : last_valid) + 16;
+    const uint32_t bar = bar0 + stage * 8, dst = ring0 + stage * kPfStageBytes;
+    const uint8_t* src = next_src;
+    next_src += wstride;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
   };
   if (lane == 0) {
-    if (wfirst < chunk_hi) issue(wfirst, 0);
-    if (wfirst + wstride < chunk_hi) issue(wfirst + wstride, 1);
+    if (n_steps > 0) issue(0, 0);
+    if (n_steps > 1) issue(1, 1);
   }
-  uint32_t it = 0;
-  for (uint64_t wbase = wfirst; wbase < chunk_hi; wbase += wstride, ++it) {
-    const int stage = it & 1;
+  constexpr int kBitsPerGroup = 16 / STRIDE;
+  constexpr int kHitBits = kGroups * kBitsPerGroup;
+  const bool cta_warp_first = blockIdx.x == 0 && warp == 0;
+  uint64_t wbase = wfirst;
+  for (uint32_t it = 0; it < n_steps; ++it, wbase += wstride) {
+    const uint32_t stage = it & 1;
     const uint32_t parity = (it >> 1) & 1;
     while (!mbar_try_wait(&bars[stage], parity)) {}
     const unsigned char* tile = ring + stage * kPfStageBytes;
-    const uint32_t valid = (uint32_t)min((uint64_t)kPfTile, chunk_hi - wbase);  // multiple of 16
-    // lane L owns the 16-byte groups at tile offsets g*512 + 16L (conflict-free 16-byte reads)
     uint32_t wv[kGroups][5];
-    uint32_t ok_bits = 0;  // which of the lane's hit bits belong to valid positions
-    constexpr int kBitsPerGroup = 16 / STRIDE;
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       const unsigned char* gp = tile + g * 512 + lane * 16;
       const uint4 v = *reinterpret_cast<const uint4*>(gp);
       wv[g][0] = v.x; wv[g][1] = v.y; wv[g][2] = v.z; wv[g][3] = v.w;
       wv[g][4] = *reinterpret_cast<const uint32_t*>(gp + 16);  // look-ahead word behind the group
-      if ((uint32_t)(g * 512 + lane * 16) < valid) ok_bits |= ((1u << kBitsPerGroup) - 1) << (g * kBitsPerGroup);
     }
     // hit mask of this lane, kBitsPerGroup bits per group.  Stride 1: bit 16g+o = offset o of
     // group g.  Stride 2: only even offsets are probed (3-byte fingerprints of the pattern bytes
@@ -332,13 +356,20 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     // the next even offset); bit 8g+i = offset 2i of group g.
     uint32_t mask = 0;
 #define ACB_WIN(o, lo, hi) (((o) & 3) ? __funnelshift_r(lo, hi, ((o) & 3) * 8) : (lo))
-#define ACB_GRAM(o, lo, hi) (STRIDE == 2 ? ((MASKED ? (ACB_WIN(o, lo, hi) | fold1) : ACB_WIN(o, lo, hi)) & 0x00FFFFFFu) \
-                                         : (MASKED ? ((ACB_WIN(o, lo, hi) | fold) & kmask) : ACB_WIN(o, lo, hi)))
 #define ACB_PROBE(o, lo, hi)                                                                  \
   do {                                                                                        \
-    const uint32_t h = ACB_GRAM(o, lo, hi) * mult;                                            \
-    const uint32_t rep = (uint32_t)s_bytes[h >> bshift] * 0x01010101u;                        \
-    mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, h), 1);                            \
+    uint32_t gm, h, sel;                                                                      \
+    if constexpr (STRIDE == 2) {                                                              \
+      gm = MASKED ? (ACB_WIN(o, lo, hi) | fold1) : ACB_WIN(o, lo, hi);                        \
+      h = gm * mult8;                                                                         \
+      sel = gm;                                                                               \
+    } else {                                                                                  \
+      gm = MASKED ? ((ACB_WIN(o, lo, hi) | fold) & kmask) : ACB_WIN(o, lo, hi);               \
+      h = gm * mult;                                                                          \
+      sel = h;                                                                                \
+    }                                                                                         \
+    const uint32_t rep = (uint32_t)s_bytes[h >> kBloomShift] * 0x01010101u;                   \
+    mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, sel), 1);                          \
   } while (0)
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
@@ -353,15 +384,20 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       }
     }
 #undef ACB_PROBE
-#undef ACB_GRAM
 #undef ACB_WIN
     // the probes were funnelled in from the top: move the first one down to bit 0
-    constexpr int kHitBits = kGroups * kBitsPerGroup;
     if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
-    mask &= ok_bits;
-    // tile offset of hit bit `b` of this lane
-    auto hit_offset = [&](int b) -> uint32_t {
-      return (uint32_t)((b / kBitsPerGroup) * 512 + lane * 16 + (b % kBitsPerGroup) * STRIDE);
+    if (it + 1 == n_steps) {
+      // the last tile may be short: drop the hit bits of groups behind its end
+      uint32_t ok_bits = 0;
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g)
+        if ((uint32_t)(g * 512 + lane * 16) < last_valid) ok_bits |= (uint32_t)((1ull << kBitsPerGroup) - 1) << (g * kBitsPerGroup);
+      mask &= ok_bits;
+    }
+    // tile offset of hit bit `b` of lane `ln`
+    auto hit_offset = [&](uint32_t b, uint32_t ln) -> uint32_t {
+      return (b / kBitsPerGroup) * 512 + ln * 16 + (b % kBitsPerGroup) * STRIDE;
     };
     // slot allocation for this step's first-probe hits without touching shared memory: the
     // per-lane counts (almost always < 8) are summed across the warp bit plane by bit plane with
@@ -378,68 +414,76 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     }
     if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
+      // the very first probe of the region has no start before it
+      const bool region_first = cta_warp_first && it == 0;
       if (total > (uint32_t)kPfSlots) {
         // fingerprints not selective here: verify this step's hits in place
         uint32_t nver = 0;
         while (mask) {
           const int b = __ffs(mask) - 1;
           mask &= mask - 1;
-          const uint64_t e = wbase + hit_offset(b);
+          const uint64_t e = wbase + hit_offset((uint32_t)b, (uint32_t)lane);
 #pragma unroll
           for (int j = 0; j < STRIDE; ++j)
             if (e >= p.region_lo + j) { verify_at<MODE>(d, p, s_cls, e - j, em); ++nver; }
         }
         cand_total += __reduce_add_sync(0xffffffffu, nver);
       } else {
-        while (mask) {
-          const int b = __ffs(mask) - 1;
-          mask &= mask - 1;
-          slots[slot++] = (uint16_t)hit_offset(b);
+        // hit t of the step is recorded as (lane << 5 | bit); the consumer decodes the offset
+        {
+          uint16_t* sp = slots + slot;
+          const uint32_t tag = (uint32_t)lane << 5;
+          while (mask) {
+            const uint32_t b = (uint32_t)__ffs(mask) - 1;
+            mask &= mask - 1;
+            *sp++ = (uint16_t)(tag | b);
+          }
         }
         __syncwarp();
-        // second stage, compacted: lane t handles hit t of this step.  Every start offset the
-        // hit owns (the probed offset and, with stride 2, the one before it) is tested with two
-        // Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
+        // second stage, compacted: the work items are (hit, start offset the hit owns) -- the
+        // probed offset and, with stride 2, the one before it -- one per lane.  Each is tested
+        // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
         const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
-        for (uint32_t base = 0; base < total; base += 32) {
-          const uint32_t t = base + lane;
-          const uint32_t e = t < total ? slots[t] : 0u;
-#pragma unroll
-          for (int j = 0; j < STRIDE; ++j) {
-            bool pass = false;
-            uint32_t gram_keep = 0;
-            if (t < total && wbase + e >= p.region_lo + j) {
-              uint32_t gram;
-              if (STRIDE == 1 || e >= (uint32_t)j) {
-                const uint32_t off = e - j;
-                const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (off & ~3u));
-                gram = __funnelshift_r(sc[0], sc[1], (off & 3) * 8);
-              } else {  // the start lies one byte before the tile: fetch from global memory
-                const uint8_t* a = p.hay + wbase + e - j;
-                gram = (uint32_t)__ldg(a) | ((uint32_t)__ldg(a + 1) << 8) | ((uint32_t)__ldg(a + 2) << 16) |
-                       ((uint32_t)__ldg(a + 3) << 24);
-              }
+        const uint32_t n_items = total * STRIDE;
+        for (uint32_t base = 0; base < n_items; base += 32) {
+          const uint32_t w = base + lane;
+          const uint32_t j = STRIDE == 2 ? (w & 1u) : 0u;
+          bool pass = false;
+          uint32_t gram_keep = 0, e = 0;
+          if (w < n_items) {
+            const uint32_t raw = slots[STRIDE == 2 ? (w >> 1) : w];
+            e = hit_offset(raw & 31u, raw >> 5);
+            if (STRIDE == 2 && e < j) {
+              // the start lies one byte before the tile (at most one item per step): no second
+              // probe, the verifier decides -- unless it would fall before the filter region
+              pass = !region_first;
+            } else {
+              const uint32_t off = e - j;
+              const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (off & ~3u));
+              uint32_t gram = __funnelshift_r(sc[0], sc[1], (off & 3) * 8);
               if (MASKED) gram = (gram | fold) & kmask;
               gram_keep = gram;
-              pass = bloom_test(s_bitmap, bloom_hash2(gram), bshift);
-              if (STRIDE == 2) pass = pass && bloom_test(s_bitmap, gram * mult, bshift);
+              // stride 2: the first stage saw only three of the four bytes, so the cheap
+              // multiplicative hash of the whole fingerprint rejects most items before the mix
+              if (STRIDE == 2) pass = bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
+              else pass = bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+          if (bal) {
+            if (pass) {
               const uint32_t rel = wrel + e - j;
-              if (pass) {
-                if constexpr (DENSE) q2[q2len + __popc(bal & ((1u << lane) - 1))] = make_uint2(rel, gram_keep);
-                else q2[q2len + __popc(bal & ((1u << lane) - 1))] = rel;
-              }
-              q2len += __popc(bal);
-              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+              if constexpr (DENSE) q2[q2len + __popc(bal & lt)] = make_uint2(rel, gram_keep);
+              else q2[q2len + __popc(bal & lt)] = rel;
             }
+            q2len += __popc(bal);
+            if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
           }
         }
       }
     }
     __syncwarp();  // every lane is done with this stage: refill it with the tile two steps ahead
-    if (lane == 0 && wbase + 2 * wstride < chunk_hi) issue(wbase + 2 * wstride, stage);
+    if (lane == 0 && it + 2 < n_steps) issue(it + 2, stage);
   }
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
@@ -493,9 +537,11 @@ struct MaxOp {
 }  // namespace
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
-  const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const bool dense = p.gbitmap != nullptr;
   const bool wide_geom = p.stride == 2 && p.wide;
+  const uint32_t want_log = wide_geom ? PfBloom<true>::kLogBits : PfBloom<false>::kLogBits;
+  if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
+  const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
   const int threads = wide_geom ? PfGeom<true>::kThreads : PfGeom<false>::kThreads;
   const int warps = threads / 32;
   const int stage_bytes = wide_geom ? PfGeom<true>::kStageBytes : PfGeom<false>::kStageBytes;
