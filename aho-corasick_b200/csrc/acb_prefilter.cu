@@ -102,6 +102,28 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// shared-memory reads by 32-bit shared address (volatile: they must stay behind the mbarrier wait)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Emitter {
@@ -316,7 +338,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint64_t wspan = chunk_hi > wfirst ? chunk_hi - wfirst : 0;
   const uint32_t n_steps = wspan ? (uint32_t)((wspan - 1) / wstride) + 1 : 0;
   const uint32_t last_valid = n_steps ? (uint32_t)min((uint64_t)kPfTile, wspan - (uint64_t)(n_steps - 1) * wstride) : 0;
-  const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
+  // shared addresses of this warp's barriers and ring, and of the lane's first 16-byte group;
+  // opaque to the compiler so that they stay in registers instead of being re-derived from the
+  // thread index at every use
+  uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring), lane0 = ring0 + (uint32_t)lane * 16u;
+  asm volatile("" : "+r"(bar0), "+r"(ring0), "+r"(lane0));
   // Refilling a stage needs no proxy fence: every lane has consumed its shared-memory reads of the
   // tile (their values fed the probes) before the __syncwarp that precedes the copy.
   const uint8_t* next_src = p.hay + wfirst;  // source of the next tile to request
@@ -340,15 +366,16 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t it = 0; it < n_steps; ++it, wbase += wstride) {
     const uint32_t stage = it & 1;
     const uint32_t parity = (it >> 1) & 1;
-    while (!mbar_try_wait(&bars[stage], parity)) {}
-    const unsigned char* tile = ring + stage * kPfStageBytes;
+    while (!mbar_try_wait_a(bar0 + stage * 8, parity)) {}
+    const uint32_t stage_off = stage * (uint32_t)kPfStageBytes;
+    const uint32_t tile_a = ring0 + stage_off;
     uint32_t wv[kGroups][5];
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
-      const unsigned char* gp = tile + g * 512 + lane * 16;
-      const uint4 v = *reinterpret_cast<const uint4*>(gp);
+      const uint32_t ga = lane0 + stage_off + g * 512;
+      const uint4 v = lds128(ga);
       wv[g][0] = v.x; wv[g][1] = v.y; wv[g][2] = v.z; wv[g][3] = v.w;
-      wv[g][4] = *reinterpret_cast<const uint32_t*>(gp + 16);  // look-ahead word behind the group
+      wv[g][4] = lds32(ga + 16);  // look-ahead word behind the group
     }
     // hit mask of this lane, kBitsPerGroup bits per group.  Stride 1: bit 16g+o = offset o of
     // group g.  Stride 2: only even offsets are probed (3-byte fingerprints of the pattern bytes
@@ -459,8 +486,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
               pass = !region_first;
             } else {
               const uint32_t off = e - j;
-              const uint32_t* sc = reinterpret_cast<const uint32_t*>(tile + (off & ~3u));
-              uint32_t gram = __funnelshift_r(sc[0], sc[1], (off & 3) * 8);
+              const uint32_t sa = tile_a + (off & ~3u);
+              uint32_t gram = __funnelshift_r(lds32(sa), lds32(sa + 4), (off & 3) * 8);
               if (MASKED) gram = (gram | fold) & kmask;
               gram_keep = gram;
               // stride 2: the first stage saw only three of the four bytes, so the cheap
