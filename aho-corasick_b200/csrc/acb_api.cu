@@ -68,9 +68,10 @@ struct PrefilterPlan {
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
   uint64_t n_grams = 0;
   std::vector<uint32_t> bitmap;
-  // third level (dense pattern sets only): single-hash bitmap of 2^glog bits kept in global memory
-  std::vector<uint32_t> gbitmap;
-  uint32_t glog = 0;
+  bool dense = false;  // many fingerprints: the kernel filters survivors through the anchor map
+  // anchor map: (k-byte haystack prefix -> trie state at depth k), open addressing, see DfaDev::amap
+  std::vector<uint64_t> amap;  // low word = key, high word = premultiplied state id (0 = empty)
+  uint32_t amap_log = 0;
 };
 
 struct acg_dfa {
@@ -78,7 +79,7 @@ struct acg_dfa {
   std::vector<uint16_t> depth16;
   PrefilterPlan pf;
   uint32_t* d_bitmap = nullptr;
-  uint32_t* d_gbitmap = nullptr;
+  uint2* d_amap = nullptr;
   bool has_empty = false;
   uint32_t max_list_len = 0;
   bool on_device = false;
@@ -176,6 +177,7 @@ void derive_metadata(acg_dfa* a) {
   const uint32_t kmax = uint32_t(std::min<uint64_t>(4, h.min_pattern_len));
   struct Item { uint32_t row; uint32_t gram; };
   std::vector<std::vector<uint32_t>> grams(kmax + 1);
+  std::vector<std::vector<Item>> level(kmax + 1);  // (row, raw bytes) of every trie path of that length
   std::vector<Item> cur{{h.start_unanchored_id >> s2, 0u}}, nxt;
   for (uint32_t j = 0; j < kmax; ++j) {
     nxt.clear();
@@ -188,6 +190,7 @@ void derive_metadata(acg_dfa* a) {
       }
     }
     cur.swap(nxt);
+    level[j + 1] = cur;
     auto& g = grams[j + 1];
     g.reserve(cur.size());
     for (const Item& it : cur) g.push_back(it.gram);
@@ -276,7 +279,7 @@ void derive_metadata(acg_dfa* a) {
     const double n_bits_set = double(g3.size()) + 2.0 * double(best_set.size());
     const double true3 = double(g3.size()) / space;
     const double pass1 = n_bits_set / double(uint64_t(1) << pf.log_bits) + true3;  // per probed offset
-    if (pass1 < 0.04) {
+    if (pass1 < 0.07) {  // beyond that the second stage costs more than the halved probe count saves
       pf.stride = 2;
       // rare hits even with a 16 KiB bitmap: the wide geometry (2 KiB tiles, two CTAs per SM,
       // PfBloom<true> in acb_prefilter.cu) amortises the per-step bookkeeping better
@@ -338,14 +341,19 @@ void derive_metadata(acg_dfa* a) {
     }
   }
   (void)best_fp;
-  if (!pf.brute && best_set.size() > 8192) {
-    // the shared-memory Bloom filter lets through more than 0.1 % false positives (many
-    // patterns): add a large single-hash bitmap that lives in L2 and is probed only by survivors
-    pf.glog = uint32_t(std::min(28, std::max(20, bits_for(uint64_t(best_set.size()) * 512 - 1))));
-    pf.gbitmap.assign(size_t(1) << (pf.glog - 5), 0u);
-    for (uint32_t g : best_set) {
-      const uint32_t hsh = bloom_hash3(g);
-      pf.gbitmap[hsh >> (37 - pf.glog)] |= 1u << (hsh & 31);
+  pf.dense = !pf.brute && best_set.size() > 8192;
+  // Anchor map: the verifier looks the first k bytes at a candidate offset up here and starts at
+  // depth k.  Keys are raw (unfolded) byte strings: one entry per trie path of length k.
+  const std::vector<Item>& paths = level[pf.k];
+  if (!paths.empty() && paths.size() <= (4u << 20)) {
+    pf.amap_log = uint32_t(std::max(4, bits_for(uint64_t(paths.size()) * 2 - 1)));
+    pf.amap.assign(size_t(1) << pf.amap_log, 0ull);
+    const uint32_t cap_mask = (1u << pf.amap_log) - 1;
+    for (const Item& it : paths) {
+      const uint32_t key = it.gram & pf.kmask;
+      uint32_t slot = bloom_hash3(key) >> (32 - pf.amap_log);
+      while (pf.amap[slot] != 0 && uint32_t(pf.amap[slot]) != key) slot = (slot + 1) & cap_mask;
+      pf.amap[slot] = uint64_t(key) | (uint64_t(it.row << s2) << 32);
     }
   }
 }
@@ -371,7 +379,7 @@ int upload(acg_dfa* a) {
   CK(up(&a->d_plens, h.pattern_lens.data(), h.pattern_lens.size() * 4));
   CK(up(&a->d_depth16, a->depth16.data(), a->depth16.size() * 2));
   if (a->pf.supported && !a->pf.bitmap.empty()) CK(up(&a->d_bitmap, a->pf.bitmap.data(), a->pf.bitmap.size() * 4));
-  if (a->pf.supported && !a->pf.gbitmap.empty()) CK(up(&a->d_gbitmap, a->pf.gbitmap.data(), a->pf.gbitmap.size() * 4));
+  if (a->pf.supported && !a->pf.amap.empty()) CK(up(&a->d_amap, a->pf.amap.data(), a->pf.amap.size() * 8));
   DfaDev& d = a->dev;
   d.trans = a->d_trans;
   d.classes = a->d_classes;
@@ -385,6 +393,11 @@ int upload(acg_dfa* a) {
   d.start_anchored_id = h.start_anchored_id;
   d.max_pattern_len = uint32_t(std::min<uint64_t>(h.max_pattern_len, UINT32_MAX));
   d.min_pattern_len = uint32_t(std::min<uint64_t>(h.min_pattern_len, UINT32_MAX));
+  d.amap = a->d_amap;
+  d.amap_shift = a->pf.amap_log ? 32 - a->pf.amap_log : 0;
+  d.amap_mask = a->pf.amap_log ? (1u << a->pf.amap_log) - 1 : 0;
+  d.amap_k = a->pf.k;
+  d.amap_kmask = a->pf.kmask;
   Workspace& w = a->ws;
   CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
@@ -575,8 +588,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.mult = pf.mult;
   p.mult3 = pf.mult3;
   p.shift = pf.shift;
-  p.gbitmap = a->d_gbitmap;
-  p.gshift = pf.glog ? 37 - pf.glog : 0;
+  p.dense = pf.dense ? 1 : 0;
   p.brute = pf.brute ? 1 : 0;
   p.mode = mode;
   p.dup_shift = pf.dup_shift;
@@ -1088,7 +1100,7 @@ void acg_dfa_free(acg_dfa* a) {
     Workspace& w = a->ws;
     if (w.stream) cudaStreamSynchronize(w.stream);
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
-    cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_gbitmap);
+    cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_amap);
     for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
     cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
     cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);

@@ -31,6 +31,15 @@ struct DfaDev {
   uint32_t start_anchored_id;
   uint32_t max_pattern_len;
   uint32_t min_pattern_len;
+  // Anchor map (prefilter engine): open-addressing hash table from the first k haystack bytes at a
+  // candidate offset to the trie state those bytes lead to, so that the verifier starts at depth
+  // k with one lookup instead of k dependent table reads.  Entry = (key, premultiplied state id),
+  // empty slots hold id 0 (DEAD is never a target).  nullptr: walk from the start state.
+  const uint2* amap;
+  uint32_t amap_shift;            // slot = hash3(key) >> amap_shift
+  uint32_t amap_mask;             // capacity - 1
+  uint32_t amap_k;                // key length in bytes (1..4)
+  uint32_t amap_kmask;            // mask of the low amap_k bytes
 };
 
 // ---- launch wrappers (acb_kernels.cu) --------------------------------------
@@ -85,8 +94,8 @@ struct PrefilterLaunch {
   uint32_t mult;                // first Bloom hash: gram * mult
   uint32_t mult3;               // stride 2: multiplier of the 3-byte first-stage fingerprint
   uint32_t shift;               // hash >> shift = byte offset into the bitmap (= 35 - log_bits)
-  const uint32_t* gbitmap;      // optional third-level bitmap in global memory (nullptr: unused)
-  uint32_t gshift;              // word index = hash3 >> gshift
+  int dense;                    // many fingerprints: survivors of both probes are filtered once more
+                                // (anchor-map lookup) before the warp-wide verification
   int brute;                    // 1: skip the bitmap, every position is a candidate
   int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)
   uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break

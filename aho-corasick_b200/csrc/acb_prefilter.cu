@@ -146,26 +146,48 @@ struct Emitter {
   }
 };
 
-// Verify one candidate start offset `s` (K3b): walk the shipped DFA from the start state while
-// the state stays on the trie path anchored at s (depth == bytes consumed).
+// Anchor-map lookup: the state reached from the start state by the k bytes at `s`, 0 if those
+// bytes are not the beginning of any pattern.  Must match the table built in acb_api.cu.
+__device__ __forceinline__ uint32_t anchor_lookup(const DfaDev& d, const PrefilterLaunch& p, uint64_t s) {
+  if (s + d.amap_k > p.span_end) return 0;  // no pattern fits any more
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p.hay + s);
+  const uintptr_t end = reinterpret_cast<uintptr_t>(p.hay + p.hay_len);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+  const uint32_t lo = __ldg(w);
+  const uint32_t hi = ((a & 3) && reinterpret_cast<uintptr_t>(w + 1) < end) ? __ldg(w + 1) : 0u;
+  const uint32_t key = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8) & d.amap_kmask;
+  uint32_t slot = bloom_hash3(key) >> d.amap_shift;
+  for (;;) {
+    const uint2 e = __ldg(d.amap + slot);
+    if (e.y == 0 || e.x == key) return e.y;
+    slot = (slot + 1) & d.amap_mask;
+  }
+}
+
+// Verify one candidate start offset `s` (K3b): walk the shipped DFA while the state stays on the
+// trie path anchored at s (depth == bytes consumed), starting from state `sid` at depth `j`
+// (the start state, or the state the anchor map gave for the first j bytes).
 template <int MODE>
-__device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch& p, const uint8_t* s_cls,
-                                          uint64_t s, Emitter& em) {
+__device__ __forceinline__ void verify_from(const DfaDev& d, const PrefilterLaunch& p, const uint8_t* s_cls,
+                                            uint64_t s, uint32_t sid, uint32_t j, Emitter& em) {
   const uint8_t* __restrict__ hay = p.hay;
   const uint32_t* __restrict__ trans = d.trans;
-  uint32_t sid = d.start_unanchored_id;
-  uint64_t pos = s;
-  uint32_t j = 0;
+  uint64_t pos = s + j;
   uint32_t best_pid = 0, best_len = 0;
-  while (pos < p.span_end) {
-    const uint32_t b = __ldg(hay + pos);
-    sid = __ldg(trans + sid + s_cls[b]);
-    ++j;
-    ++pos;
-    if (sid == 0) break;  // DEAD (leftmost automata): nothing longer can start at s
-    const uint32_t row = sid >> d.stride2;
-    if (__ldg(d.depth16 + row) != j) break;  // left the trie path anchored at s
+  bool entered = j != 0;  // the anchor state may itself hold patterns of length j
+  for (;;) {
+    if (!entered) {
+      if (pos >= p.span_end) break;
+      const uint32_t b = __ldg(hay + pos);
+      sid = __ldg(trans + sid + s_cls[b]);
+      ++j;
+      ++pos;
+      if (sid == 0) break;  // DEAD (leftmost automata): nothing longer can start at s
+      if (__ldg(d.depth16 + (sid >> d.stride2)) != j) break;  // left the trie path anchored at s
+    }
+    entered = false;
     if (sid <= d.max_match_id) {
+      const uint32_t row = sid >> d.stride2;
       const uint32_t lo = __ldg(d.match_offsets + row - 2), hi = __ldg(d.match_offsets + row - 1);
       if (MODE == 0) {
         // the node's own patterns come first in its list and all have length j
@@ -182,6 +204,17 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
     }
   }
   if (MODE == 1 && best_len) em.emit(((s - p.span_start) << kTieBits) | best_len, best_pid);
+}
+
+template <int MODE>
+__device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch& p, const uint8_t* s_cls,
+                                          uint64_t s, Emitter& em) {
+  if (d.amap != nullptr) {
+    const uint32_t sid = anchor_lookup(d, p, s);
+    if (sid != 0) verify_from<MODE>(d, p, s_cls, s, sid, d.amap_k, em);
+  } else {
+    verify_from<MODE>(d, p, s_cls, s, d.start_unanchored_id, 0, em);
+  }
 }
 
 // The size of the shared-memory Bloom bitmap is a compile-time property of the kernel geometry,
@@ -291,8 +324,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   uint64_t* bars = s_bars + warp * kPfStages;
   uint16_t* slots = s_slots + warp * kPfSlots;
   Q2Entry* q2 = s_queue2 + warp * kPfQ2;
-  const uint32_t* __restrict__ gbits = p.gbitmap;  // third-level bitmap in global memory (DENSE only)
-  const uint32_t gshift = p.gshift;
   uint32_t q2len = 0;  // warp-uniform
 
   auto q2_off = [](const Q2Entry& e) -> uint32_t {
@@ -301,24 +332,32 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
     __syncwarp();
     if constexpr (DENSE) {
-      // dense pattern sets: one more fingerprint probe against a large L2-resident bitmap, the
-      // survivors are compacted in place so that the DFA walks still run with full warps
-      uint32_t w = 0;
-      for (uint32_t base = 0; base < q2len; base += 32) {
-        const uint32_t i = base + lane;
-        bool pass = false;
-        uint2 e = make_uint2(0, 0);
-        if (i < q2len) {
-          e = q2[i];
-          const uint32_t h = bloom_hash3(e.y);
-          pass = (__ldg(gbits + (h >> gshift)) >> (h & 31)) & 1u;
+      // dense pattern sets: the Bloom probes still let through far more offsets than there are
+      // pattern beginnings, so look each survivor up in the anchor map first (one L2 access) and
+      // compact in place: the DFA walks then run with full warps, from depth k
+      if (d.amap != nullptr) {
+        uint32_t w = 0;
+        for (uint32_t base = 0; base < q2len; base += 32) {
+          const uint32_t i = base + lane;
+          uint2 e = make_uint2(0, 0);
+          if (i < q2len) {
+            e = q2[i];
+            e.y = anchor_lookup(d, p, chunk_base + e.x);
+          }
+          const uint32_t bal = __ballot_sync(0xffffffffu, e.y != 0);
+          if (e.y != 0) q2[w + __popc(bal & ((1u << lane) - 1))] = e;
+          w += __popc(bal);
+          __syncwarp();
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) q2[w + __popc(bal & ((1u << lane) - 1))] = e;
-        w += __popc(bal);
+        cand_total += w;
+        for (uint32_t i = lane; i < w; i += 32) {
+          const uint2 e = q2[i];
+          verify_from<MODE>(d, p, s_cls, chunk_base + e.x, e.y, d.amap_k, em);
+        }
+        q2len = 0;
         __syncwarp();
+        return;
       }
-      q2len = w;
     }
     for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_base + q2_off(q2[i]), em);
     cand_total += q2len;
@@ -564,7 +603,7 @@ struct MaxOp {
 }  // namespace
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
-  const bool dense = p.gbitmap != nullptr;
+  const bool dense = p.dense != 0;
   const bool wide_geom = p.stride == 2 && p.wide;
   const uint32_t want_log = wide_geom ? PfBloom<true>::kLogBits : PfBloom<false>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
