@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/acb200.h"
+#include "../../include/acb200_debug.h"
 #include "acb_build.hpp"
 #include "acb_device.cuh"
 
@@ -1161,6 +1162,23 @@ int acg_packed_variant(const acg_dfa* a, int* fat, int* mask_len) {
   if (fat) *fat = a->h.packed.fat;
   if (mask_len) *mask_len = a->h.packed.mask_len;
   return 1;
+}
+
+int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
+  if (!a || !out) return ACG_E_INVALID_ARG;
+  const PrefilterPlan& pf = a->pf;
+  *out = acg_prefilter_plan{};
+  out->supported = pf.supported ? 1 : 0;
+  out->brute = pf.brute ? 1 : 0;
+  out->dense = pf.dense ? 1 : 0;
+  out->stride = int32_t(pf.stride);
+  out->wide = pf.wide ? 1 : 0;
+  out->k = pf.k; out->kmask = pf.kmask; out->fold = pf.fold;
+  out->mult = pf.mult; out->mult3 = pf.mult3; out->shift = pf.shift; out->log_bits = pf.log_bits;
+  out->bitmap = pf.bitmap.data(); out->bitmap_words = pf.bitmap.size();
+  out->amap = pf.amap.data(); out->amap_log = pf.amap_log;
+  out->depth16 = a->depth16.data(); out->n_rows = a->depth16.size();
+  return ACG_OK;
 }
 
 int acg_set_engine(acg_dfa* a, int engine) {

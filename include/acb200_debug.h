@@ -1,0 +1,40 @@
+/*
+ * acb200_debug.h -- introspection of the device engine's derived tables (libacb200.so).
+ *
+ * Test infrastructure, not part of the drop-in boundary (include/acb200.h): it lets the CPU test
+ * suite check the contract between the host-side table construction and the kernels' probe
+ * functions (no false negatives in the fingerprint bitmap, anchor map == DFA walk) on handles
+ * built without a GPU (acg_build_host).
+ */
+#ifndef ACB200_DEBUG_H
+#define ACB200_DEBUG_H
+
+#include "acb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  int32_t supported; /* 0: the automaton runs on the walk / sequential engines only */
+  int32_t brute;     /* fingerprints not selective: every offset is verified */
+  int32_t dense;     /* > 8192 fingerprints: survivors are compacted through the anchor map */
+  int32_t stride;    /* 1 or 2 (first-stage probe stride) */
+  int32_t wide;      /* stride 2 only: 2 KiB tiles, 16 KiB bitmap */
+  uint32_t k;        /* fingerprint length in bytes, 1..4 */
+  uint32_t kmask, fold, mult, mult3, shift, log_bits;
+  const uint32_t* bitmap; /* 1 << (log_bits - 5) words, borrowed until acg_dfa_free */
+  uint64_t bitmap_words;
+  const uint64_t* amap;   /* 1 << amap_log entries: low word key, high word premultiplied state id */
+  uint32_t amap_log;
+  const uint16_t* depth16; /* trie depth per table row */
+  uint64_t n_rows;
+} acg_prefilter_plan;
+
+/* Fills *out with views of the handle's derived tables.  Works on host-only handles. */
+int acg_debug_prefilter_plan(const acg_dfa* dfa, acg_prefilter_plan* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -64,9 +64,9 @@ def test_sharded_overlapping_gloo(world):
         for p in procs:
             p.start()
         for p in procs:
-            p.join(120)
+            p.join(600)
             assert p.exitcode == 0
-        ok, n, want = q.get(timeout=10)
+        ok, n, want = q.get(timeout=60)
         assert ok, (n, want, case[2], world)
 
 
