@@ -84,6 +84,7 @@ struct acg_dfa {
   bool has_empty = false;
   uint32_t max_list_len = 0;
   bool on_device = false;
+  bool dev_touched = false;  // upload() started: device resources may exist even if it failed
   int device = -1;
   uint32_t* d_trans = nullptr;
   uint8_t* d_classes = nullptr;
@@ -366,6 +367,7 @@ int upload(acg_dfa* a) {
     return ACG_E_NO_DEVICE;
   }
   CK(cudaGetDevice(&a->device));
+  a->dev_touched = true;
   HostDfa& h = a->h;
   auto up = [&](auto** dptr, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(bytes, 16));
@@ -1096,7 +1098,7 @@ int acg_dfa_create(const acg_dfa_desc* d, acg_dfa** out) {
 
 void acg_dfa_free(acg_dfa* a) {
   if (!a) return;
-  if (a->on_device) {
+  if (a->on_device || a->dev_touched) {
     DeviceGuard guard(a->device);
     Workspace& w = a->ws;
     if (w.stream) cudaStreamSynchronize(w.stream);
@@ -1334,6 +1336,114 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
     win = std::min<uint64_t>(win * 16, 1ull << 30);
   }
   return ACG_OK;
+}
+
+// ---- packed searcher (src/packed/api.rs) ----------------------------------------------------
+
+struct acg_packed {
+  acg_dfa* inner = nullptr;  // leftmost DFA over the same patterns: the device engine
+  int match_kind = ACG_LEFTMOST_FIRST;
+  bool teddy = false;
+  bool fat = false;
+  int mask_len = 0;
+  int vector_bytes = 0;
+  uint64_t minimum_len = 0;
+};
+
+void acg_packed_config_default(acg_packed_config* c) {
+  c->match_kind = ACG_LEFTMOST_FIRST;
+  c->force = ACG_PACKED_FORCE_NONE;
+  c->only_teddy_fat = -1;
+  c->only_teddy_256bit = -1;
+  c->heuristic_pattern_limits = 1;
+}
+
+static int packed_build_common(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                               const acg_packed_config* cfg, bool to_device, acg_packed** out) {
+  if (!out) return ACG_E_INVALID_ARG;
+  *out = nullptr;
+  acg_packed_config def;
+  acg_packed_config_default(&def);
+  if (!cfg) cfg = &def;
+  if (n && (!patterns || !lens)) return ACG_E_INVALID_ARG;
+  if (cfg->match_kind != ACG_LEFTMOST_FIRST && cfg->match_kind != ACG_LEFTMOST_LONGEST) return ACG_E_INVALID_ARG;
+  // Builder::add (api.rs:303-322): the builder turns inert -- and build() returns None -- once a
+  // 129th pattern or an empty pattern is offered; build() also returns None without patterns.
+  constexpr uint64_t kPatternLimit = 128;  // PATTERN_LIMIT, api.rs:15
+  if (n == 0 || n > kPatternLimit) return ACG_OK;
+  uint64_t min_len = UINT64_MAX;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (lens[i] == 0) return ACG_OK;
+    min_len = std::min(min_len, lens[i]);
+  }
+  acg_packed plan;
+  plan.match_kind = cfg->match_kind;
+  if (cfg->force != ACG_PACKED_FORCE_RABINKARP) {
+    // teddy::Builder::build_imp (teddy/builder.rs:98-231) as it decides on x86-64 with AVX2
+    const bool limits = cfg->heuristic_pattern_limits != 0;
+    if (limits && n > 64) return ACG_OK;
+    const int mask_len = int(std::min<uint64_t>(4, min_len));
+    const bool use_256 = cfg->only_teddy_256bit != 0;  // None -> AVX2 is available
+    bool fat;
+    if (cfg->only_teddy_fat < 0) fat = use_256 && n > 32;
+    else if (cfg->only_teddy_fat == 0) fat = false;
+    else { if (!use_256) return ACG_OK; fat = true; }
+    if (limits && mask_len == 1 && n > 16) return ACG_OK;
+    plan.teddy = true;
+    plan.fat = fat;
+    plan.mask_len = mask_len;
+    // Slim SSSE3: 16 lanes; Slim AVX2: 32; Fat AVX2: 16 (two 128-bit halves), teddy/generic.rs:94-96, 427-429
+    plan.vector_bytes = use_256 ? 32 : 16;
+    const int width = (use_256 && !fat) ? 32 : 16;
+    plan.minimum_len = uint64_t(width + mask_len - 1);
+  }
+  acg_build_opts o;
+  acg_build_opts_default(&o);
+  o.match_kind = cfg->match_kind;
+  o.kind = ACG_KIND_DFA;
+  acg_dfa* inner = nullptr;
+  const int rc = to_device ? acg_build(patterns, lens, n, &o, &inner) : acg_build_host(patterns, lens, n, &o, &inner);
+  if (rc != ACG_OK) return rc;
+  acg_packed* s = new (std::nothrow) acg_packed(plan);
+  if (!s) { acg_dfa_free(inner); return ACG_E_NOMEM; }
+  s->inner = inner;
+  *out = s;
+  return ACG_OK;
+}
+
+int acg_packed_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                     const acg_packed_config* cfg, acg_packed** out) {
+  return packed_build_common(patterns, lens, n, cfg, true, out);
+}
+int acg_packed_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                          const acg_packed_config* cfg, acg_packed** out) {
+  return packed_build_common(patterns, lens, n, cfg, false, out);
+}
+void acg_packed_free(acg_packed* s) {
+  if (!s) return;
+  acg_dfa_free(s->inner);
+  delete s;
+}
+int acg_packed_find_iter(const acg_packed* s, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+                         uint64_t span_end, acg_match* out, uint64_t cap, uint64_t* n_out) {
+  if (!s) return ACG_E_INVALID_ARG;
+  return acg_find_iter(s->inner, hay, hay_len, span_start, span_end, 0, out, cap, n_out);
+}
+int acg_packed_find(const acg_packed* s, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+                    uint64_t span_end, acg_match* out, int* found) {
+  if (!s) return ACG_E_INVALID_ARG;
+  return acg_find(s->inner, hay, hay_len, span_start, span_end, 0, 0, out, found);
+}
+int acg_packed_match_kind(const acg_packed* s) { return s ? s->match_kind : 0; }
+uint64_t acg_packed_minimum_len(const acg_packed* s) { return s ? s->minimum_len : 0; }
+uint64_t acg_packed_memory_usage(const acg_packed* s) { return s ? acg_memory_usage(s->inner) : 0; }
+uint64_t acg_packed_patterns_len(const acg_packed* s) { return s ? acg_patterns_len(s->inner) : 0; }
+int acg_packed_searcher_variant(const acg_packed* s, int* fat, int* mask_len, int* vector_bytes) {
+  if (!s || !s->teddy) return 0;
+  if (fat) *fat = s->fat ? 1 : 0;
+  if (mask_len) *mask_len = s->mask_len;
+  if (vector_bytes) *vector_bytes = s->vector_bytes;
+  return 1;
 }
 
 const char* acg_strerror(int code) {

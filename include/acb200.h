@@ -181,6 +181,48 @@ int acg_count_overlapping_dev(const acg_dfa* dfa, const void* d_hay, uint64_t ha
                               uint64_t span_start, uint64_t span_end,
                               uint64_t* n_out, uint64_t* fnv, float* kernel_ms);
 
+/* ---- packed searcher: packed::Config / Builder / Searcher, src/packed/api.rs ----------------
+ * The reference's standalone "packed" API is Teddy (or Rabin-Karp) over a small pattern set with
+ * leftmost semantics.  On the device its role is played by the same K3/K3b kernel pair that serves
+ * AhoCorasick (a fingerprint prefilter feeding the DFA verifier); what this API keeps from the
+ * reference is the construction contract -- when Builder::build returns None -- and the search
+ * results, which are the leftmost-first / leftmost-longest non-overlapping matches. */
+enum { ACG_PACKED_FORCE_NONE = 0, ACG_PACKED_FORCE_TEDDY = 1, ACG_PACKED_FORCE_RABINKARP = 2 };
+typedef struct {
+  int32_t match_kind;               /* ACG_LEFTMOST_FIRST (default) | ACG_LEFTMOST_LONGEST, api.rs:28-46 */
+  int32_t force;                    /* Config::only_teddy / only_rabin_karp, api.rs:143-190 */
+  int32_t only_teddy_fat;           /* -1 = None, 0 / 1 = Some(false / true), api.rs:158 */
+  int32_t only_teddy_256bit;        /* -1 = None, 0 / 1 = Some(false / true), api.rs:170 */
+  int32_t heuristic_pattern_limits; /* default 1, api.rs:196 */
+} acg_packed_config;
+typedef struct acg_packed acg_packed;
+void acg_packed_config_default(acg_packed_config* c);
+/* Builder::extend + Builder::build (api.rs:253-345).  Returns ACG_OK with *out == NULL where the
+ * reference returns None: no patterns, an empty pattern, more than 128 patterns, or a pattern set
+ * Teddy declines (teddy/builder.rs:98-231, decided as on x86-64 with AVX2). */
+int acg_packed_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                     const acg_packed_config* cfg, acg_packed** out);
+/* Same decision and tables without CUDA; searches return ACG_E_NO_DEVICE. */
+int acg_packed_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                          const acg_packed_config* cfg, acg_packed** out);
+void acg_packed_free(acg_packed* s);
+/* Searcher::find_iter (api.rs:580) -- and find_in (:529) applied repeatedly for a sub-span:
+ * non-overlapping leftmost matches inside [span_start, span_end).  Two-call protocol on
+ * ACG_E_OVERFLOW; ACG_E_INVALID_SPAN where the reference's slice indexing panics. */
+int acg_packed_find_iter(const acg_packed* s, const uint8_t* hay, uint64_t hay_len,
+                         uint64_t span_start, uint64_t span_end, acg_match* out, uint64_t cap,
+                         uint64_t* n_out);
+/* Searcher::find (api.rs:491) / find_in (:529). */
+int acg_packed_find(const acg_packed* s, const uint8_t* hay, uint64_t hay_len, uint64_t span_start,
+                    uint64_t span_end, acg_match* out, int* found);
+int acg_packed_match_kind(const acg_packed* s);        /* api.rs:612 */
+uint64_t acg_packed_minimum_len(const acg_packed* s);  /* api.rs:627: 0 for Rabin-Karp, else Teddy's */
+uint64_t acg_packed_memory_usage(const acg_packed* s); /* api.rs:634 (heap of the device engine's tables) */
+uint64_t acg_packed_patterns_len(const acg_packed* s);
+/* Which searcher the reference would run: returns 1 for Teddy (and fills fat / mask_len /
+ * vector_bytes), 0 for Rabin-Karp. */
+int acg_packed_searcher_variant(const acg_packed* s, int* fat, int* mask_len, int* vector_bytes);
+
 /* per-call statistics of the most recent search on this handle (bench glue) */
 typedef struct {
   int32_t engine;
