@@ -25,6 +25,7 @@
 // identical to the reference's lazy iteration).
 #pragma once
 #include <cstdint>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -289,5 +290,134 @@ AhoCorasick AhoCorasickBuilder::build(const Patterns& patterns) const {
   if (rc) throw DeviceError(rc);
   return AhoCorasick(h);
 }
+
+// ---- `aho_corasick::packed`, src/packed/api.rs --------------------------------------------------
+namespace packed {
+
+enum class MatchKind : int { LeftmostFirst = ACG_LEFTMOST_FIRST, LeftmostLongest = ACG_LEFTMOST_LONGEST };  // :28-46
+
+class Builder;
+class Searcher;
+
+// `packed::Config`, :87-230
+class Config {
+ public:
+  Config() { acg_packed_config_default(&c_); }
+  Builder builder() const;                                                                       // :127
+  Config& match_kind(MatchKind k) { c_.match_kind = int(k); return *this; }                       // :132
+  Config& only_teddy(bool yes) { c_.force = yes ? ACG_PACKED_FORCE_TEDDY : ACG_PACKED_FORCE_NONE; return *this; }  // :143
+  Config& only_teddy_fat(std::optional<bool> yes) { c_.only_teddy_fat = yes ? int(*yes) : -1; return *this; }      // :158
+  Config& only_teddy_256bit(std::optional<bool> yes) { c_.only_teddy_256bit = yes ? int(*yes) : -1; return *this; }  // :170
+  Config& only_rabin_karp(bool yes) { c_.force = yes ? ACG_PACKED_FORCE_RABINKARP : ACG_PACKED_FORCE_NONE; return *this; }  // :181
+  Config& heuristic_pattern_limits(bool yes) { c_.heuristic_pattern_limits = yes; return *this; }  // :196
+  // not in the reference: decide and build the tables without touching CUDA
+  Config& host_only(bool yes) { host_only_ = yes; return *this; }
+ private:
+  friend class Builder;
+  acg_packed_config c_;
+  bool host_only_ = false;
+};
+
+// `packed::Searcher`, :396-660
+class Searcher {
+ public:
+  Searcher(Searcher&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  Searcher& operator=(Searcher&& o) noexcept {
+    if (this != &o) { if (h_) acg_packed_free(h_); h_ = o.h_; o.h_ = nullptr; }
+    return *this;
+  }
+  Searcher(const Searcher&) = delete;
+  Searcher& operator=(const Searcher&) = delete;
+  ~Searcher() { if (h_) acg_packed_free(h_); }
+
+  template <class Patterns>
+  static std::optional<Searcher> create(const Patterns& patterns);  // Searcher::new, :440
+  static Config config() { return Config(); }                       // :451
+  static Builder builder();                                         // :458
+
+  // find_in, :529 (the span of `in`; anchored / earliest do not exist for packed searchers)
+  bool find_in(const Input& in, Match* out) const {
+    acg_match m{};
+    int found = 0;
+    const int rc = acg_packed_find(h_, hay(in), in.haystack().size(), in.start(), in.end(), &m, &found);
+    if (rc) Result<int>::throw_error(rc);
+    if (found && out) *out = Match(m.pid, m.start, m.end);
+    return found != 0;
+  }
+  bool find(std::string_view haystack, Match* out) const { return find_in(Input(haystack), out); }  // :491
+  // find_iter, :580
+  MatchIter find_iter(const Input& in) const {
+    std::vector<acg_match> buf(cap_hint_);
+    uint64_t n = 0;
+    for (;;) {
+      const int rc = acg_packed_find_iter(h_, hay(in), in.haystack().size(), in.start(), in.end(), buf.data(),
+                                          buf.size(), &n);
+      if (rc == ACG_E_OVERFLOW) { cap_hint_ = n + n / 8 + 64; buf.resize(cap_hint_); continue; }
+      if (rc) Result<int>::throw_error(rc);
+      break;
+    }
+    std::vector<Match> out;
+    out.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) out.emplace_back(buf[i].pid, buf[i].start, buf[i].end);
+    return MatchIter(std::move(out));
+  }
+  MatchKind match_kind() const { return MatchKind(acg_packed_match_kind(h_)); }  // :612
+  uint64_t minimum_len() const { return acg_packed_minimum_len(h_); }            // :627
+  uint64_t memory_usage() const { return acg_packed_memory_usage(h_); }          // :634
+  uint64_t patterns_len() const { return acg_packed_patterns_len(h_); }
+
+ private:
+  friend class Builder;
+  explicit Searcher(acg_packed* h) : h_(h) {}
+  static const uint8_t* hay(const Input& in) { return reinterpret_cast<const uint8_t*>(in.haystack().data()); }
+  acg_packed* h_ = nullptr;
+  mutable uint64_t cap_hint_ = 4096;
+};
+
+// `packed::Builder`, :232-357
+class Builder {
+ public:
+  Builder() = default;
+  explicit Builder(const Config& c) : cfg_(c) {}
+  Builder& add(std::string_view pattern) { pats_.emplace_back(pattern); return *this; }  // :303
+  template <class Patterns>
+  Builder& extend(const Patterns& patterns) {                                            // :337
+    for (const auto& p : patterns) add(std::string_view(p));
+    return *this;
+  }
+  size_t len() const { return pats_.size(); }                                            // :349
+  size_t minimum_len() const {                                                           // :354
+    size_t m = 0;
+    for (size_t i = 0; i < pats_.size(); ++i) m = (i == 0 || pats_[i].size() < m) ? pats_[i].size() : m;
+    return m;
+  }
+  // build, :253: nullopt where the reference returns None
+  std::optional<Searcher> build() const {
+    std::vector<const uint8_t*> ptrs;
+    std::vector<uint64_t> lens;
+    for (const auto& p : pats_) {
+      ptrs.push_back(reinterpret_cast<const uint8_t*>(p.data()));
+      lens.push_back(p.size());
+    }
+    acg_packed* h = nullptr;
+    const int rc = (cfg_.host_only_ ? acg_packed_build_host : acg_packed_build)(ptrs.data(), lens.data(), ptrs.size(),
+                                                                                &cfg_.c_, &h);
+    if (rc == ACG_E_STATE_ID_OVERFLOW || rc == ACG_E_PATTERN_ID_OVERFLOW || rc == ACG_E_PATTERN_TOO_LONG)
+      throw BuildError(rc);
+    if (rc) throw DeviceError(rc);
+    if (!h) return std::nullopt;
+    return Searcher(h);
+  }
+ private:
+  Config cfg_;
+  std::vector<std::string> pats_;
+};
+
+inline Builder Config::builder() const { return Builder(*this); }
+inline Builder Searcher::builder() { return Builder(); }
+template <class Patterns>
+std::optional<Searcher> Searcher::create(const Patterns& patterns) { return Builder().extend(patterns).build(); }
+
+}  // namespace packed
 
 }  // namespace acb200
