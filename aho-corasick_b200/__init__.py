@@ -454,23 +454,43 @@ class AhoCorasick:
         return self.try_find(hay, span, earliest=earliest) is not None
 
     # ---- replace / stream: host-side glue over find_iter, as in the reference -------------------
-    def try_replace_all_with(self, hay, dst: bytearray, replace_with):
-        """`try_replace_all_with_bytes`, src/automaton.rs:498-550: `replace_with(match, matched
-        bytes, dst) -> bool`; returning False stops the replacement after that match."""
-        keep, ptr, n = _hay_ptr(hay)
-        view = memoryview(keep).cast("B") if n else b""
+    @staticmethod
+    def _is_char_boundary(view, n, i):
+        """`str::is_char_boundary` on UTF-8 bytes."""
+        if i == 0 or i == n:
+            return True
+        return i < n and (view[i] & 0xC0) != 0x80
+
+    @staticmethod
+    def _splice(view, n, matches, dst: bytearray, replace_with, char_boundaries=False):
+        """The loop of `try_replace_all_with{,_bytes}`, src/automaton.rs:498-550, over an already
+        materialised match list.  With `char_boundaries` (the `&str` flavour) matches that split a
+        UTF-8 code point are skipped (:514-518)."""
         last = 0
-        for m in self.try_find_iter(keep):
+        for m in matches:
+            if char_boundaries and not (AhoCorasick._is_char_boundary(view, n, m.start())
+                                        and AhoCorasick._is_char_boundary(view, n, m.end())):
+                continue
             dst += bytes(view[last:m.start()])
             last = m.end()
             if not replace_with(m, bytes(view[m.start():m.end()]), dst):
                 break
         dst += bytes(view[last:])
 
-    def try_replace_all_bytes(self, hay, replace_with):  # src/automaton.rs:457-480
+    def try_replace_all_with(self, hay, dst: bytearray, replace_with):
+        """`try_replace_all_with_bytes`, src/automaton.rs:525-550: `replace_with(match, matched
+        bytes, dst) -> bool`; returning False stops the replacement after that match."""
+        keep, ptr, n = _hay_ptr(hay)
+        view = memoryview(keep).cast("B") if n else b""
+        self._splice(view, n, self.try_find_iter(keep), dst, replace_with)
+
+    def _replacements(self, replace_with):
         if len(replace_with) != self.patterns_len():
             raise ValueError("replace_all requires a replacement for every pattern in the automaton")
-        reps = [r.encode() if isinstance(r, str) else bytes(r) for r in replace_with]
+        return [r.encode() if isinstance(r, str) else bytes(r) for r in replace_with]
+
+    def try_replace_all_bytes(self, hay, replace_with):  # src/automaton.rs:457-480
+        reps = self._replacements(replace_with)
         dst = bytearray()
 
         def put(m, _, out):
@@ -479,8 +499,17 @@ class AhoCorasick:
         self.try_replace_all_with(hay, dst, put)
         return bytes(dst)
 
-    def try_replace_all(self, hay: str, replace_with):  # src/automaton.rs:433-455
-        return self.try_replace_all_bytes(hay.encode(), replace_with).decode()
+    def try_replace_all(self, hay: str, replace_with):  # src/automaton.rs:433-455 -> :498-523
+        reps = self._replacements(replace_with)
+        keep, ptr, n = _hay_ptr(hay.encode())
+        view = memoryview(keep).cast("B") if n else b""
+        dst = bytearray()
+
+        def put(m, _, out):
+            out += reps[m.pattern()]
+            return True
+        self._splice(view, n, self.try_find_iter(keep), dst, put, char_boundaries=True)
+        return dst.decode()
 
     replace_all = try_replace_all                # src/ahocorasick.rs:651
     replace_all_bytes = try_replace_all_bytes    # :693

@@ -158,6 +158,28 @@ class MatchIter {
 using FindIter = MatchIter;
 using FindOverlappingIter = MatchIter;
 
+namespace detail {
+// `str::is_char_boundary` on UTF-8 bytes
+inline bool is_char_boundary(std::string_view s, uint64_t i) {
+  if (i == 0 || i == s.size()) return true;
+  return i < s.size() && (static_cast<unsigned char>(s[i]) & 0xC0) != 0x80;
+}
+// The loop of try_replace_all_with{,_bytes} (src/automaton.rs:498-550) over a materialised match
+// list: `f(match, matched text, dst) -> bool`, false stops after that match.  With
+// `char_boundaries` (the &str flavour) matches that split a UTF-8 code point are skipped (:514-518).
+template <class F>
+void splice(std::string_view hay, const std::vector<Match>& matches, std::string& dst, F&& f, bool char_boundaries) {
+  uint64_t last = 0;
+  for (const Match& m : matches) {
+    if (char_boundaries && !(is_char_boundary(hay, m.start()) && is_char_boundary(hay, m.end()))) continue;
+    dst.append(hay.substr(last, m.start() - last));
+    last = m.end();
+    if (!f(m, hay.substr(m.start(), m.end() - m.start()), dst)) break;
+  }
+  dst.append(hay.substr(last));
+}
+}  // namespace detail
+
 class AhoCorasick;
 
 // `AhoCorasickBuilder`, src/ahocorasick.rs:2135-2617
@@ -236,10 +258,43 @@ class AhoCorasick {
     return std::move(try_find_overlapping_iter(in).unwrap());
   }
 
+  // replace_all_with / replace_all_with_bytes, :834 / :887 (src/automaton.rs:498-550)
+  template <class F>
+  void replace_all_with(std::string_view haystack, std::string& dst, F&& replace_with) const {
+    detail::splice(haystack, find_iter(Input(haystack)).collect(), dst, replace_with, true);
+  }
+  template <class F>
+  void replace_all_with_bytes(std::string_view haystack, std::string& dst, F&& replace_with) const {
+    detail::splice(haystack, find_iter(Input(haystack)).collect(), dst, replace_with, false);
+  }
+  // replace_all / replace_all_bytes, :651 / :693: one replacement per pattern (the reference panics
+  // otherwise, src/automaton.rs:443-448)
+  template <class Replacements>
+  std::string replace_all(std::string_view haystack, const Replacements& replace_with) const {
+    return replace_impl(haystack, replace_with, true);
+  }
+  template <class Replacements>
+  std::string replace_all_bytes(std::string_view haystack, const Replacements& replace_with) const {
+    return replace_impl(haystack, replace_with, false);
+  }
+
   acg_dfa* raw() const { return h_; }
 
  private:
   friend class AhoCorasickBuilder;
+  template <class Replacements>
+  std::string replace_impl(std::string_view haystack, const Replacements& replace_with, bool char_boundaries) const {
+    std::vector<std::string_view> reps;
+    for (const auto& r : replace_with) reps.emplace_back(r);
+    if (reps.size() != patterns_len())
+      throw std::invalid_argument("replace_all requires a replacement for every pattern in the automaton");
+    std::string dst;
+    dst.reserve(haystack.size());
+    detail::splice(haystack, find_iter(Input(haystack)).collect(), dst,
+                   [&](const Match& m, std::string_view, std::string& out) { out.append(reps[m.pattern()]); return true; },
+                   char_boundaries);
+    return dst;
+  }
   explicit AhoCorasick(acg_dfa* h) : h_(h) {}
   void reset() {
     if (h_) acg_dfa_free(h_);

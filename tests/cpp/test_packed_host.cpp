@@ -56,6 +56,46 @@ int main() {
   try { acb200::Match m; s->find("xx maple xx", &m); } catch (const acb200::DeviceError& e) { threw = e.code() == ACG_E_NO_DEVICE; }
   CHECK(threw);
 
+  // ---- replace glue (src/automaton.rs:498-550) over hand-made match lists -------------------
+  {
+    using acb200::Match;
+    const std::string hay = "append the app to the appendage";
+    // leftmost-first matches of {append, appendage, app} (src/ahocorasick.rs:651-690)
+    const std::vector<Match> lf = {Match(0, 0, 6), Match(2, 11, 14), Match(0, 22, 28)};
+    const std::vector<std::string> reps = {"x", "y", "z"};
+    std::string dst;
+    acb200::detail::splice(hay, lf, dst, [&](const Match& m, std::string_view, std::string& out) {
+      out.append(reps[m.pattern()]);
+      return true;
+    }, true);
+    CHECK(dst == "x the z to the xage");
+    dst.clear();
+    acb200::detail::splice(hay, lf, dst, [&](const Match& m, std::string_view txt, std::string& out) {
+      for (char c : txt) out.push_back(char(c - 32));
+      return m.pattern() != 2;
+    }, false);
+    CHECK(dst == "APPEND the APP to the appendage");  // stops after the first "app"
+    // a match that splits a code point is skipped by the &str flavour only
+    const std::string utf = "a\xc3\xa9" "b";
+    const std::vector<Match> split = {Match(0, 1, 2), Match(1, 3, 4)};
+    const std::vector<std::string> r2 = {"?", "B"};
+    auto put = [&](const Match& m, std::string_view, std::string& out) { out.append(r2[m.pattern()]); return true; };
+    dst.clear();
+    acb200::detail::splice(utf, split, dst, put, true);
+    CHECK(dst == "a\xc3\xa9" "B");
+    dst.clear();
+    acb200::detail::splice(utf, split, dst, put, false);
+    CHECK(dst == "a?\xa9" "B");
+    CHECK(acb200::detail::is_char_boundary(utf, 0) && acb200::detail::is_char_boundary(utf, 1) &&
+          !acb200::detail::is_char_boundary(utf, 2) && acb200::detail::is_char_boundary(utf, 3) &&
+          acb200::detail::is_char_boundary(utf, 4) && !acb200::detail::is_char_boundary(utf, 5));
+    // replace_all on a host-only automaton: argument check first, then "no device"
+    acb200::AhoCorasick ac;  // empty handle: patterns_len() == 0
+    bool threw2 = false;
+    try { ac.replace_all("abc", std::vector<std::string>{"x"}); } catch (const std::invalid_argument&) { threw2 = true; }
+    CHECK(threw2);
+  }
+
   if (failures == 0) std::printf("all checks passed\n");
   return failures == 0 ? 0 : 1;
 }
