@@ -515,12 +515,13 @@ class AhoCorasick:
     replace_all_bytes = try_replace_all_bytes    # :693
     replace_all_with = try_replace_all_with      # :834 (bytes flavour)
 
-    def try_stream_find_iter(self, rdr, chunk_bytes=64 << 20):
-        """`try_stream_find_iter`, src/ahocorasick.rs:1677 -> src/automaton.rs:1059-1256: matches of
-        a byte stream (anything with .read(n)), offsets relative to the start of the stream.  Like
-        the reference it is limited to MatchKind::Standard without empty patterns, and like the
-        reference's 64 KB roll buffer (src/util/buffer.rs) only max_pattern_len-1 bytes are carried
-        from one device scan to the next."""
+    def _stream_chunks(self, rdr, chunk_bytes):
+        """`StreamChunkIter`, src/automaton.rs:1059-1256: the stream as an alternation of
+        ("bytes", data) for text between matches and ("match", Match, matched bytes), offsets
+        relative to the start of the stream.  Like the reference it is limited to
+        MatchKind::Standard without empty patterns (:1087-1103), and like the reference's roll buffer
+        (src/util/buffer.rs) only max_pattern_len-1 bytes are carried from one device scan to the
+        next: a match that straddles a block boundary starts no earlier than that."""
         if self.match_kind() != MatchKind.Standard:
             raise MatchError(-12)
         if self.patterns_len() and self.min_pattern_len() == 0:
@@ -529,6 +530,7 @@ class AhoCorasick:
         carry = b""
         base = 0          # stream offset of carry[0]
         cursor = 0        # stream offset where the iterator restarts
+        emitted = 0       # stream offset up to which chunks have been yielded
         while True:
             block = rdr.read(chunk_bytes)
             if not block:
@@ -536,29 +538,49 @@ class AhoCorasick:
             buf = np.frombuffer(carry + bytes(block), dtype=np.uint8)
             r = self.try_find_iter_np(buf, span=(cursor - base, buf.size))
             for pid, s, e in zip(r["pid"].tolist(), r["start"].tolist(), r["end"].tolist()):
-                yield Match(pid, base + s, base + e)
+                if base + s > emitted:
+                    yield ("bytes", buf[emitted - base:s].tobytes())
+                yield ("match", Match(pid, base + s, base + e), buf[s:e].tobytes())
+                emitted = base + e
             if len(r):
                 cursor = base + int(r["end"][-1])
-            # a match that straddles the block boundary starts no earlier than end-(max_len-1)
             keep_from = max(cursor, base + buf.size - back)
+            if keep_from > emitted:  # these bytes can no longer be part of a match
+                yield ("bytes", buf[emitted - base:keep_from - base].tobytes())
+                emitted = keep_from
             carry = buf[keep_from - base:].tobytes()
             base = keep_from
             cursor = max(cursor, base)
+        if emitted - base < len(carry):
+            yield ("bytes", carry[emitted - base:])
+
+    def try_stream_find_iter(self, rdr, chunk_bytes=64 << 20):
+        """`try_stream_find_iter`, src/ahocorasick.rs:1677: matches of a byte stream (anything with
+        .read(n)); equals find_iter over the concatenated stream."""
+        for chunk in self._stream_chunks(rdr, chunk_bytes):
+            if chunk[0] == "match":
+                yield chunk[1]
 
     stream_find_iter = try_stream_find_iter      # :906
+
+    def try_stream_replace_all_with(self, rdr, wtr, replace_with, chunk_bytes=64 << 20):
+        """`try_stream_replace_all_with`, src/ahocorasick.rs:1807 -> src/automaton.rs:601-636:
+        `replace_with(match, matched bytes, wtr)` writes the replacement; text between matches is
+        copied through as soon as it can no longer be part of a match."""
+        for chunk in self._stream_chunks(rdr, chunk_bytes):
+            if chunk[0] == "bytes":
+                wtr.write(chunk[1])
+            else:
+                replace_with(chunk[1], chunk[2], wtr)
 
     def try_stream_replace_all(self, rdr, wtr, replace_with, chunk_bytes=64 << 20):  # :1751
         if len(replace_with) != self.patterns_len():
             raise ValueError("stream_replace_all requires a replacement for every pattern in the automaton")
         reps = [r.encode() if isinstance(r, str) else bytes(r) for r in replace_with]
-        data = rdr.read()   # replacement needs the unmatched bytes as well; kept simple: one read
-        last = 0
-        import io
-        for m in self.try_stream_find_iter(io.BytesIO(data), chunk_bytes):
-            wtr.write(data[last:m.start()])
-            wtr.write(reps[m.pattern()])
-            last = m.end()
-        wtr.write(data[last:])
+        self.try_stream_replace_all_with(rdr, wtr, lambda m, _, w: w.write(reps[m.pattern()]), chunk_bytes)
+
+    stream_replace_all = try_stream_replace_all            # :964
+    stream_replace_all_with = try_stream_replace_all_with  # :1007
 
     # ---- device-resident haystack (torch tensor / raw pointer), for the roofline measurement ----
     def find_overlapping_iter_dev_np(self, dev_ptr, hay_len, span=None):

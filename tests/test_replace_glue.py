@@ -68,3 +68,90 @@ def test_char_boundary_rule():
     want = [i == 0 or i == n or (i < n and (b[i] & 0xC0) != 0x80) for i in range(n + 2)]
     got = [ab.AhoCorasick._is_char_boundary(b, n, i) for i in range(n + 2)]
     assert got == want and got[:4] == [True, True, False, True] and got[n + 1] is False
+
+
+# ---- stream search / replace (src/automaton.rs:1059-1256, 567-636) ----------------------------
+import io  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+import golden_util as G  # noqa: E402
+from aho_corasick_b200 import workload as W  # noqa: E402
+
+AC = G.load("ac_vectors.json")
+
+
+class OracleBackedNp(OracleBacked):
+    def try_find_iter_np(self, hay, span=None, anchored=ab.Anchored.No):
+        return self._o.find_iter_np(np.ascontiguousarray(hay), span=span)
+
+
+def _apply(hay, matches, reps):
+    out, last = bytearray(), 0
+    for pid, s, e in matches:
+        out += hay[last:s] + reps[pid]
+        last = e
+    return bytes(out + hay[last:])
+
+
+def test_stream_find_iter_equals_find_iter_on_reference_vectors():
+    # the stream rows of src/tests.rs:999-1036: every Standard vector without empty patterns
+    n = 0
+    for t in G.collection(AC, "AC_STANDARD_NON_OVERLAPPING"):
+        if any(len(p) == 0 for p in t["patterns"]):
+            continue
+        ac = OracleBackedNp(t["patterns"], ab.MatchKind.Standard)
+        for chunk in (1, 2, 3, 7, 64 << 20):
+            got = [m.as_tuple() for m in ac.stream_find_iter(io.BytesIO(t["haystack"]), chunk_bytes=chunk)]
+            assert got == t["matches"], (t["name"], chunk)
+            out = io.BytesIO()
+            reps = [b"<%d>" % i for i in range(len(t["patterns"]))]
+            ac.stream_replace_all(io.BytesIO(t["haystack"]), out, reps, chunk_bytes=chunk)
+            assert out.getvalue() == _apply(t["haystack"], t["matches"], reps), (t["name"], chunk)
+        n += 1
+    assert n > 20
+
+
+def test_stream_unsupported_configurations():
+    # src/automaton.rs:1087-1103
+    with pytest.raises(ab.MatchError) as e:
+        list(OracleBackedNp([b"a"], ab.MatchKind.LeftmostFirst).stream_find_iter(io.BytesIO(b"a")))
+    assert e.value.kind == "UnsupportedStream"
+    with pytest.raises(ab.MatchError) as e:
+        list(OracleBackedNp([b"a", b""], ab.MatchKind.Standard).stream_find_iter(io.BytesIO(b"a")))
+    assert e.value.kind == "UnsupportedEmpty"
+    with pytest.raises(ValueError):
+        OracleBackedNp([b"a", b"b"], ab.MatchKind.Standard).stream_replace_all(io.BytesIO(b"a"), io.BytesIO(), [b"x"])
+
+
+def test_stream_with_straddling_matches_and_chunked_output():
+    pats = W.make_patterns(200, 77)
+    t = np.empty(1 << 20, dtype=np.uint8)
+    W.fill_haystack(t, 99)
+    W.plant(t, pats, 5, period=512, window=256)
+    ac = OracleBackedNp(pats, ab.MatchKind.Standard)
+    want = ac._o.find_iter(t)
+    assert len(want) > 1500
+    data = t.tobytes()
+    for chunk in ((1 << 16) + 13, 4099, 1 << 20, 5 << 20):
+        got = [m.as_tuple() for m in ac.stream_find_iter(io.BytesIO(data), chunk_bytes=chunk)]
+        assert got == want, chunk
+    # the chunk stream is a partition of the input: text and matches in stream order
+    pos, pieces = 0, []
+    for c in ac._stream_chunks(io.BytesIO(data), 70001):
+        if c[0] == "bytes":
+            pieces.append(c[1])
+            pos += len(c[1])
+        else:
+            assert c[1].start() == pos and data[c[1].start():c[1].end()] == c[2]
+            pieces.append(c[2])
+            pos = c[1].end()
+    assert b"".join(pieces) == data
+    reps = [b"<%d>" % i for i in range(len(pats))]
+    out = io.BytesIO()
+    ac.try_stream_replace_all(io.BytesIO(data), out, reps, chunk_bytes=1 << 15)
+    assert out.getvalue() == _apply(data, want, reps)
+    # closure flavour: sees the matched bytes and the writer
+    out = io.BytesIO()
+    ac.stream_replace_all_with(io.BytesIO(data), out, lambda m, txt, w: w.write(txt.upper()), chunk_bytes=1 << 17)
+    assert out.getvalue().lower() == data.lower() and len(out.getvalue()) == len(data)
