@@ -201,6 +201,27 @@ def _span(span, n):
     return int(span[0]), int(span[1])
 
 
+class OverlappingState:
+    """`OverlappingState`, src/automaton.rs:782-840: the cursor of a resumable overlapping search.
+    The device scan is eager, so the state holds the ordered match list of the search it was first
+    used with and hands out one match per `try_find_overlapping` call -- the same sequence the
+    reference's state machine produces.  As in the reference, a state must be reused only with the
+    same automaton and input."""
+    __slots__ = ("_matches", "_next", "_mat")
+
+    def __init__(self):
+        self._matches = None
+        self._next = 0
+        self._mat = None
+
+    @staticmethod
+    def start():  # :817
+        return OverlappingState()
+
+    def get_match(self):  # :829
+        return self._mat
+
+
 class AhoCorasickBuilder:
     """`AhoCorasickBuilder`, src/ahocorasick.rs:2135-2617 (same knobs, same defaults)."""
 
@@ -428,6 +449,21 @@ class AhoCorasick:
     def try_find_overlapping_iter(self, hay, span=None, anchored=Anchored.No):  # :1350
         r = self.try_find_overlapping_iter_np(hay, span, anchored)
         return [Match(a, b, c) for a, b, c in zip(r["pid"], r["start"], r["end"])]
+
+    def try_find_overlapping(self, hay, state: OverlappingState, span=None, anchored=Anchored.No):
+        """`try_find_overlapping`, src/ahocorasick.rs:1184: advance `state` to the next overlapping
+        match (or to None).  Errors are the ones of try_find_overlapping_iter (src/automaton.rs
+        :397-423) and are reported on every call, as in the reference."""
+        if state._matches is None:
+            state._matches = self.try_find_overlapping_iter(hay, span, anchored)
+            state._next = 0
+        if state._next < len(state._matches):
+            state._mat = state._matches[state._next]
+            state._next += 1
+        else:
+            state._mat = None
+
+    find_overlapping = try_find_overlapping  # :470
 
     find_iter = try_find_iter  # :562 (the infallible versions panic where these raise)
     find_overlapping_iter = try_find_overlapping_iter  # :609

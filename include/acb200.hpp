@@ -158,6 +158,22 @@ class MatchIter {
 using FindIter = MatchIter;
 using FindOverlappingIter = MatchIter;
 
+// `OverlappingState`, src/automaton.rs:782-840: the cursor of a resumable overlapping search.  The
+// device scan is eager, so the state holds the ordered match list of the search it was first used
+// with and hands out one match per try_find_overlapping call -- the sequence the reference's state
+// machine produces.  As in the reference, reuse a state only with the same automaton and input.
+class OverlappingState {
+ public:
+  static OverlappingState start() { return OverlappingState(); }  // :817
+  std::optional<Match> get_match() const { return mat_; }         // :829
+ private:
+  friend class AhoCorasick;
+  bool started_ = false;
+  std::vector<Match> matches_;
+  size_t next_ = 0;
+  std::optional<Match> mat_;
+};
+
 namespace detail {
 // `str::is_char_boundary` on UTF-8 bytes
 inline bool is_char_boundary(std::string_view s, uint64_t i) {
@@ -257,6 +273,23 @@ class AhoCorasick {
   FindOverlappingIter find_overlapping_iter(const Input& in) const {  // :609
     return std::move(try_find_overlapping_iter(in).unwrap());
   }
+
+  // try_find_overlapping, :1184: advance `state` to the next overlapping match (or to none)
+  Result<bool> try_find_overlapping(const Input& in, OverlappingState& state) const {
+    Result<bool> r;
+    if (!state.started_) {
+      auto it = try_find_overlapping_iter(in);
+      if (it.is_err()) { r.error = it.error; return r; }
+      state.matches_ = it.value.collect();
+      state.next_ = 0;
+      state.started_ = true;
+    }
+    if (state.next_ < state.matches_.size()) state.mat_ = state.matches_[state.next_++];
+    else state.mat_.reset();
+    r.value = state.mat_.has_value();
+    return r;
+  }
+  void find_overlapping(const Input& in, OverlappingState& state) const { try_find_overlapping(in, state).unwrap(); }  // :470
 
   // replace_all_with / replace_all_with_bytes, :834 / :887 (src/automaton.rs:498-550)
   template <class F>

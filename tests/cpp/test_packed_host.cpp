@@ -96,6 +96,18 @@ int main() {
     CHECK(threw2);
   }
 
+  // ---- OverlappingState on a host-only automaton: the error is reported on every call ----------
+  {
+    std::vector<std::string> p3 = {"append", "appendage", "app"};
+    acb200::OverlappingState st = acb200::OverlappingState::start();
+    CHECK(!st.get_match().has_value());
+    acb200::AhoCorasick none;  // empty handle: acg_find_overlapping reports an invalid argument
+    auto r1 = none.try_find_overlapping("append", st);
+    CHECK(r1.is_err() && !st.get_match().has_value());
+    auto r2 = none.try_find_overlapping("append", st);
+    CHECK(r2.is_err());
+  }
+
   if (failures == 0) std::printf("all checks passed\n");
   return failures == 0 ? 0 : 1;
 }

@@ -410,6 +410,23 @@ def test_replace_all_and_stream():
     assert out.getvalue() == _apply(t.tobytes(), want, reps)
 
 
+def test_find_overlapping_with_state():
+    """`find_overlapping` + `OverlappingState`, doc example of src/ahocorasick.rs:430-470."""
+    ac = build([b"append", b"appendage", b"app"], 0)
+    hay = b"append the app to the appendage"
+    state = ab.OverlappingState.start()
+    got = []
+    while True:
+        ac.find_overlapping(hay, state)
+        m = state.get_match()
+        if m is None:
+            break
+        got.append(m.as_tuple())
+    assert got == [(2, 0, 3), (0, 0, 6), (2, 11, 14), (2, 22, 25), (0, 22, 28), (1, 22, 31)]
+    with pytest.raises(ab.MatchError):
+        build([b"a"], 1).try_find_overlapping(b"a", ab.OverlappingState.start())
+
+
 def test_dense_outputs_and_unselective_fingerprints():
     """Stress the slow paths: (1) far more matches than the initial tuple capacity (counter
     overflow -> regrow -> rescan), (2) pattern sets whose fingerprints cannot be selective (every

@@ -155,3 +155,44 @@ def test_stream_with_straddling_matches_and_chunked_output():
     out = io.BytesIO()
     ac.stream_replace_all_with(io.BytesIO(data), out, lambda m, txt, w: w.write(txt.upper()), chunk_bytes=1 << 17)
     assert out.getvalue().lower() == data.lower() and len(out.getvalue()) == len(data)
+
+
+# ---- OverlappingState / find_overlapping (src/ahocorasick.rs:470, 1184; automaton.rs:756-840) ---
+class OracleBackedOverlapping(OracleBacked):
+    def try_find_overlapping_iter(self, hay, span=None, anchored=ab.Anchored.No):
+        if self.match_kind() != ab.MatchKind.Standard:
+            raise ab.MatchError(-13)
+        return [ab.Match(*m) for m in self._o.find_overlapping_iter(bytes(hay), span=span)]
+
+
+def test_find_overlapping_state_doc_example():
+    ac = OracleBackedOverlapping(PATS, ab.MatchKind.Standard)
+    state = ab.OverlappingState.start()
+    assert state.get_match() is None
+    got = []
+    while True:
+        ac.find_overlapping(HAY, state)
+        m = state.get_match()
+        if m is None:
+            break
+        got.append(m.as_tuple())
+    assert got == [(2, 0, 3), (0, 0, 6), (2, 11, 14), (2, 22, 25), (0, 22, 28), (1, 22, 31)]
+    ac.find_overlapping(HAY, state)      # stays exhausted
+    assert state.get_match() is None
+    # a sub-span, fresh state
+    state = ab.OverlappingState.start()
+    ac.try_find_overlapping(HAY, state, span=(11, 25))
+    assert state.get_match().as_tuple() == (2, 11, 14)
+    ac.try_find_overlapping(HAY, state, span=(11, 25))
+    assert state.get_match().as_tuple() == (2, 22, 25)
+    ac.try_find_overlapping(HAY, state, span=(11, 25))
+    assert state.get_match() is None
+
+
+def test_find_overlapping_errors_are_reported_each_call():
+    ac = OracleBackedOverlapping(PATS, ab.MatchKind.LeftmostFirst)
+    state = ab.OverlappingState.start()
+    for _ in range(2):
+        with pytest.raises(ab.MatchError) as e:
+            ac.try_find_overlapping(HAY, state)
+        assert e.value.kind == "UnsupportedOverlapping" and state.get_match() is None
