@@ -201,6 +201,98 @@ def _span(span, n):
     return int(span[0]), int(span[1])
 
 
+class Input:
+    """`Input`, src/util/search.rs:60-720: a haystack with a span, an anchored mode and the
+    `earliest` flag.  Every search method accepts either a plain haystack (with keyword arguments)
+    or an `Input`."""
+    __slots__ = ("_hay", "_n", "_start", "_end", "_anchored", "_earliest")
+
+    def __init__(self, haystack):  # Input::new, :93
+        keep, _, n = _hay_ptr(haystack)
+        self._hay, self._n = keep, n
+        self._start, self._end = 0, n
+        self._anchored, self._earliest = Anchored.No, False
+
+    new = staticmethod(lambda haystack: Input(haystack))
+
+    def clone(self):
+        c = Input.__new__(Input)
+        for k in Input.__slots__:
+            setattr(c, k, getattr(self, k))
+        return c
+
+    # builder-style setters (consume and return, :142-310)
+    def span(self, span):
+        self.set_span(span)
+        return self
+
+    def range(self, rng):
+        self.set_range(rng)
+        return self
+
+    def anchored(self, mode):
+        self.set_anchored(mode)
+        return self
+
+    def earliest(self, yes):
+        self.set_earliest(yes)
+        return self
+
+    # setters (:332-480)
+    def set_span(self, span):
+        start, end = int(span[0]), int(span[1])
+        # the reference panics on an invalid span (:335-341)
+        if not (0 <= start and end <= self._n and start <= end + 1):
+            raise ValueError(f"invalid span ({start}, {end}) for haystack of length {self._n}")
+        self._start, self._end = start, end
+
+    def set_range(self, rng):
+        if isinstance(rng, (range, slice)):
+            if rng.step not in (None, 1):
+                raise ValueError("ranges must have step 1")
+            start = 0 if rng.start is None else rng.start
+            end = self._n if rng.stop is None else rng.stop
+            rng = (start, end)
+        self.set_span(rng)
+
+    def set_start(self, start):
+        self.set_span((start, self._end))
+
+    def set_end(self, end):
+        self.set_span((self._start, end))
+
+    def set_anchored(self, mode):
+        self._anchored = Anchored(mode)
+
+    def set_earliest(self, yes):
+        self._earliest = bool(yes)
+
+    # getters (:493-630)
+    def haystack(self):
+        return self._hay
+
+    def start(self):
+        return self._start
+
+    def end(self):
+        return self._end
+
+    def get_span(self):
+        return (self._start, self._end)
+
+    def get_range(self):
+        return range(self._start, self._end)
+
+    def get_anchored(self):
+        return self._anchored
+
+    def get_earliest(self):
+        return self._earliest
+
+    def is_done(self):  # :627
+        return self._start > self._end
+
+
 class OverlappingState:
     """`OverlappingState`, src/automaton.rs:782-840: the cursor of a resumable overlapping search.
     The device scan is eager, so the state holds the ordered match list of the search it was first
@@ -421,6 +513,8 @@ class AhoCorasick:
         raise DeviceError(rc)
 
     def _collect(self, fn, hay, span, anchored):
+        if isinstance(hay, Input):
+            hay, span, anchored = hay.haystack(), hay.get_span(), hay.get_anchored()
         keep, ptr, n = _hay_ptr(hay)
         s, e = _span(span, n)
         cap = self._cap_hint
@@ -469,6 +563,8 @@ class AhoCorasick:
     find_overlapping_iter = try_find_overlapping_iter  # :609
 
     def try_find(self, hay, span=None, anchored=Anchored.No, earliest=False):  # :1021
+        if isinstance(hay, Input):
+            hay, span, anchored, earliest = hay.haystack(), hay.get_span(), hay.get_anchored(), hay.get_earliest()
         keep, ptr, n = _hay_ptr(hay)
         s, e = _span(span, n)
         out = np.zeros(1, MATCH_DTYPE)
@@ -487,6 +583,8 @@ class AhoCorasick:
         # under `earliest` iff one exists without it, so leftmost automata stay on the windowed
         # device scan instead of the single-lane engine.
         earliest = self.match_kind() == MatchKind.Standard
+        if isinstance(hay, Input):
+            return self.try_find(hay.clone().earliest(earliest)) is not None
         return self.try_find(hay, span, earliest=earliest) is not None
 
     # ---- replace / stream: host-side glue over find_iter, as in the reference -------------------

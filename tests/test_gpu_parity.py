@@ -410,6 +410,23 @@ def test_replace_all_and_stream():
     assert out.getvalue() == _apply(t.tobytes(), want, reps)
 
 
+def test_searches_accept_input_objects():
+    """`Input` (src/util/search.rs:60-720) carries span / anchored / earliest into every search;
+    the Teddy-prefilter range regression of src/tests.rs:1523-1530 written the reference's way."""
+    ac = build([b"abcd", b"bcd", b"cd", b"b"], 1, start_kind=ab.StartKind.Both)
+    hay = b"abcdabcd"
+    assert tuples(ac.find_iter(ab.Input(hay))) == tuples(ac.find_iter(hay))
+    assert tuples(ac.find_iter(ab.Input(hay).span((1, 8)))) == tuples(ac.find_iter(hay, span=(1, 8)))
+    assert ac.find(ab.Input(hay).range(range(1, 8))).as_tuple() == ac.find(hay, span=(1, 8)).as_tuple()
+    a = ac.find(ab.Input(hay).span((1, 8)).anchored(ab.Anchored.Yes))
+    assert a.as_tuple() == ac.find(hay, span=(1, 8), anchored=ab.Anchored.Yes).as_tuple() == (1, 1, 4)
+    assert ac.is_match(ab.Input(hay).span((5, 8)))
+    assert not ac.is_match(ab.Input(hay).span((0, 1)))
+    std = build([b"abcd", b"bcd", b"cd", b"b"], 0)
+    assert tuples(std.find_overlapping_iter(ab.Input(hay).span((0, 4)))) == tuples(std.find_overlapping_iter(hay, span=(0, 4)))
+    assert std.find(ab.Input(hay).earliest(True)).as_tuple() == std.find(hay, earliest=True).as_tuple()
+
+
 def test_find_overlapping_with_state():
     """`find_overlapping` + `OverlappingState`, doc example of src/ahocorasick.rs:430-470."""
     ac = build([b"append", b"appendage", b"app"], 0)
