@@ -1058,10 +1058,43 @@ int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_
   return build_common(patterns, lens, n, opts, false, out);
 }
 
+// Structural checks of an adopted table (the layout facts of src/dfa.rs:91-132 the kernels rely
+// on): a malformed descriptor is rejected instead of being indexed out of bounds on the device.
+static bool desc_is_consistent(const acg_dfa_desc* d) {
+  if (!d->trans || !d->match_offsets || !d->pattern_lens && d->n_patterns) return false;
+  if (d->stride2 > 8 || d->alphabet_len == 0 || d->alphabet_len > (1u << d->stride2)) return false;
+  const uint64_t stride = 1ull << d->stride2;
+  if (d->trans_len == 0 || (d->trans_len & (stride - 1)) || d->trans_len > (1ull << 32)) return false;
+  const uint64_t rows = d->trans_len >> d->stride2;
+  if (rows < 4) return false;  // DEAD, FAIL and the two start rows always exist
+  if (d->match_kind > ACG_LEFTMOST_LONGEST || d->start_kind > ACG_START_BOTH) return false;
+  for (int b = 0; b < 256; ++b)
+    if (d->byte_classes[b] >= d->alphabet_len) return false;
+  auto id_ok = [&](uint32_t id) { return (id & (stride - 1)) == 0 && id < d->trans_len; };
+  if (!id_ok(d->max_match_id) || !id_ok(d->start_unanchored_id) || !id_ok(d->start_anchored_id) ||
+      !id_ok(d->max_special_id))
+    return false;
+  const uint64_t max_match_row = d->max_match_id >> d->stride2;
+  if (max_match_row < 1 || max_match_row >= rows) return false;
+  for (uint64_t i = 0; i < d->trans_len; ++i)
+    if (!id_ok(d->trans[i])) return false;
+  const uint64_t nms = max_match_row - 1;  // match rows are 2 ..= max_match_row
+  if (d->match_offsets[0] != 0) return false;
+  for (uint64_t m = 0; m < nms; ++m)
+    if (d->match_offsets[m + 1] < d->match_offsets[m]) return false;
+  const uint64_t n_pids = d->match_offsets[nms];
+  if (n_pids && !d->match_pids) return false;
+  for (uint64_t i = 0; i < n_pids; ++i)
+    if (d->match_pids[i] >= d->n_patterns) return false;
+  for (uint32_t i = 0; i < d->n_patterns; ++i)
+    if (d->pattern_lens[i] < d->min_pattern_len || d->pattern_lens[i] > d->max_pattern_len) return false;
+  return true;
+}
+
 int acg_dfa_create(const acg_dfa_desc* d, acg_dfa** out) {
   if (!d || !out) return ACG_E_INVALID_ARG;
   *out = nullptr;
-  if (d->stride2 > 8 || (d->trans_len & ((1ull << d->stride2) - 1))) return ACG_E_INVALID_ARG;
+  if (!desc_is_consistent(d)) return ACG_E_INVALID_ARG;
   acg_dfa* a = new (std::nothrow) acg_dfa();
   if (!a) return ACG_E_NOMEM;
   HostDfa& h = a->h;
