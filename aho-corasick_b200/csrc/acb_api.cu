@@ -201,7 +201,7 @@ void derive_metadata(acg_dfa* a) {
     if (cur.size() > (64u << 20)) break;  // pathological fan-out: give up on longer fingerprints
   }
   // pick the fingerprint length with the sparsest bitmap (ties -> longer)
-  double best_fill = 2.0, best_fp = 0.0;
+  double best_fill = 2.0;
   std::vector<uint32_t> best_set;
   for (uint32_t k = 1; k <= kmax; ++k) {
     if (grams[k].empty()) continue;
@@ -232,7 +232,6 @@ void derive_metadata(acg_dfa* a) {
     }
     double fill = double(set_bits) / double(uint64_t(1) << log_bits);
     fill = fill * fill;  // both probes must hit
-    const double fp_only = fill;
     // expected candidate rate on text drawn from the patterns' own alphabet: Bloom false positives
     // plus genuine k-gram prefix hits (n_grams / prod_j |bytes seen at position j|)
     double space = 1.0;
@@ -249,7 +248,6 @@ void derive_metadata(acg_dfa* a) {
       pf.mult = mult; pf.shift = shift; pf.log_bits = log_bits;
       pf.fill = fill; pf.n_grams = set.size();
       pf.bitmap.swap(bm);
-      best_fp = fp_only;
       best_set = set;
       for (uint32_t& g : best_set) g &= kmask;
     }
@@ -342,7 +340,6 @@ void derive_metadata(acg_dfa* a) {
       }
     }
   }
-  (void)best_fp;
   pf.dense = !pf.brute && best_set.size() > 8192;
   // Anchor map: the verifier looks the first k bytes at a candidate offset up here and starts at
   // depth k.  Keys are raw (unfolded) byte strings: one entry per trie path of length k.
@@ -1213,6 +1210,7 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
   out->bitmap = pf.bitmap.data(); out->bitmap_words = pf.bitmap.size();
   out->amap = pf.amap.data(); out->amap_log = pf.amap_log;
   out->depth16 = a->depth16.data(); out->n_rows = a->depth16.size();
+  out->dup_shift = pf.dup_shift;
   return ACG_OK;
 }
 

@@ -29,6 +29,7 @@ typedef struct {
   uint32_t amap_log;
   const uint16_t* depth16; /* trie depth per table row */
   uint64_t n_rows;
+  uint32_t dup_shift;      /* tie-break layout: (max_len - len) << dup_shift | index among equal patterns */
 } acg_prefilter_plan;
 
 /* Fills *out with views of the handle's derived tables.  Works on host-only handles. */

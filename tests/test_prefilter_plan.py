@@ -29,7 +29,7 @@ class Plan(C.Structure):
                 ("mult", C.c_uint32), ("mult3", C.c_uint32), ("shift", C.c_uint32), ("log_bits", C.c_uint32),
                 ("bitmap", C.POINTER(C.c_uint32)), ("bitmap_words", C.c_uint64),
                 ("amap", C.POINTER(C.c_uint64)), ("amap_log", C.c_uint32),
-                ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64)]
+                ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64), ("dup_shift", C.c_uint32)]
 
 
 def plan_of(ac):
