@@ -8,20 +8,16 @@
 //                                 empty-pattern automata)
 //   K4  sort_pairs                ordering of the appended tuples (CUB radix sort)
 #include "acb_device.cuh"
+#ifndef ACB_PTX_HEADER
+#define ACB_PTX_HEADER "acb_ptx.cuh"
+#endif
+#include ACB_PTX_HEADER
 
 #include <cub/device/device_radix_sort.cuh>
 
 namespace acb {
 
 namespace {
-
-__device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
 
 // Append the whole pattern list of match state `sid` (entered after consuming
 // the byte at absolute offset end-1) to the tuple buffer.
@@ -82,7 +78,7 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   const uint8_t* __restrict__ hay = p.hay;
   while (pos < g1 && ((reinterpret_cast<uintptr_t>(hay + pos)) & 15)) ACB_STEP(hay[pos]);
   while (pos + 16 <= g1) {
-    const uint4 v = ld_nc_u4(hay + pos);
+    const uint4 v = ptx::ld_nc_u4(hay + pos);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     bool dead = false;
 #pragma unroll
@@ -211,23 +207,23 @@ __global__ void lower_bound_kernel(const uint64_t* keys, uint64_t n, uint64_t bo
 cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s) {
   const uint64_t m = e.n - e.first;
   if (m == 0) return cudaSuccess;
-  expand_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(e);
+  ACB_LAUNCH(expand_kernel, (unsigned)((m + 255) / 256), 256, 0, s, e);
   return cudaGetLastError();
 }
 cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_key,
                                unsigned long long* d_result, cudaStream_t s) {
-  lower_bound_kernel<<<1, 32, 0, s>>>(keys, n, bound_key, d_result);
+  ACB_LAUNCH(lower_bound_kernel, 1, 32, 0, s, keys, n, bound_key, d_result);
   return cudaGetLastError();
 }
 
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s) {
   const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;
-  walk_overlapping_kernel<<<(unsigned)blocks, kWalkThreads, 0, s>>>(dfa, p);
+  ACB_LAUNCH(walk_overlapping_kernel, (unsigned)blocks, kWalkThreads, 0, s, dfa, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_seq_find(const DfaDev& dfa, const SeqLaunch& p, cudaStream_t s) {
-  seq_find_kernel<<<1, 32, 0, s>>>(dfa, p);
+  ACB_LAUNCH(seq_find_kernel, 1, 32, 0, s, dfa, p);
   return cudaGetLastError();
 }
 

@@ -13,6 +13,10 @@
 // (depth(state) == bytes consumed) and reports the node's own patterns -- the set
 // of patterns that are a prefix of the haystack at that offset.
 #include "acb_device.cuh"
+#ifndef ACB_PTX_HEADER
+#define ACB_PTX_HEADER "acb_ptx.cuh"
+#endif
+#include ACB_PTX_HEADER
 
 #include <type_traits>
 
@@ -42,14 +46,6 @@ template <bool DENSE> struct PfCfg {
   static constexpr int kQ2 = DENSE ? 64 : 96;
 };
 
-__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-
 // Second Bloom hash: a full avalanche mix (evaluated only for first-probe hits, so its cost is
 // irrelevant); the first probe is a single multiply.  Must match bloom_hash2() in acb_api.cu.
 __device__ __forceinline__ uint32_t bloom_hash2(uint32_t x) {
@@ -72,59 +68,7 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
   return x;
 }
 
-// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared staging of the haystack ----
-constexpr int kPfStages = 2;            // ring depth per warp
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// cp.async.bulk (TMA, SASS UBLKCP): `bytes` (multiple of 16) from 16-byte aligned global memory
-// into shared memory, completion signalled on the mbarrier as transaction bytes.
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// shared-memory reads by 32-bit shared address (volatile: they must stay behind the mbarrier wait)
-__device__ __forceinline__ uint4 lds128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t a) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr int kPfStages = 2;            // ring depth per warp (TMA bulk copies + mbarriers, acb_ptx.cuh)
 
 struct Emitter {
   uint64_t* g_keys;
@@ -275,9 +219,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint32_t bitmap_words = p.brute ? 0u : (1u << (p.log_bits - 5));
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
-  if (tid < kPfWarps * kPfStages) mbar_init(&s_bars[tid], 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  fence_proxy_async();
+  if (tid < kPfWarps * kPfStages) ptx::mbar_init(ptx::smem_addr(&s_bars[tid]), 1);
+  ptx::mbar_init_fence();
+  ptx::fence_proxy_async();
   __syncthreads();
 
   Emitter em{p.keys, p.pids, p.counter, p.cap};
@@ -380,8 +324,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   // shared addresses of this warp's barriers and ring, and of the lane's first 16-byte group;
   // opaque to the compiler so that they stay in registers instead of being re-derived from the
   // thread index at every use
-  uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring), lane0 = ring0 + (uint32_t)lane * 16u;
-  asm volatile("" : "+r"(bar0), "+r"(ring0), "+r"(lane0));
+  uint32_t bar0 = ptx::smem_addr(bars), ring0 = ptx::smem_addr(ring), lane0 = ring0 + (uint32_t)lane * 16u;
+  ptx::keep_in_registers(bar0, ring0, lane0);
   // Refilling a stage needs no proxy fence: every lane has consumed its shared-memory reads of the
   // tile (their values fed the probes) before the __syncwarp that precedes the copy.
   const uint8_t* next_src = p.hay + wfirst;  // source of the next tile to request
@@ -390,9 +334,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     const uint32_t bar = bar0 + stage * 8, dst = ring0 + stage * kPfStageBytes;
     const uint8_t* src = next_src;
     next_src += wstride;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    ptx::mbar_arrive_expect_tx(bar, bytes);
+    ptx::tma_load_1d(dst, src, bytes, bar);
   };
   if (lane == 0) {
     if (n_steps > 0) issue(0, 0);
@@ -405,16 +348,16 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t it = 0; it < n_steps; ++it, wbase += wstride) {
     const uint32_t stage = it & 1;
     const uint32_t parity = (it >> 1) & 1;
-    while (!mbar_try_wait_a(bar0 + stage * 8, parity)) {}
+    while (!ptx::mbar_try_wait(bar0 + stage * 8, parity)) {}
     const uint32_t stage_off = stage * (uint32_t)kPfStageBytes;
     const uint32_t tile_a = ring0 + stage_off;
     uint32_t wv[kGroups][5];
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       const uint32_t ga = lane0 + stage_off + g * 512;
-      const uint4 v = lds128(ga);
+      const uint4 v = ptx::lds128(ga);
       wv[g][0] = v.x; wv[g][1] = v.y; wv[g][2] = v.z; wv[g][3] = v.w;
-      wv[g][4] = lds32(ga + 16);  // look-ahead word behind the group
+      wv[g][4] = ptx::lds32(ga + 16);  // look-ahead word behind the group
     }
     // hit mask of this lane, kBitsPerGroup bits per group.  Stride 1: bit 16g+o = offset o of
     // group g.  Stride 2: only even offsets are probed (3-byte fingerprints of the pattern bytes
@@ -526,7 +469,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
             } else {
               const uint32_t off = e - j;
               const uint32_t sa = tile_a + (off & ~3u);
-              uint32_t gram = __funnelshift_r(lds32(sa), lds32(sa + 4), (off & 3) * 8);
+              uint32_t gram = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8);
               if (MASKED) gram = (gram | fold) & kmask;
               gram_keep = gram;
               // stride 2: the first stage saw only three of the four bytes, so the cheap
@@ -642,18 +585,18 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const uint64_t cta_step = uint64_t(warps) * tile;
   const uint64_t warp_steps = ((p.region_hi - p.region_lo) + cta_step - 1) / cta_step;
   if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
-  kern<<<(unsigned)grid, threads, smem, s>>>(dfa, p);
+  ACB_LAUNCH(kern, (unsigned)grid, threads, smem, s, dfa, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_chain_ends(const ChainLaunch& c, cudaStream_t s) {
   const unsigned blocks = (unsigned)((c.n + 255) / 256);
-  chain_ends_kernel<<<blocks, 256, 0, s>>>(c);
+  ACB_LAUNCH(chain_ends_kernel, blocks, 256, 0, s, c);
   return cudaGetLastError();
 }
 cudaError_t launch_chain_select(const ChainLaunch& c, cudaStream_t s) {
   const unsigned blocks = (unsigned)((c.n + 255) / 256);
-  chain_select_kernel<<<blocks, 256, 0, s>>>(c);
+  ACB_LAUNCH(chain_select_kernel, blocks, 256, 0, s, c);
   return cudaGetLastError();
 }
 cudaError_t scan_max_u64(void* d_temp, size_t& temp_bytes, uint64_t* data, uint64_t n, cudaStream_t s) {
