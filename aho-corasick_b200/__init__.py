@@ -117,34 +117,41 @@ class _Stats(C.Structure):
 MATCH_DTYPE = np.dtype([("pid", "<u4"), ("_pad", "<u4"), ("start", "<u8"), ("end", "<u8")])
 
 _vp, _u64, _i = C.c_void_p, C.c_uint64, C.c_int
-_lib.acg_strerror.restype = C.c_char_p
-_lib.acg_strerror.argtypes = [_i]
-_lib.acg_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_BuildOpts), C.POINTER(_vp)]
-_lib.acg_build_host.argtypes = _lib.acg_build.argtypes
-_lib.acg_dfa_create.argtypes = [C.POINTER(_Desc), C.POINTER(_vp)]
-_lib.acg_dfa_free.argtypes = [_vp]
-_lib.acg_dfa_free.restype = None
-_lib.acg_dfa_table.argtypes = [_vp, C.POINTER(_Desc)]
-for _f in ("acg_dfa_state_len", "acg_patterns_len", "acg_min_pattern_len", "acg_max_pattern_len",
-           "acg_memory_usage"):
-    getattr(_lib, _f).argtypes = [_vp]
-    getattr(_lib, _f).restype = _u64
-for _f in ("acg_kind", "acg_match_kind", "acg_start_kind", "acg_prefilter_kind", "acg_last_engine"):
-    getattr(_lib, _f).argtypes = [_vp]
-_lib.acg_packed_variant.argtypes = [_vp, C.POINTER(_i), C.POINTER(_i)]
-_lib.acg_set_engine.argtypes = [_vp, _i]
-_lib.acg_last_stats.argtypes = [_vp, C.POINTER(_Stats)]
-_lib.acg_find_overlapping.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _vp, _u64, C.POINTER(_u64)]
-_lib.acg_find_iter.argtypes = _lib.acg_find_overlapping.argtypes
-_lib.acg_find.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _i, _vp, C.POINTER(_i)]
-_lib.acg_find_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_u64),
-                                          C.POINTER(C.c_float)]
-_lib.acg_find_iter_dev.argtypes = _lib.acg_find_overlapping_dev.argtypes
-_lib.acg_count_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64),
-                                           C.POINTER(C.c_float)]
-_lib.acg_find_overlapping_devout.argtypes = [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _u64,
-                                             C.POINTER(_u64), C.POINTER(C.c_float)]
-_lib.acg_device_count.argtypes = []
+
+
+def _declare(lib):
+    """ctypes signatures of the C ABI (include/acb200.h)."""
+    lib.acg_strerror.restype = C.c_char_p
+    lib.acg_strerror.argtypes = [_i]
+    lib.acg_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_BuildOpts), C.POINTER(_vp)]
+    lib.acg_build_host.argtypes = lib.acg_build.argtypes
+    lib.acg_dfa_create.argtypes = [C.POINTER(_Desc), C.POINTER(_vp)]
+    lib.acg_dfa_free.argtypes = [_vp]
+    lib.acg_dfa_free.restype = None
+    lib.acg_dfa_table.argtypes = [_vp, C.POINTER(_Desc)]
+    for _f in ("acg_dfa_state_len", "acg_patterns_len", "acg_min_pattern_len", "acg_max_pattern_len",
+               "acg_memory_usage"):
+        getattr(lib, _f).argtypes = [_vp]
+        getattr(lib, _f).restype = _u64
+    for _f in ("acg_kind", "acg_match_kind", "acg_start_kind", "acg_prefilter_kind", "acg_last_engine"):
+        getattr(lib, _f).argtypes = [_vp]
+    lib.acg_packed_variant.argtypes = [_vp, C.POINTER(_i), C.POINTER(_i)]
+    lib.acg_set_engine.argtypes = [_vp, _i]
+    lib.acg_last_stats.argtypes = [_vp, C.POINTER(_Stats)]
+    lib.acg_find_overlapping.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _vp, _u64, C.POINTER(_u64)]
+    lib.acg_find_iter.argtypes = lib.acg_find_overlapping.argtypes
+    lib.acg_find.argtypes = [_vp, _vp, _u64, _u64, _u64, _i, _i, _vp, C.POINTER(_i)]
+    lib.acg_find_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_u64),
+                                              C.POINTER(C.c_float)]
+    lib.acg_find_iter_dev.argtypes = lib.acg_find_overlapping_dev.argtypes
+    lib.acg_count_overlapping_dev.argtypes = [_vp, _vp, _u64, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64),
+                                               C.POINTER(C.c_float)]
+    lib.acg_find_overlapping_devout.argtypes = [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _u64,
+                                                 C.POINTER(_u64), C.POINTER(C.c_float)]
+    lib.acg_device_count.argtypes = []
+
+
+_declare(_lib)
 
 
 def device_count() -> int:

@@ -94,6 +94,7 @@ struct acg_dfa {
   uint16_t* d_depth16 = nullptr;
   DfaDev dev{};
   int engine_override = ACG_ENGINE_AUTO;
+  uint64_t pipeline_chunk = 64ull << 20;  // H2D chunk of the pipelined host path (acg_debug_set_pipeline_chunk)
   mutable std::mutex mu;
   mutable Workspace ws;
   mutable acg_stats stats{};
@@ -659,7 +660,7 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
     } else {
       // chunked H2D on the copy stream; a chunk's start offsets are scanned once the bytes a
       // verification can touch (max_pattern_len + fingerprint look-ahead) have landed
-      const uint64_t chunk = 64ull << 20;
+      const uint64_t chunk = a->pipeline_chunk;
       const uint64_t tail = std::min<uint64_t>(a->h.max_pattern_len, 1u << 30) + 64;
       uint64_t scanned = span_start;
       CK(cudaEventRecord(w.ev2, w.copy_stream));
@@ -1058,7 +1059,7 @@ int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_
 // Structural checks of an adopted table (the layout facts of src/dfa.rs:91-132 the kernels rely
 // on): a malformed descriptor is rejected instead of being indexed out of bounds on the device.
 static bool desc_is_consistent(const acg_dfa_desc* d) {
-  if (!d->trans || !d->match_offsets || !d->pattern_lens && d->n_patterns) return false;
+  if (!d->trans || !d->match_offsets || (!d->pattern_lens && d->n_patterns)) return false;
   if (d->stride2 > 8 || d->alphabet_len == 0 || d->alphabet_len > (1u << d->stride2)) return false;
   const uint64_t stride = 1ull << d->stride2;
   if (d->trans_len == 0 || (d->trans_len & (stride - 1)) || d->trans_len > (1ull << 32)) return false;
@@ -1211,6 +1212,12 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
   out->amap = pf.amap.data(); out->amap_log = pf.amap_log;
   out->depth16 = a->depth16.data(); out->n_rows = a->depth16.size();
   out->dup_shift = pf.dup_shift;
+  return ACG_OK;
+}
+
+int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
+  if (!a || bytes < 4096 || (bytes & 4095)) return ACG_E_INVALID_ARG;
+  a->pipeline_chunk = bytes;
   return ACG_OK;
 }
 

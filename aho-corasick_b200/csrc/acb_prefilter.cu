@@ -205,7 +205,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   constexpr uint32_t kBloomShift = PfBloom<WIDE>::kShift;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  ACB_DYNAMIC_SMEM(smem_raw);
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
   uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
   Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_bars + kPfWarps * kPfStages);  // [kPfWarps][kPfQ2]

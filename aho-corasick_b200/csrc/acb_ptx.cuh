@@ -10,6 +10,8 @@
 #include <stdint.h>
 
 #define ACB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// the kernel's dynamic shared memory as a byte array
+#define ACB_DYNAMIC_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
 
 namespace acb {
 namespace ptx {

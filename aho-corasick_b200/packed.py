@@ -26,17 +26,22 @@ class _Cfg(C.Structure):
                 ("only_teddy_256bit", C.c_int32), ("heuristic_pattern_limits", C.c_int32)]
 
 
-_lib.acg_packed_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_Cfg), C.POINTER(_vp)]
-_lib.acg_packed_build_host.argtypes = _lib.acg_packed_build.argtypes
-_lib.acg_packed_free.argtypes = [_vp]
-_lib.acg_packed_free.restype = None
-_lib.acg_packed_find_iter.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_u64)]
-_lib.acg_packed_find.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_i)]
-_lib.acg_packed_match_kind.argtypes = [_vp]
-for _f in ("acg_packed_minimum_len", "acg_packed_memory_usage", "acg_packed_patterns_len"):
-    getattr(_lib, _f).argtypes = [_vp]
-    getattr(_lib, _f).restype = _u64
-_lib.acg_packed_searcher_variant.argtypes = [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
+def _declare(lib):
+    """ctypes signatures of the acg_packed_* entry points (include/acb200.h)."""
+    lib.acg_packed_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_Cfg), C.POINTER(_vp)]
+    lib.acg_packed_build_host.argtypes = lib.acg_packed_build.argtypes
+    lib.acg_packed_free.argtypes = [_vp]
+    lib.acg_packed_free.restype = None
+    lib.acg_packed_find_iter.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, _u64, C.POINTER(_u64)]
+    lib.acg_packed_find.argtypes = [_vp, _vp, _u64, _u64, _u64, _vp, C.POINTER(_i)]
+    lib.acg_packed_match_kind.argtypes = [_vp]
+    for _f in ("acg_packed_minimum_len", "acg_packed_memory_usage", "acg_packed_patterns_len"):
+        getattr(lib, _f).argtypes = [_vp]
+        getattr(lib, _f).restype = _u64
+    lib.acg_packed_searcher_variant.argtypes = [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]
+
+
+_declare(_lib)
 
 
 def _opt(v):

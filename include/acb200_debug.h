@@ -35,6 +35,10 @@ typedef struct {
 /* Fills *out with views of the handle's derived tables.  Works on host-only handles. */
 int acg_debug_prefilter_plan(const acg_dfa* dfa, acg_prefilter_plan* out);
 
+/* Size of the H2D chunks of the pipelined host path (default 64 MiB; a multiple of 4096).  Lets
+ * tests exercise the multi-chunk logic on small inputs. */
+int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

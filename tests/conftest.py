@@ -32,6 +32,21 @@ def _has_cuda():
 def pytest_collection_modifyitems(config, items):
     if _has_cuda():
         return
+    if os.environ.get("ACB_EMULATE") == "1":
+        # dry run against the product's kernel sources compiled for the CPU (tests/emu/): "device"
+        # pointers are host pointers, one CTA at a time, CUDA threads as fibers.  Tests that need
+        # torch.cuda still fail -- select with -k
+        import ctypes
+        sys.path.insert(0, str(ROOT / "tests" / "emu"))
+        import build_emu
+        import aho_corasick_b200 as ab
+        from aho_corasick_b200 import packed
+        lib = ctypes.CDLL(str(build_emu.build()))
+        ab._declare(lib)
+        packed._declare(lib)
+        ab._lib = lib
+        packed._lib = lib
+        return
     if os.environ.get("ACB_FAKE_DEVICE") == "1":
         # dry run of the GPU test programs against the CPU oracle (tests/fake_device.py); tests that
         # need device-resident haystacks still fail -- select with -k

@@ -1,0 +1,170 @@
+"""The product's kernel sources executed on the CPU (tests/emu/: g++ build of csrc/*.cu against a
+dry-run CUDA runtime, CUDA threads as fibers) and compared with the oracle.
+
+This is a check of the kernels' *logic* -- chunk/tile partitioning, ownership of start offsets at
+every alignment, the stride-1 / stride-2 / wide / dense variants, queues and overflow paths,
+ordering keys, chain resolution, the device-resident and sharded entry points, the pipelined host
+path -- on machines without a GPU.  It models neither the hardware's concurrency nor its memory
+model; the `-m gpu` suite on a B200 remains the parity gate."""
+import ctypes
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "emu"))
+import aho_corasick_b200 as ab  # noqa: E402
+import oracle_py as O  # noqa: E402
+from aho_corasick_b200 import packed, sharded as S, workload as W  # noqa: E402
+from test_prefilter_plan import plan_of  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated_library():
+    import build_emu
+    lib = ctypes.CDLL(str(build_emu.build()))
+    ab._declare(lib)
+    packed._declare(lib)
+    lib.acg_debug_set_pipeline_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+    saved = ab._lib, packed._lib
+    ab._lib = packed._lib = lib
+    try:
+        yield lib
+    finally:
+        ab._lib, packed._lib = saved
+
+
+def eq(got, want, ctx=None):
+    assert len(got) == len(want), (len(got), len(want), ctx)
+    for k in ("pid", "start", "end"):
+        assert np.array_equal(got[k], want[k]), (k, ctx)
+
+
+def workload(n_pat, seed, nbytes, ci=False):
+    pats = W.make_patterns(n_pat, seed)
+    hay = np.empty(nbytes, dtype=np.uint8)
+    W.fill_haystack(hay, 5)
+    W.plant(hay, pats, 6, period=1024, window=512)
+    if ci:
+        W.flip_case(hay, 7)
+    return pats, hay
+
+
+def build(pats, kind=0, ci=False, engine=ab.Engine.Auto):
+    return (ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci)
+            .kind(ab.AhoCorasickKind.DFA).build(pats).set_engine(engine))
+
+
+# name -> (patterns, seed, bytes, match kind, case-insensitive, expected plan)
+VARIANTS = {
+    "stride2_narrow": (5000, 0xAC5000, 768 << 10, 0, False),
+    "stride2_narrow_ci_leftmost": (5000, 0xAC5000, 512 << 10, 1, True),
+    "stride2_wide": (50, 0xAC0050, 768 << 10, 1, False),
+    "stride1_short_patterns": (300, 31, 256 << 10, 2, False),
+    "dense": (20000, 0xAC1000, 384 << 10, 0, False),
+}
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_prefilter_variants_device_and_host_paths(name):
+    n, seed, nbytes, kind, ci = VARIANTS[name]
+    pats, hay = workload(n, seed, nbytes, ci)
+    if name == "stride1_short_patterns":
+        pats = [p[:3] for p in pats[:150]] + pats[150:]
+    ac = build(pats, kind, ci)
+    plan = plan_of(ac)   # the variant must really be the kernel instantiation its name says
+    assert plan.supported and not plan.brute
+    assert (plan.stride, bool(plan.wide), bool(plan.dense), plan.k) == {
+        "stride2_narrow": (2, False, False, 4), "stride2_narrow_ci_leftmost": (2, False, False, 4),
+        "stride2_wide": (2, True, False, 4), "stride1_short_patterns": (1, False, False, 3),
+        "dense": (1, False, True, 4)}[name]
+    assert bool(plan.fold) == ci
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    ptr = hay.ctypes.data  # "device" memory is host memory in the dry run
+    if kind == 0:
+        want = o.find_overlapping_iter_np(hay)
+        got, _ = ac.find_overlapping_iter_dev_np(ptr, hay.size)
+        eq(got, want, name)
+        assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+        eq(ac.try_find_overlapping_iter_np(hay), want, name + " host")
+        cnt, fnv, _ = ac.count_overlapping_dev(ptr, hay.size)
+        ocnt, ofnv = o.scan_overlapping_count(hay)
+        assert (cnt, fnv) == (ocnt, ofnv)
+        ac.set_engine(ab.Engine.Walk)
+        eq(ac.find_overlapping_iter_dev_np(ptr, hay.size)[0], want, name + " walk")
+        ac.set_engine(ab.Engine.Auto)
+    want = o.find_iter_np(hay)
+    assert len(want) > 100
+    eq(ac.find_iter_dev_np(ptr, hay.size)[0], want, name)
+    eq(ac.try_find_iter_np(hay), want, name + " host")
+    s, e = 4099, hay.size - 777
+    eq(ac.find_iter_dev_np(ptr, hay.size, span=(s, e))[0], o.find_iter_np(hay, span=(s, e)), name + " span")
+
+
+@pytest.mark.parametrize("name", ["stride2_narrow", "stride2_wide", "stride1_short_patterns"])
+def test_every_alignment_of_the_device_pointer(name):
+    """Head / aligned region / tail bookkeeping: the same bytes at 18 different pointer phases and
+    span ends, against the oracle."""
+    n, seed, _, kind, ci = VARIANTS[name]
+    pats, hay = workload(n, seed, 40 << 10, ci)
+    if name == "stride1_short_patterns":
+        pats = [p[:3] for p in pats[:150]] + pats[150:]
+    W.plant(hay, pats, 8, period=64, window=32)   # dense matches, also across every boundary
+    ac = build(pats, 0, ci)
+    o = O.Oracle(pats, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    backing = np.zeros(hay.size + 64, dtype=np.uint8)
+    for phase in range(18):
+        view = backing[phase:phase + hay.size]
+        view[:] = hay
+        for cut in (0, 1, 2, 3, 15, 16, 17, 33):
+            sub = view[:hay.size - cut]
+            eq(ac.find_overlapping_iter_dev_np(sub.ctypes.data, sub.size)[0], o.find_overlapping_iter_np(sub), (phase, cut))
+
+
+def test_sharded_slices_reproduce_the_whole():
+    """acg_find_overlapping_devout with ownership by end offset: the
+    concatenation of the ranks' outputs equals the single-device stream."""
+    pats, hay = workload(5000, 0xAC5000, 512 << 10)
+    ac = build(pats)
+    want = O.Oracle(pats, kind=O.KIND_DFA).find_overlapping_iter_np(hay)
+    back = int(ac.max_pattern_len()) - 1
+    for world in (2, 3, 5):
+        parts = []
+        for lo, hi, read_lo in S.slice_plan(0, hay.size, world, ac.max_pattern_len()):
+            piece = np.ascontiguousarray(hay[read_lo:hi])
+            out = np.zeros(len(want) + 16, ab.MATCH_DTYPE)
+            n, _ = ac.find_overlapping_devout(piece.ctypes.data, piece.size, (0, piece.size), lo - read_lo, read_lo,
+                                              out.ctypes.data, out.size)
+            parts.append(out[:n])
+            assert read_lo == max(0, lo - back)
+        eq(np.concatenate(parts), want, world)
+
+
+def test_pipelined_host_path_with_many_chunks():
+    """The chunked H2D + scan overlap of the host entry points, with the chunk shrunk so that a
+    1 MiB haystack takes many launches with their own scan ranges."""
+    pats, hay = workload(5000, 0xAC5000, 1 << 20)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    for chunk in (4096, 64 << 10, 200 << 12):
+        ac = build(pats)
+        assert ab._lib.acg_debug_set_pipeline_chunk(ac._h, chunk) == 0
+        eq(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay), chunk)
+        eq(ac.try_find_iter_np(hay, span=(123, hay.size - 5)), o.find_iter_np(hay, span=(123, hay.size - 5)), chunk)
+    lf = build(pats, 1)
+    ab._lib.acg_debug_set_pipeline_chunk(lf._h, 8192)
+    eq(lf.try_find_iter_np(hay), O.Oracle(pats, match_kind=1, kind=O.KIND_DFA).find_iter_np(hay), "leftmost-first")
+
+
+def test_tuple_buffer_overflow_rescan_and_brute_mode():
+    """More matches than the initial tuple capacity (counter overflow -> regrow -> rescan) and a
+    pattern set whose fingerprints cannot be selective (every offset is verified)."""
+    hay = np.frombuffer(b"ab" * (1 << 19), dtype=np.uint8)           # 1 Mi bytes, a match at every offset
+    pats = [b"a", b"b", b"ab", b"ba", b"aba"]
+    ac = build(pats)
+    want = O.Oracle(pats, kind=O.KIND_DFA).find_overlapping_iter_np(hay[: 600 << 10])
+    assert len(want) > (1 << 20)
+    eq(ac.try_find_overlapping_iter_np(hay[: 600 << 10]), want)
+    eq(build(pats, 2).try_find_iter_np(hay[: 64 << 10]), O.Oracle(pats, match_kind=2, kind=O.KIND_DFA).find_iter_np(hay[: 64 << 10]))
