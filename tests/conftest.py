@@ -41,7 +41,7 @@ def pytest_collection_modifyitems(config, items):
         import build_emu
         import aho_corasick_b200 as ab
         from aho_corasick_b200 import packed
-        lib = ctypes.CDLL(str(build_emu.build()))
+        lib = ctypes.CDLL(str(build_emu.build(asan=os.environ.get("ACB_EMU_ASAN") == "1")))
         ab._declare(lib)
         packed._declare(lib)
         ab._lib = lib

@@ -12,12 +12,12 @@ namespace acb {
 namespace ptx {
 
 inline unsigned char* smem_ptr(uint32_t a, size_t bytes) {
-  if ((size_t)a + bytes > emu::kDynSmemBytes) emu::die("shared-memory access out of range");
+  if ((size_t)a + bytes > emu::g_dyn_smem_bytes) emu::die("shared-memory access out of range");
   return emu::g_dyn_smem + a;
 }
 inline uint32_t smem_addr(const void* p) {
   const size_t off = (size_t)((const unsigned char*)p - emu::g_dyn_smem);
-  if (off >= emu::kDynSmemBytes) emu::die("smem_addr of a pointer outside dynamic shared memory");
+  if (off >= emu::g_dyn_smem_bytes) emu::die("smem_addr of a pointer outside dynamic shared memory");
   return (uint32_t)off;
 }
 // mbarrier word = number of completed phases; with one arrival + transaction bytes per phase the

@@ -131,7 +131,8 @@ struct Cta {
 inline Cta* g_cta = nullptr;
 inline Fiber* g_cur = nullptr;
 inline ucontext_t g_sched;
-alignas(128) inline unsigned char g_dyn_smem[kDynSmemBytes];
+inline unsigned char* g_dyn_smem = nullptr;  // exactly the requested bytes per launch: overruns are visible to ASAN
+inline size_t g_dyn_smem_bytes = 0;
 
 inline void yield() { swapcontext(&g_cur->ctx, &g_sched); }
 [[noreturn]] inline void die(const char* what) {
@@ -228,6 +229,10 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A
     cta.warps.resize((block.x + 31) / 32);
     cta.alive_threads = block.x;
     cta.body = [&]() { kernel(args...); };
+    void* sm = nullptr;
+    if (posix_memalign(&sm, 128, smem ? smem : 128)) die("out of memory");
+    g_dyn_smem = static_cast<unsigned char*>(sm);
+    g_dyn_smem_bytes = smem;
     std::memset(g_dyn_smem, 0xCD, smem);  // shared memory is not zero-initialised
     g_cta = &cta;
     for (unsigned t = 0; t < block.x; ++t) {
@@ -255,6 +260,9 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A
     }
     g_cta = nullptr;
     g_cur = nullptr;
+    std::free(g_dyn_smem);
+    g_dyn_smem = nullptr;
+    g_dyn_smem_bytes = 0;
   }
 }
 

@@ -25,7 +25,8 @@ from test_prefilter_plan import plan_of  # noqa: E402
 @pytest.fixture(scope="module", autouse=True)
 def emulated_library():
     import build_emu
-    lib = ctypes.CDLL(str(build_emu.build()))
+    import os
+    lib = ctypes.CDLL(str(build_emu.build(asan=os.environ.get("ACB_EMU_ASAN") == "1")))
     ab._declare(lib)
     packed._declare(lib)
     lib.acg_debug_set_pipeline_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
