@@ -246,11 +246,26 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A
       f.ctx.uc_link = nullptr;
       makecontext(&f.ctx, reinterpret_cast<void (*)()>(trampoline), 0);
     }
+    // Schedule: which runnable thread goes next is not defined by CUDA between synchronisation
+    // points, so the order is a knob -- ACB_EMU_SCHED=forward (default) | reverse | random:<seed>.
+    // Results that depend on it reveal a missing __syncwarp / __syncthreads.
+    static const char* sched_env = std::getenv("ACB_EMU_SCHED");
+    const bool reverse = sched_env && !std::strcmp(sched_env, "reverse");
+    const bool random = sched_env && !std::strncmp(sched_env, "random", 6);
+    static uint64_t rng = random && std::strlen(sched_env) > 7 ? std::strtoull(sched_env + 7, nullptr, 10) * 2 + 1 : 12345;
+    std::vector<unsigned> order(block.x);
+    for (unsigned t = 0; t < block.x; ++t) order[t] = reverse ? block.x - 1 - t : t;
     unsigned remaining = block.x;
     while (remaining) {
       const uint64_t before = cta.progress;
       remaining = 0;
-      for (Fiber& f : cta.fibers) {
+      if (random)
+        for (unsigned t = block.x; t > 1; --t) {
+          rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+          std::swap(order[t - 1], order[(rng >> 33) % t]);
+        }
+      for (unsigned t : order) {
+        Fiber& f = cta.fibers[t];
         if (f.done) continue;
         g_cur = &f;
         swapcontext(&g_sched, &f.ctx);
