@@ -6,7 +6,7 @@ instead of the CUDA kernels, on handles built with the real host-side builder.  
 test *programs* and the Python mirror (argument marshalling, Input handling, overflow protocol,
 replace/stream glue, packed wrapper) be exercised on a machine without a GPU:
 
-    ACB_FAKE_DEVICE=1 python -m pytest tests/test_gpu_packed.py tests/test_gpu_parity.py -k "..."
+    ACB_FAKE_DEVICE=1 python -m pytest tests/test_gpu_zz_packed.py tests/test_gpu_parity.py -k "..."
 
 Tests that use device-resident haystacks (torch.cuda, *_dev entry points) cannot run this way.
 A pass here says nothing about the kernels; the real `-m gpu` run on a B200 does.

@@ -410,40 +410,6 @@ def test_replace_all_and_stream():
     assert out.getvalue() == _apply(t.tobytes(), want, reps)
 
 
-def test_searches_accept_input_objects():
-    """`Input` (src/util/search.rs:60-720) carries span / anchored / earliest into every search;
-    the Teddy-prefilter range regression of src/tests.rs:1523-1530 written the reference's way."""
-    ac = build([b"abcd", b"bcd", b"cd", b"b"], 1, start_kind=ab.StartKind.Both)
-    hay = b"abcdabcd"
-    assert tuples(ac.find_iter(ab.Input(hay))) == tuples(ac.find_iter(hay))
-    assert tuples(ac.find_iter(ab.Input(hay).span((1, 8)))) == tuples(ac.find_iter(hay, span=(1, 8)))
-    assert ac.find(ab.Input(hay).range(range(1, 8))).as_tuple() == ac.find(hay, span=(1, 8)).as_tuple()
-    a = ac.find(ab.Input(hay).span((1, 8)).anchored(ab.Anchored.Yes))
-    assert a.as_tuple() == ac.find(hay, span=(1, 8), anchored=ab.Anchored.Yes).as_tuple() == (1, 1, 4)
-    assert ac.is_match(ab.Input(hay).span((5, 8)))
-    assert not ac.is_match(ab.Input(hay).span((0, 1)))
-    std = build([b"abcd", b"bcd", b"cd", b"b"], 0)
-    assert tuples(std.find_overlapping_iter(ab.Input(hay).span((0, 4)))) == tuples(std.find_overlapping_iter(hay, span=(0, 4)))
-    assert std.find(ab.Input(hay).earliest(True)).as_tuple() == std.find(hay, earliest=True).as_tuple()
-
-
-def test_find_overlapping_with_state():
-    """`find_overlapping` + `OverlappingState`, doc example of src/ahocorasick.rs:430-470."""
-    ac = build([b"append", b"appendage", b"app"], 0)
-    hay = b"append the app to the appendage"
-    state = ab.OverlappingState.start()
-    got = []
-    while True:
-        ac.find_overlapping(hay, state)
-        m = state.get_match()
-        if m is None:
-            break
-        got.append(m.as_tuple())
-    assert got == [(2, 0, 3), (0, 0, 6), (2, 11, 14), (2, 22, 25), (0, 22, 28), (1, 22, 31)]
-    with pytest.raises(ab.MatchError):
-        build([b"a"], 1).try_find_overlapping(b"a", ab.OverlappingState.start())
-
-
 def test_dense_outputs_and_unselective_fingerprints():
     """Stress the slow paths: (1) far more matches than the initial tuple capacity (counter
     overflow -> regrow -> rescan), (2) pattern sets whose fingerprints cannot be selective (every
@@ -479,3 +445,37 @@ def test_dense_outputs_and_unselective_fingerprints():
     hay = np.frombuffer(b"ab" * 200000, dtype=np.uint8)
     ac = build(pats, 0, kind=ab.AhoCorasickKind.DFA)
     assert_np_equal(ac.try_find_overlapping_iter_np(hay), O.Oracle(pats, kind=O.KIND_DFA).find_overlapping_iter_np(hay))
+
+
+def test_searches_accept_input_objects():
+    """`Input` (src/util/search.rs:60-720) carries span / anchored / earliest into every search;
+    the Teddy-prefilter range regression of src/tests.rs:1523-1530 written the reference's way."""
+    ac = build([b"abcd", b"bcd", b"cd", b"b"], 1, start_kind=ab.StartKind.Both)
+    hay = b"abcdabcd"
+    assert tuples(ac.find_iter(ab.Input(hay))) == tuples(ac.find_iter(hay))
+    assert tuples(ac.find_iter(ab.Input(hay).span((1, 8)))) == tuples(ac.find_iter(hay, span=(1, 8)))
+    assert ac.find(ab.Input(hay).range(range(1, 8))).as_tuple() == ac.find(hay, span=(1, 8)).as_tuple()
+    a = ac.find(ab.Input(hay).span((1, 8)).anchored(ab.Anchored.Yes))
+    assert a.as_tuple() == ac.find(hay, span=(1, 8), anchored=ab.Anchored.Yes).as_tuple() == (1, 1, 4)
+    assert ac.is_match(ab.Input(hay).span((5, 8)))
+    assert not ac.is_match(ab.Input(hay).span((0, 1)))
+    std = build([b"abcd", b"bcd", b"cd", b"b"], 0)
+    assert tuples(std.find_overlapping_iter(ab.Input(hay).span((0, 4)))) == tuples(std.find_overlapping_iter(hay, span=(0, 4)))
+    assert std.find(ab.Input(hay).earliest(True)).as_tuple() == std.find(hay, earliest=True).as_tuple()
+
+
+def test_find_overlapping_with_state():
+    """`find_overlapping` + `OverlappingState`, doc example of src/ahocorasick.rs:430-470."""
+    ac = build([b"append", b"appendage", b"app"], 0)
+    hay = b"append the app to the appendage"
+    state = ab.OverlappingState.start()
+    got = []
+    while True:
+        ac.find_overlapping(hay, state)
+        m = state.get_match()
+        if m is None:
+            break
+        got.append(m.as_tuple())
+    assert got == [(2, 0, 3), (0, 0, 6), (2, 11, 14), (2, 22, 25), (0, 22, 28), (1, 22, 31)]
+    with pytest.raises(ab.MatchError):
+        build([b"a"], 1).try_find_overlapping(b"a", ab.OverlappingState.start())
