@@ -94,12 +94,21 @@ struct Emitter {
 // bytes are not the beginning of any pattern.  Must match the table built in acb_api.cu.
 __device__ __forceinline__ uint32_t anchor_lookup(const DfaDev& d, const PrefilterLaunch& p, uint64_t s) {
   if (s + d.amap_k > p.span_end) return 0;  // no pattern fits any more
+  // the k bytes at s: two aligned word loads when both words lie inside the haystack buffer,
+  // byte loads within a word of its edges (nothing outside [hay, hay + hay_len) is ever read)
   const uintptr_t a = reinterpret_cast<uintptr_t>(p.hay + s);
-  const uintptr_t end = reinterpret_cast<uintptr_t>(p.hay + p.hay_len);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-  const uint32_t lo = __ldg(w);
-  const uint32_t hi = ((a & 3) && reinterpret_cast<uintptr_t>(w + 1) < end) ? __ldg(w + 1) : 0u;
-  const uint32_t key = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8) & d.amap_kmask;
+  const uintptr_t lo_edge = reinterpret_cast<uintptr_t>(p.hay), hi_edge = lo_edge + p.hay_len;
+  const uintptr_t wa = a & ~uintptr_t(3);
+  uint32_t key;
+  if (wa >= lo_edge && wa + ((a & 3) ? 8 : 4) <= hi_edge) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(wa);
+    const uint32_t lo = __ldg(w);
+    const uint32_t hi = (a & 3) ? __ldg(w + 1) : 0u;
+    key = __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8) & d.amap_kmask;
+  } else {
+    key = 0;
+    for (uint32_t i = 0; i < d.amap_k; ++i) key |= (uint32_t)__ldg(p.hay + s + i) << (8 * i);
+  }
   uint32_t slot = bloom_hash3(key) >> d.amap_shift;
   for (;;) {
     const uint2 e = __ldg(d.amap + slot);

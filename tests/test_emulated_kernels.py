@@ -169,3 +169,35 @@ def test_tuple_buffer_overflow_rescan_and_brute_mode():
     assert len(want) > (1 << 20)
     eq(ac.try_find_overlapping_iter_np(hay[: 600 << 10]), want)
     eq(build(pats, 2).try_find_iter_np(hay[: 64 << 10]), O.Oracle(pats, match_kind=2, kind=O.KIND_DFA).find_iter_np(hay[: 64 << 10]))
+
+
+@pytest.mark.parametrize("name", ["stride2_narrow", "stride2_wide", "stride1_short_patterns", "dense"])
+def test_exact_size_device_buffers(name):
+    """Haystacks that fill their allocation exactly, with a pattern ending on the last byte: every
+    read the kernels make must stay inside [0, hay_len) (under ACB_EMU_ASAN=1 an over-read aborts
+    the run; without the sanitizer this still checks the tiny and ragged sizes)."""
+    n, seed, _, kind, ci = VARIANTS[name]
+    pats = W.make_patterns(n, seed)
+    if name == "stride1_short_patterns":
+        pats = [p[:3] for p in pats[:150]] + pats[150:]
+    ac = build(pats, 0, ci)
+    o = O.Oracle(pats, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    rng = np.random.default_rng(17)
+    for size in list(range(0, 70)) + [127, 128, 129, 1023, 1024, 1025, 2047, 2048, 2049, 4095, 4096, 4097, 33000]:
+        hay = np.empty(size, dtype=np.uint8)          # its own allocation of exactly `size` bytes
+        hay[:] = rng.integers(0x20, 0x7F, size=size, dtype=np.uint8)
+        for p in (pats[size % len(pats)], pats[(size * 7 + 1) % len(pats)]):
+            if len(p) <= size:
+                hay[size - len(p):] = np.frombuffer(p, dtype=np.uint8)   # ends on the last byte
+                break
+        want = o.find_overlapping_iter_np(hay)
+        got, _ = ac.find_overlapping_iter_dev_np(hay.ctypes.data if size else 0, size)
+        eq(got, want, (name, size))
+        eq(ac.try_find_overlapping_iter_np(hay), want, (name, size, "host"))
+        if size in (0, 1, 5, 17, 64, 129, 1025, 4097):
+            ac.set_engine(ab.Engine.Walk)
+            eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data if size else 0, size)[0], want, (name, size, "walk"))
+            ac.set_engine(ab.Engine.Sequential)
+            eq(ac.find_iter_dev_np(hay.ctypes.data if size else 0, size)[0], o.find_iter_np(hay), (name, size, "seq"))
+            ac.set_engine(ab.Engine.Auto)
+            eq(ac.find_iter_dev_np(hay.ctypes.data if size else 0, size)[0], o.find_iter_np(hay), (name, size, "iter"))
