@@ -201,3 +201,51 @@ def test_exact_size_device_buffers(name):
             eq(ac.find_iter_dev_np(hay.ctypes.data if size else 0, size)[0], o.find_iter_np(hay), (name, size, "seq"))
             ac.set_engine(ab.Engine.Auto)
             eq(ac.find_iter_dev_np(hay.ctypes.data if size else 0, size)[0], o.find_iter_np(hay), (name, size, "iter"))
+
+
+def test_random_sets_on_exact_size_buffers():
+    """Randomized differential on haystacks that fill their allocation exactly: small alphabets,
+    duplicates, 1-byte patterns, all match kinds, every entry point family."""
+    import random
+    rng = random.Random(4242)
+    for it in range(90):
+        alphabet = [b"ab", b"abcd", b"aAbBcC ", bytes(range(256)), b"abcdefghijklmnopqrstuvwxyz"][it % 5]
+        npat = rng.choice([1, 2, 5, 20, 200])
+        pats = [bytes(rng.choice(alphabet) for _ in range(rng.randint(1, rng.choice([3, 8, 20])))) for _ in range(npat)]
+        if it % 4 == 0:
+            pats += [pats[0], pats[-1][:2]]
+        size = rng.choice([0, 1, 2, 3, 4, 5, 7, 15, 16, 17, 31, 33, 100, 1000, 5000, 40000])
+        hay = np.empty(size, dtype=np.uint8)
+        hay[:] = np.frombuffer(bytes(rng.choice(alphabet) for _ in range(size)), dtype=np.uint8)
+        ptr = hay.ctypes.data if size else 0
+        kind = it % 3
+        ci = it % 7 == 0
+        ac = build(pats, kind, ci)
+        o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+        lo = rng.randrange(0, size + 1)
+        hi = rng.randrange(lo, size + 1)
+        for span in ((0, size), (lo, hi)):
+            if kind == 0:
+                eq(ac.find_overlapping_iter_dev_np(ptr, size, span=span)[0], o.find_overlapping_iter_np(hay, span=span), (it, span))
+            eq(ac.find_iter_dev_np(ptr, size, span=span)[0], o.find_iter_np(hay, span=span), (it, span))
+            eq(ac.try_find_iter_np(hay, span=span), o.find_iter_np(hay, span=span), (it, span, "host"))
+            m = ac.try_find(hay, span=span)
+            assert (m.as_tuple() if m else None) == o.try_find(hay, span=span), (it, span)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_unselective_steps_verify_in_place(kind):
+    """A selective fingerprint set (so the Bloom path is taken) on a haystack made of pattern
+    beginnings: every probe hits, the per-step hit count exceeds the slot queue and the step falls
+    back to verifying its hits in place (the `total > kPfSlots` path), for stride 2 and stride 1."""
+    for extra, stride in ((W.make_patterns(300, 5), 2), ([p[:3] for p in W.make_patterns(150, 5)], 1)):
+        pats = [b"abab", b"baba", b"ababab", b"bab"][: 3 if stride == 2 else 4] + extra
+        ac = build(pats, kind)
+        plan = plan_of(ac)
+        assert plan.supported and not plan.brute and plan.stride == stride
+        hay = np.frombuffer(b"ab" * 20000 + b"xyz" + b"ba" * 3000, dtype=np.uint8).copy()
+        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA)
+        if kind == 0:
+            eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), stride)
+            assert ac.last_stats()["candidates"] > hay.size // 2   # (nearly) every offset was verified
+        eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
