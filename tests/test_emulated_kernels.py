@@ -249,3 +249,49 @@ def test_unselective_steps_verify_in_place(kind):
             eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), stride)
             assert ac.last_stats()["candidates"] > hay.size // 2   # (nearly) every offset was verified
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
+
+
+# ---- the reference's regression tests around its memchr-class prefilters, src/tests.rs:1537-1660:
+# results only (the device engine has no such prefilters), through the product on the dry-run library
+def test_reference_regressions():
+    pat = "Tsubaki House-Triple Shot Vol01校花三姐妹".encode()
+    assert ab.AhoCorasick.builder().ascii_case_insensitive(True).build([pat]).find(b"") is None
+    assert ab.AhoCorasick.new([b"ab/j/", b"x/"]).is_match(b"ab/j/")      # issue 53
+    for c in range(ord("a"), ord("z"), 3):
+        for c2 in range(ord("a"), ord("z"), 2):
+            needle = bytes([c, c2])
+            ac = ab.AhoCorasick.builder().ascii_case_insensitive(True).prefilter(True).build([needle])
+            assert len(ac.find_iter(needle.upper())) == 1, needle
+
+
+def test_reference_regression_stream_across_reads():
+    """src/tests.rs:1588-1660 (issue 64): a match that straddles two reads of a stream."""
+    magic, begin = b"1234j", 65535
+
+    class Reader:
+        def __init__(self):
+            self.pos = 0
+
+        def read(self, n):
+            if self.pos > 100000:
+                return b""
+            out = bytearray(n)
+            lo, hi = max(begin, self.pos), min(begin + len(magic), self.pos + n)
+            if lo < hi:
+                out[lo - self.pos:hi - self.pos] = magic[lo - begin:hi - begin]
+            self.pos += n
+            return bytes(out)
+
+    ac = ab.AhoCorasick.builder().byte_classes(False).build([magic])
+    whole = bytearray()
+    r = Reader()
+    while True:
+        b = r.read(8192)
+        if not b:
+            break
+        whole += b
+    from_whole = ac.find_iter(bytes(whole))[0].start()
+    assert from_whole == begin
+    for chunk in (8192, 65536, 65535 + 2, 4096 + 1):
+        first = next(iter(ac.stream_find_iter(Reader(), chunk_bytes=chunk)))
+        assert first.start() == from_whole, chunk

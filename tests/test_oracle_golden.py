@@ -171,3 +171,23 @@ def test_oracle_vs_bruteforce_on_golden():
             assert bruteforce.find_iter(t["patterns"], t["haystack"], kind) == t["matches"], t["name"]
     for t in G.collection(AC, "AC_STANDARD_OVERLAPPING"):
         assert bruteforce.find_overlapping(t["patterns"], t["haystack"]) == t["matches"], t["name"]
+
+
+# ---- src/tests.rs:1537-1660: regressions around the memchr-class prefilters (results only) ------
+def test_regression_ascii_case_insensitive_no_exponential():
+    pat = "Tsubaki House-Triple Shot Vol01校花三姐妹".encode()
+    assert O.Oracle([pat], ascii_case_insensitive=True).try_find(b"") is None
+
+
+def test_regression_rare_byte_prefilter():
+    # https://github.com/BurntSushi/aho-corasick/issues/53
+    o = O.Oracle([b"ab/j/", b"x/"])
+    assert o.try_find(b"ab/j/", earliest=True) is not None
+
+
+def test_regression_case_insensitive_prefilter():
+    for c in range(ord("a"), ord("z")):
+        for c2 in range(ord("a"), ord("z")):
+            needle = bytes([c, c2])
+            o = O.Oracle([needle], ascii_case_insensitive=True, prefilter=True)
+            assert len(o.find_iter(needle.upper())) == 1, needle
