@@ -131,3 +131,28 @@ def test_build_errors():
     assert ab.BuildError(-1).code == -1
     t = ab.AhoCorasick.builder().host_only().build([]).tables()
     assert t["state_len"] == 4 and int(t["max_match_id"]) >> t["stride2"] == 1
+
+
+def test_byte_class_corner_cases_from_the_reference_unit_tests():
+    # src/util/alphabet.rs:337-408 (full_byte_classes, elements_singletons, elements_empty), reached
+    # the way the automaton builders reach ByteClassSet: one set_range(b, b) per pattern byte
+    # (src/nfa/noncontiguous.rs:1119-1123).  Product and oracle must agree with those expectations.
+    def classes(pats, **kw):
+        b = ab.AhoCorasick.builder().host_only().kind(ab.AhoCorasickKind.DFA)
+        for k, v in kw.items():
+            getattr(b, k)(v)
+        t = b.build(pats).tables()
+        o = O.Oracle(pats, kind=O.KIND_DFA, **kw).dfa()
+        assert np.array_equal(t["byte_classes"], o["byte_classes"]) and t["alphabet_len"] == o["alphabet_len"]
+        return t
+    t = classes([])                                   # ByteClasses::empty(): one class for everything
+    assert t["alphabet_len"] == 1 and not t["byte_classes"].any()
+    t = classes([bytes(range(256))])                  # every byte its own class
+    assert t["alphabet_len"] == 256 and np.array_equal(t["byte_classes"], np.arange(256, dtype=np.uint8))
+    t = classes([b"a"], byte_classes=False)           # ByteClasses::singletons()
+    assert t["alphabet_len"] == 256 and np.array_equal(t["byte_classes"], np.arange(256, dtype=np.uint8))
+    t = classes([b"bd", b"z"])                        # classes: \\x00-a | b | c | d | e-y | z | {-\\xff
+    bc = t["byte_classes"]
+    assert t["alphabet_len"] == 7
+    assert (bc[0], bc[ord("a")], bc[ord("b")], bc[ord("c")], bc[ord("d")], bc[ord("e")], bc[ord("y")],
+            bc[ord("z")], bc[ord("{")], bc[255]) == (0, 0, 1, 2, 3, 4, 4, 5, 6, 6)
