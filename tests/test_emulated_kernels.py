@@ -295,3 +295,18 @@ def test_reference_regression_stream_across_reads():
     for chunk in (8192, 65536, 65535 + 2, 4096 + 1):
         first = next(iter(ac.stream_find_iter(Reader(), chunk_bytes=chunk)))
         assert first.start() == from_whole, chunk
+
+
+def test_verify_equality_vectors_of_packed_pattern_rs():
+    """src/packed/pattern.rs:422-480 (is_equal / is_prefix, the memcmp behind Teddy's verify): the
+    same vectors against the device verifier -- a candidate whose last byte differs must not match."""
+    base = b"abcdefghijklmn"
+    for n in range(1, len(base) + 1):
+        x, y = base[:n], base[:n - 1] + b"x"
+        for searcher in (ab.AhoCorasick.builder().match_kind(ab.MatchKind.LeftmostFirst).build([x]),
+                         packed.Searcher.new([x])):
+            assert searcher.find(y) is None and searcher.find(x).as_tuple() == (0, 0, n), n
+            assert searcher.find(b"zz" + x + y).as_tuple() == (0, 2, 2 + n)
+            assert [m.as_tuple() for m in searcher.find_iter(y + x + y + x)] == [(0, n, 2 * n), (0, 3 * n, 4 * n)]
+    foo = packed.Searcher.new([b"foo"])
+    assert foo.find(b"foobar").as_tuple() == (0, 0, 3) and foo.find(b"fobfo") is None
