@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 // ---- language keywords ------------------------------------------------------------------------
@@ -131,6 +132,7 @@ struct Cta {
 inline Cta* g_cta = nullptr;
 inline Fiber* g_cur = nullptr;
 inline ucontext_t g_sched;
+inline std::mutex g_one_launch_at_a_time;
 inline unsigned char* g_dyn_smem = nullptr;  // exactly the requested bytes per launch: overruns are visible to ASAN
 inline size_t g_dyn_smem_bytes = 0;
 
@@ -216,6 +218,7 @@ inline std::vector<void*>& stack_pool() {
 
 template <class K, class... A>
 inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A... args) {
+  std::lock_guard<std::mutex> lock(g_one_launch_at_a_time);  // the fiber scheduler's state is global
   if (smem > kDynSmemBytes) die("dynamic shared memory request too large");
   if (block.x % 32 && block.x > 32) die("block size must be a multiple of the warp size");
   auto& pool = stack_pool();

@@ -68,3 +68,28 @@ def test_packed_random_differential(okind, kind):
         ref = o.find_iter(hay[sub[0]:sub[1]])
         want = (ref[0][0], ref[0][1] + sub[0], ref[0][2] + sub[0]) if ref else None
         assert (got.as_tuple() if got is not None else None) == want, (it, sub)
+
+
+def test_concurrent_searches_on_one_handle():
+    """The reference's automata are Send + Sync and searched through &self from many threads
+    (src/lib.rs:274-326); an acg_dfa handle serialises concurrent searches internally.  Several
+    threads share one AhoCorasick and one packed Searcher (ctypes releases the GIL during a call)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import aho_corasick_b200 as ab
+    rng = random.Random(5)
+    pats = [bytes(rng.choice(b"abcd") for _ in range(rng.randint(2, 6))) for _ in range(40)]
+    hays = [bytes(rng.choice(b"abcd") for _ in range(rng.choice([10, 500, 20000]))) for _ in range(24)]
+    ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats)
+    lf = packed.Config().builder().extend(pats).build()
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    olf = O.Oracle(pats, match_kind=1, kind=O.KIND_DFA)
+    want = [(o.find_overlapping_iter(h), o.find_iter(h), olf.find_iter(h)) for h in hays]
+
+    def work(i):
+        h = hays[i % len(hays)]
+        return (i % len(hays), tuples(ac.find_overlapping_iter(h)), tuples(ac.find_iter(h)), tuples(lf.find_iter(h)))
+
+    with ThreadPoolExecutor(4) as ex:
+        for i, a, b, c in ex.map(work, range(96)):
+            assert (a, b, c) == want[i], i
