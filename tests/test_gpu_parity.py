@@ -12,6 +12,14 @@ from aho_corasick_b200 import workload as W
 
 pytestmark = pytest.mark.gpu
 
+
+def to_device(t):
+    """The tensor on the GPU -- or unchanged under the CPU dry run of tests/emu (ACB_EMULATE=1),
+    where "device" pointers are host pointers."""
+    import torch
+    return t.cuda() if torch.cuda.is_available() else t
+
+
 AC = G.load("ac_vectors.json")
 PK = G.load("packed_vectors.json")
 
@@ -223,7 +231,7 @@ def test_config3_4_reduced_find_iter_parity(cfg, kind, ci):
     assert len(want) > 7000
     assert_np_equal(ac.try_find_iter_np(hay), want)
     assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
-    d = t.cuda()
+    d = to_device(t)
     got, ms = ac.find_iter_dev_np(d.data_ptr(), hay.size)
     assert_np_equal(got, want)
     if cfg == "cfg4":
@@ -239,7 +247,7 @@ def test_config2_reduced_full_tuple_parity(engine):
     o = O.Oracle(pats, kind=O.KIND_DFA)
     want = o.find_overlapping_iter_np(hay)
     assert len(want) >= planted
-    d = torch.from_numpy(hay).cuda()
+    d = to_device(torch.from_numpy(hay))
     got, ms = ac.find_overlapping_iter_dev_np(d.data_ptr(), hay.size)
     assert_np_equal(got, want)
     # host-buffer entry point (H2D inside the call) gives the same stream
@@ -262,7 +270,7 @@ def test_pipelined_host_path_multi_chunk():
     t = torch.empty(200 << 20, dtype=torch.uint8)
     W.torch_fill_config("cfg2", t, pats, chunk=1 << 24)
     hay = t.numpy()
-    d = t.cuda()
+    d = to_device(t)
     for kind, overlapping in ((0, True), (0, False), (1, False)):
         ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA)
         if overlapping:
