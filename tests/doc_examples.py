@@ -117,7 +117,22 @@ def getters(ab):
     assert ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).ascii_case_insensitive(True).build(pats).memory_usage() == 11136
 
 
-ALL = [lib_and_readme, new_builder_is_match, find_under_each_match_kind, overlapping_state,
+def packed_examples(ab):
+    # src/packed/mod.rs:30-45 and src/packed/api.rs:60-80, 205-225, 375-605
+    from aho_corasick_b200 import packed
+    s = packed.Searcher.new(["foobar", "foo"])
+    assert pids(s.find_iter("foobar")) == [0]
+    ll = packed.Config.new().match_kind(packed.MatchKind.LeftmostLongest).builder().add("foo").add("foobar").build()
+    assert pids(ll.find_iter("foobar")) == [1]
+    assert pids(packed.Builder.new().add("foobar").add("foo").build().find_iter("foobar")) == [0]
+    assert s.find("foobar").as_tuple() == (0, 0, 6)
+    hay = "foofoobar"
+    assert s.find_in(hay, (3, len(hay))).as_tuple() == (0, 3, 9)
+    assert pids(s.find_iter("foobar fooba foofoo")) == [0, 1, 1, 1]
+    assert s.match_kind() == packed.MatchKind.LeftmostFirst and s.minimum_len() > 0 and s.memory_usage() > 0
+
+
+ALL = [packed_examples, lib_and_readme, new_builder_is_match, find_under_each_match_kind, overlapping_state,
        find_iter_under_each_match_kind, replace_family, stream_family, try_find_configurations, getters]
 
 
