@@ -1286,6 +1286,10 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
   if ((rc = check_start(a->h, anchored))) return rc;
   if (!a->on_device) return ACG_E_NO_DEVICE;
   if (span_start > span_end) return ACG_OK;
+  // Where the reference attaches its packed (Teddy) prefilter -- leftmost kinds only -- an
+  // unanchored try_find returns what the prefilter reports, a confirmed leftmost match
+  // (Candidate::Match, src/automaton.rs:1304-1309), whether or not `earliest` was asked for.
+  if (earliest && !anchored && a->h.match_kind != ACG_STANDARD && a->h.prefilter_kind == ACG_PRE_PACKED) earliest = 0;
   std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
   a->stats = acg_stats{};

@@ -337,7 +337,9 @@ def test_find_single_vs_oracle(kind):
         pats, hay, span, ci = rand_case(rng, it, allow_empty=(it % 5 == 0))
         kw = {"ascii_case_insensitive": ci}
         ac = build(pats, kind, kind=ab.AhoCorasickKind.DFA, **kw)
-        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA, prefilter=False, **kw)
+        # same (default) prefilter knob as the product: with the packed prefilter attached, the
+        # reference's unanchored try_find returns the leftmost match even under `earliest`
+        o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA, **kw)
         for earliest in (False, True):
             got = ac.try_find(hay, span, earliest=earliest)
             want = o.try_find(hay, span, earliest=earliest)
