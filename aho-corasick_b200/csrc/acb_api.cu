@@ -591,7 +591,8 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.shift = pf.shift;
   p.dense = pf.dense ? 1 : 0;
   p.brute = pf.brute ? 1 : 0;
-  p.mode = mode;
+  p.mode = mode == 1 ? 1 : 0;
+  p.first_only = mode == 2 ? 1 : 0;  // mode 2: all occurrences for a non-overlapping consumer
   p.dup_shift = pf.dup_shift;
   p.scan_lo = scan_lo;
   p.scan_hi = scan_hi;
@@ -994,7 +995,7 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   // leftmost kinds: best match per start offset ordered by start, then the same greedy choice.
   const int mode = a->h.match_kind == ACG_STANDARD ? 0 : 1;
   TupleResult r;
-  if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode, &r, pipelined ? hay : nullptr)))
+  if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode == 0 ? 2 : 1, &r, pipelined ? hay : nullptr)))
     return rc;
   if ((rc = run_chain(a, mode, &r))) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
@@ -1349,7 +1350,7 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
     if ((rc = ensure_copied(hi + look))) return rc;
     TupleResult r;
     if ((rc = run_prefilter(a, d_base, copied_hi == span_end ? span_end + 32 : copied_hi, span_start,
-                            span_end, mode, &r, nullptr, lo, hi)))
+                            span_end, mode == 0 ? 2 : 1, &r, nullptr, lo, hi)))
       return rc;
     if (r.n) {
       uint64_t key;
@@ -1362,7 +1363,7 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
         if ((rc = ensure_copied(hi2 + look))) return rc;
         TupleResult r2;
         if ((rc = run_prefilter(a, d_base, copied_hi == span_end ? span_end + 32 : copied_hi, span_start,
-                                span_end, mode, &r2, nullptr, hi, hi2)))
+                                span_end, mode == 0 ? 2 : 1, &r2, nullptr, hi, hi2)))
           return rc;
         if (r2.n) {
           uint64_t key2;

@@ -98,6 +98,8 @@ struct PrefilterLaunch {
                                 // (anchor-map lookup) before the warp-wide verification
   int brute;                    // 1: skip the bitmap, every position is a candidate
   int mode;                     // 0: all occurrences (overlapping); 1: best match per start (leftmost)
+  int first_only;               // mode 0 for a non-overlapping consumer (find_iter / find): of several equal
+                                // patterns ending at a node only the first can ever be yielded -- skip the rest
   uint32_t dup_shift;           // log2 of the per-node duplicate capacity in the tie-break
   uint64_t scan_lo, scan_hi;      // start offsets this launch is responsible for (within the span)
   uint64_t region_lo, region_hi;  // 16-byte aligned filter region inside [scan_lo, scan_hi)

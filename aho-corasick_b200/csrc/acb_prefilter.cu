@@ -147,6 +147,7 @@ __device__ __forceinline__ void verify_from(const DfaDev& d, const PrefilterLaun
         for (uint32_t i = lo; i < hi; ++i) {
           const uint32_t pid = __ldg(d.match_pids + i);
           if (__ldg(d.pattern_lens + pid) != j) break;
+          if (p.first_only && i > lo) break;  // duplicates of one pattern: the iterator can only yield the first
           const uint64_t tie = ((uint64_t)(d.max_pattern_len - j) << p.dup_shift) | (uint64_t)(i - lo);
           em.emit(((pos - p.span_start) << kTieBits) | tie, pid);
         }
