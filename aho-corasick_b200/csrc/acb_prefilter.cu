@@ -202,7 +202,7 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
 template <int MODE, bool MASKED, bool DENSE, int STRIDE, bool WIDE>
-__global__ void __launch_bounds__(PfGeom<WIDE>::kThreads, 1)
+__global__ void __launch_bounds__(PfGeom<WIDE>::kThreads, WIDE ? 2 : 1)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(!WIDE || STRIDE == 2, "the wide geometry needs the stride-2 first stage (32 hit bits per lane)");
