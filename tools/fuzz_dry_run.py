@@ -89,7 +89,9 @@ def one(rng, it):
                 ac.set_engine(eng)
                 eq(ac.find_iter_dev_np(ptr, n, span=span)[0], want, ctx + (span, int(eng), "find_iter dev"))
             ac.set_engine(ab.Engine.Auto)
-            if kind == 0:
+            # all occurrences: skip when the expected output is enormous (duplicate-heavy sets)
+            expect = n * sum(len(set(hay[:4000].tolist()) or {0}) ** -float(len(p)) for p in pats if p) if n else 0
+            if kind == 0 and expect < 2e6:
                 want = o.find_overlapping_iter_np(hay, span=span)
                 for eng in (ab.Engine.Auto, ab.Engine.Walk):
                     ac.set_engine(eng)
