@@ -95,6 +95,7 @@ struct acg_dfa {
   DfaDev dev{};
   int engine_override = ACG_ENGINE_AUTO;
   uint64_t pipeline_chunk = 64ull << 20;  // H2D chunk of the pipelined host path (acg_debug_set_pipeline_chunk)
+  uint32_t experiment = 0;                // ACG_EXP_* kernel variants awaiting measurement (acg_debug_set_experiment)
   mutable std::mutex mu;
   mutable Workspace ws;
   mutable acg_stats stats{};
@@ -583,7 +584,10 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.log_bits = pf.log_bits;
   p.k = pf.k;
   p.stride = pf.stride;
-  p.wide = pf.wide ? 1 : 0;
+  // kernel geometry: narrow / wide as planned; the tall geometry and the paired second stage are
+  // opt-in experiments for plans that would otherwise run the narrow stride-2 kernel
+  p.geom = pf.wide ? 1 : ((pf.stride == 2 && (a->experiment & ACG_EXP_TALL)) ? 2 : 0);
+  p.pair = (pf.stride == 2 && !pf.wide && (a->experiment & ACG_EXP_PAIR)) ? 1 : 0;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
@@ -1219,6 +1223,12 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
 int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
   if (!a || bytes < 4096 || (bytes & 4095)) return ACG_E_INVALID_ARG;
   a->pipeline_chunk = bytes;
+  return ACG_OK;
+}
+
+int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
+  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR))) return ACG_E_INVALID_ARG;
+  a->experiment = flags;
   return ACG_OK;
 }
 

@@ -88,7 +88,10 @@ struct PrefilterLaunch {
   uint32_t k;                   // fingerprint length in bytes (1..4), <= min_pattern_len
   uint32_t stride;              // 1: probe every offset with the k-gram; 2: probe even offsets with
                                 // 3-byte fingerprints of pattern bytes [0,3) and [1,4) (k == 4 only)
-  int wide;                     // stride 2 only: 2 KiB tiles / 512 threads (rare first-stage hits)
+  uint16_t geom;                // stride 2 only: 0 narrow, 1 wide (2 KiB tiles / 512 threads / 16 KiB bitmap: rare
+                                // first-stage hits), 2 tall (2 KiB tiles / 640 threads / 128 KiB bitmap; experiment)
+  uint16_t pair;                // stride 2, narrow / tall: paired second stage (experiment); shares a word with
+                                // `geom` so that the layout (and the SASS of the measured kernels) stays as it was
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult

@@ -18,6 +18,8 @@
 #endif
 #include ACB_PTX_HEADER
 
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include <cub/device/device_scan.cuh>
@@ -26,17 +28,22 @@
 namespace acb {
 namespace {
 
-// Kernel geometry.  NARROW: 1 024 threads, 1 KiB tile per warp step (2 x 16 positions per lane);
-// WIDE (stride 2 only): 512 threads, 2 KiB tile per warp step (4 x 16 positions per lane, 32
-// probes) -- the per-step bookkeeping is spread over twice as many positions, which pays when
-// first-stage hits are rare (few patterns); with frequent hits the 32 resident warps of the
-// narrow geometry hide the latency of the second stage and the verifier better.
-template <bool WIDE> struct PfGeom {
-  static constexpr int kThreads = WIDE ? 512 : 1024;
+// Kernel geometry.  NARROW (0): 1 024 threads, 1 KiB tile per warp step (2 x 16 positions per lane);
+// WIDE (1, stride 2 only): 512 threads, 2 KiB tile per warp step (4 x 16 positions per lane, 32
+// probes), 16 KiB bitmap, two CTAs per SM -- the per-step bookkeeping is spread over twice as many
+// positions, which pays when first-stage hits are rare (few patterns); with frequent hits the 32
+// resident warps of the narrow geometry hide the latency of the second stage and the verifier
+// better.  TALL (2, stride 2 only; experiment, acg_debug_set_experiment): the wide tile with the
+// full 128 KiB bitmap -- 640 threads, one CTA per SM (the most warps whose rings fit beside the
+// bitmap): the wide geometry's amortisation for pattern sets that need the large bitmap.
+enum : int { kGeomNarrow = 0, kGeomWide = 1, kGeomTall = 2 };
+template <int GEOM> struct PfGeom {
+  static constexpr int kThreads = GEOM == kGeomNarrow ? 1024 : (GEOM == kGeomWide ? 512 : 640);
   static constexpr int kWarps = kThreads / 32;
-  static constexpr int kGroups = WIDE ? 4 : 2;          // 16-byte groups per lane and step
+  static constexpr int kGroups = GEOM == kGeomNarrow ? 2 : 4;  // 16-byte groups per lane and step
   static constexpr int kTile = kGroups * 512;           // haystack bytes per warp step
   static constexpr int kStageBytes = kTile + 16;        // + fingerprint look-ahead
+  static constexpr int kMinCtas = GEOM == kGeomWide ? 2 : 1;
 };
 // per-warp queue sizes: first-probe hits of one step handled by the compacted second probe, and
 // verified-candidate entries (the dense variant stores 8-byte entries, so fewer of them fit
@@ -175,8 +182,8 @@ __device__ __forceinline__ void verify_at(const DfaDev& d, const PrefilterLaunch
 // so that the byte index (hash >> shift) and the shared-memory base fold into one address
 // instruction: 2^20 bits (128 KiB) in general; 2^17 bits (16 KiB) for the wide geometry, which is
 // only chosen for small pattern sets and then leaves room for two CTAs per SM.
-template <bool WIDE> struct PfBloom {
-  static constexpr uint32_t kLogBits = WIDE ? 17 : 20;
+template <int GEOM> struct PfBloom {
+  static constexpr uint32_t kLogBits = GEOM == kGeomWide ? 17 : 20;
   static constexpr uint32_t kShift = 35 - kLogBits;
 };
 
@@ -201,19 +208,23 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-template <int MODE, bool MASKED, bool DENSE, int STRIDE, bool WIDE>
-__global__ void __launch_bounds__(PfGeom<WIDE>::kThreads, WIDE ? 2 : 1)  // wide: two CTAs per SM (64 registers)
+// PAIR (experiment, stride 2 only): the second stage gives each lane one first-stage hit and lets
+// it test both start offsets the hit owns, instead of one (hit, start) item per lane -- half the
+// second-stage passes per step.
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, bool PAIR = false>
+__global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
-  static_assert(!WIDE || STRIDE == 2, "the wide geometry needs the stride-2 first stage (32 hit bits per lane)");
-  constexpr int kPfThreads = PfGeom<WIDE>::kThreads;
-  constexpr int kPfWarps = PfGeom<WIDE>::kWarps;
-  constexpr int kPfTile = PfGeom<WIDE>::kTile;
-  constexpr int kPfStageBytes = PfGeom<WIDE>::kStageBytes;
-  constexpr int kGroups = PfGeom<WIDE>::kGroups;
+  static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
+  static_assert(!PAIR || (STRIDE == 2 && !DENSE), "the paired second stage belongs to the stride-2 first stage");
+  constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
+  constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
+  constexpr int kPfTile = PfGeom<GEOM>::kTile;
+  constexpr int kPfStageBytes = PfGeom<GEOM>::kStageBytes;
+  constexpr int kGroups = PfGeom<GEOM>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
-  constexpr uint32_t kBloomShift = PfBloom<WIDE>::kShift;
+  constexpr uint32_t kBloomShift = PfBloom<GEOM>::kShift;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
   ACB_DYNAMIC_SMEM(smem_raw);
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
@@ -464,6 +475,48 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
         const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
         const uint32_t n_items = total * STRIDE;
+        if constexpr (PAIR) {
+          // one hit per lane; the lane tests the probed (even) offset e and the odd offset e-1
+          auto survives = [&](uint32_t gram) -> bool {
+            if (MASKED) gram = (gram | fold) & kmask;
+            return bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
+          };
+          for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t w = base + lane;
+            bool pass0 = false, pass1 = false;
+            uint32_t e = 0;
+            if (w < total) {
+              const uint32_t raw = slots[w];
+              e = hit_offset(raw & 31u, raw >> 5);
+              if (e == 0) {
+                // the odd start lies one byte before the tile (at most one hit per step): no second
+                // probe, the verifier decides -- unless it would fall before the filter region
+                pass0 = survives(ptx::lds32(tile_a));
+                pass1 = !region_first;
+              } else {
+                // e is even: the bytes e-1 .. e+3 lie in the two words around (e-1) & ~3
+                const uint32_t o1 = e - 1;
+                const uint32_t sa = tile_a + (o1 & ~3u);
+                const uint32_t lo = ptx::lds32(sa), hi = ptx::lds32(sa + 4);
+                const uint32_t sh = (o1 & 3u) * 8;  // 8 or 24
+                pass1 = survives(__funnelshift_r(lo, hi, sh));
+                pass0 = survives(__funnelshift_rc(lo, hi, sh + 8));  // shift 32 (e word aligned) -> hi
+              }
+            }
+            const uint32_t bal0 = __ballot_sync(0xffffffffu, pass0);
+            const uint32_t bal1 = __ballot_sync(0xffffffffu, pass1);
+            if (bal0) {
+              if (pass0) q2[q2len + __popc(bal0 & lt)] = wrel + e;
+              q2len += __popc(bal0);
+              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            }
+            if (bal1) {
+              if (pass1) q2[q2len + __popc(bal1 & lt)] = wrel + e - 1;
+              q2len += __popc(bal1);
+              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            }
+          }
+        } else
         for (uint32_t base = 0; base < n_items; base += 32) {
           const uint32_t w = base + lane;
           const uint32_t j = STRIDE == 2 ? (w & 1u) : 0u;
@@ -557,34 +610,43 @@ struct MaxOp {
 
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const bool dense = p.dense != 0;
-  const bool wide_geom = p.stride == 2 && p.wide;
-  const uint32_t want_log = wide_geom ? PfBloom<true>::kLogBits : PfBloom<false>::kLogBits;
+  const int geom = p.stride == 2 ? p.geom : kGeomNarrow;
+  if (geom < kGeomNarrow || geom > kGeomTall) return cudaErrorInvalidValue;
+  const bool pair = p.stride == 2 && p.pair && geom != kGeomWide;
+  const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const int threads = wide_geom ? PfGeom<true>::kThreads : PfGeom<false>::kThreads;
+  static const int kThreadsOf[3] = {PfGeom<0>::kThreads, PfGeom<1>::kThreads, PfGeom<2>::kThreads};
+  static const int kStageOf[3] = {PfGeom<0>::kStageBytes, PfGeom<1>::kStageBytes, PfGeom<2>::kStageBytes};
+  static const int kTileOf[3] = {PfGeom<0>::kTile, PfGeom<1>::kTile, PfGeom<2>::kTile};
+  const int threads = kThreadsOf[geom];
   const int warps = threads / 32;
-  const int stage_bytes = wide_geom ? PfGeom<true>::kStageBytes : PfGeom<false>::kStageBytes;
-  const int tile = wide_geom ? PfGeom<true>::kTile : PfGeom<false>::kTile;
-  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 +
-                                       (dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4) +
+  const int stage_bytes = kStageOf[geom];
+  const int tile = kTileOf[geom];
+  const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
+  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 + q2_bytes +
                                        (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 227 * 1024 - 256) return cudaErrorInvalidValue;  // 256 B of static shared memory (byte classes)
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
-  // [mode][masked][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide
-  // (stride 2 is never combined with the dense variant)
-  static const KernT table[2][2][4] = {
-      {{prefilter_kernel<0, false, false, 1, false>, prefilter_kernel<0, false, true, 1, false>,
-        prefilter_kernel<0, false, false, 2, false>, prefilter_kernel<0, false, false, 2, true>},
-       {prefilter_kernel<0, true, false, 1, false>, prefilter_kernel<0, true, true, 1, false>,
-        prefilter_kernel<0, true, false, 2, false>, prefilter_kernel<0, true, false, 2, true>}},
-      {{prefilter_kernel<1, false, false, 1, false>, prefilter_kernel<1, false, true, 1, false>,
-        prefilter_kernel<1, false, false, 2, false>, prefilter_kernel<1, false, false, 2, true>},
-       {prefilter_kernel<1, true, false, 1, false>, prefilter_kernel<1, true, true, 1, false>,
-        prefilter_kernel<1, true, false, 2, false>, prefilter_kernel<1, true, false, 2, true>}}};
+  // [mode][masked][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
+  // 4 stride 2 tall, 5 stride 2 narrow + paired second stage, 6 stride 2 tall + paired second stage
+  // (stride 2 is never combined with the dense variant; 4-6 are experiments, acb200_debug.h)
+#define ACB_PF_ROW(M, K)                                                                              \
+  {prefilter_kernel<M, K, false, 1, kGeomNarrow>, prefilter_kernel<M, K, true, 1, kGeomNarrow>,          \
+   prefilter_kernel<M, K, false, 2, kGeomNarrow>, prefilter_kernel<M, K, false, 2, kGeomWide>,           \
+   prefilter_kernel<M, K, false, 2, kGeomTall>, prefilter_kernel<M, K, false, 2, kGeomNarrow, true>,     \
+   prefilter_kernel<M, K, false, 2, kGeomTall, true>}
+  static const KernT table[2][2][7] = {{ACB_PF_ROW(0, false), ACB_PF_ROW(0, true)},
+                                       {ACB_PF_ROW(1, false), ACB_PF_ROW(1, true)}};
+#undef ACB_PF_ROW
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
-  const bool wide = p.stride == 2 && p.wide;
-  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.stride == 2 ? (wide ? 3 : 2) : (dense ? 1 : 0)];
+  int variant = dense ? 1 : 0;
+  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (geom == kGeomTall ? (pair ? 6 : 4) : (pair ? 5 : 2));
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][variant];
+#ifdef ACB_EMULATE
+  if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d threads %d smem %zu\n", variant, threads, smem);
+#endif
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;

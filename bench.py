@@ -128,6 +128,8 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 walk, 2 prefilter")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--experiment", type=int, default=0,
+                    help="ACG_EXP_* flags (include/acb200_debug.h): kernel variants awaiting measurement; 0 = default kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -165,6 +167,10 @@ def main():
     t0 = time.perf_counter()
     ac = b.build(pats).set_engine(args.engine)
     build_s = time.perf_counter() - t0
+    if args.experiment:
+        import ctypes
+        ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        assert ab._lib.acg_debug_set_experiment(ac._h, args.experiment) == 0
     # haystack slicing: this rank owns ends in (own_lo, own_hi] and reads from read_lo
     own_lo, own_hi, read_lo = S.slice_plan(0, total, world, ac.max_pattern_len())[rank]
     gen_lo = read_lo - read_lo % 4096
@@ -307,7 +313,7 @@ def main():
                                "~1 planted pattern per 4 KiB",
                    "haystack_bytes_per_gpu": per_gpu, "global_haystack_bytes": total,
                    "l2": "input per launch is far larger than the 126 MB L2",
-                   "engine": kname, "table_bytes": ac.memory_usage(), "states": ac.state_len(),
+                   "engine": kname, "experiment": args.experiment, "table_bytes": ac.memory_usage(), "states": ac.state_len(),
                    "sharding": "haystack slices, max_pattern_len-1 overlap, NCCL gather of match buffers to rank 0"
                                if world > 1 else "single GPU"},
         "matches": total_matches, "matches_per_s": total_matches * args.steps / dev_s,

@@ -310,6 +310,10 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
   return (unsigned)((((unsigned long long)hi << 32) | lo) >> (shift & 31));
 }
+// clamped variant: shift = min(shift, 32)
+inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned shift) {
+  return (unsigned)((((unsigned long long)hi << 32) | lo) >> (shift < 32 ? shift : 32));
+}
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }

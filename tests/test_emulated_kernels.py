@@ -251,6 +251,69 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
+# ---- kernel variants awaiting a measurement (include/acb200_debug.h: ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2)
+def set_experiment(ac, flags):
+    ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+    assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
+    return ac
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
+def test_experimental_variants_match_the_oracle(name, flags):
+    """The tall geometry and the paired second stage on the cfg 2 / cfg 3 pattern sets: overlapping,
+    find_iter, sub-span, host path, count + FNV."""
+    n, seed, nbytes, kind, ci = VARIANTS[name]
+    pats, hay = workload(n, seed, nbytes, ci)
+    W.plant(hay[: 64 << 10], pats, 9, period=96, window=40)   # a stretch with dense matches
+    ac = set_experiment(build(pats, kind, ci), flags)
+    assert plan_of(ac).stride == 2 and not plan_of(ac).wide
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    ptr = hay.ctypes.data
+    if kind == 0:
+        want = o.find_overlapping_iter_np(hay)
+        eq(ac.find_overlapping_iter_dev_np(ptr, hay.size)[0], want, (name, flags))
+        assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+        eq(ac.try_find_overlapping_iter_np(hay), want, (name, flags, "host"))
+        cnt, fnv, _ = ac.count_overlapping_dev(ptr, hay.size)
+        assert (cnt, fnv) == o.scan_overlapping_count(hay)
+    eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, flags))
+    s, e = 4099, hay.size - 777
+    eq(ac.find_iter_dev_np(ptr, hay.size, span=(s, e))[0], o.find_iter_np(hay, span=(s, e)), (name, flags, "span"))
+    # the default kernel on the same handle gives the same candidates-independent answer
+    set_experiment(ac, 0)
+    eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_experimental_variants_at_every_alignment(flags):
+    """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
+    paired second stage, the 2 KiB tiles of the tall geometry) at 18 pointer phases x 8 span ends."""
+    n, seed, _, kind, ci = VARIANTS["stride2_narrow"]
+    pats, hay = workload(n, seed, 72 << 10, ci)
+    W.plant(hay, pats, 8, period=64, window=32)
+    ac = set_experiment(build(pats, 0, ci), flags)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    backing = np.zeros(hay.size + 64, dtype=np.uint8)
+    for phase in range(18):
+        view = backing[phase:phase + hay.size]
+        view[:] = hay
+        for cut in (0, 1, 2, 3, 15, 16, 17, 33):
+            sub = view[:hay.size - cut]
+            eq(ac.find_overlapping_iter_dev_np(sub.ctypes.data, sub.size)[0], o.find_overlapping_iter_np(sub), (flags, phase, cut))
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_experimental_variants_unselective_steps(flags):
+    pats = [b"abab", b"baba", b"ababab"] + W.make_patterns(5000, 0xAC5000)
+    ac = set_experiment(build(pats, 0), flags)
+    assert plan_of(ac).stride == 2 and not plan_of(ac).wide
+    hay = np.frombuffer(b"ab" * 20000 + b"xyz" + b"ba" * 3000, dtype=np.uint8).copy()
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), flags)
+    eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), flags)
+
+
 # ---- the reference's regression tests around its memchr-class prefilters, src/tests.rs:1537-1660:
 # results only (the device engine has no such prefilters), through the product on the dry-run library
 def test_reference_regressions():

@@ -1,6 +1,7 @@
 """Occupancy assumptions of the kernels, checked at compile time (`nvcc -Xptxas -v`, no GPU needed):
 the narrow prefilter geometry runs 1 024 threads per CTA (at most 64 registers per thread), the
-wide geometry relies on two 512-thread CTAs per SM (again 64), and nothing may spill."""
+wide geometry relies on two 512-thread CTAs per SM (again 64), the experimental tall geometry runs
+640 threads (102), and nothing may spill."""
 import re
 import shutil
 import subprocess
@@ -39,11 +40,13 @@ def ptxas_info(source):
 
 def test_prefilter_kernel_register_budget():
     info = {k: v for k, v in ptxas_info("acb_prefilter.cu").items() if "prefilter_kernel" in k}
-    assert len(info) == 16
+    assert len(info) == 28   # 16 measured instantiations + 12 experimental ones (tall geometry, paired second stage)
     for name, v in info.items():
         assert v["spill"] == 0, name
-        # 65 536 registers per SM: 1 024 threads (narrow) or 2 x 512 threads (wide) => 64 per thread
-        assert v["regs"] <= 64, (name, v["regs"])
+        # 65 536 registers per SM: 1 024 threads (narrow) or 2 x 512 threads (wide) => 64 per thread;
+        # the tall geometry (template argument GEOM = 2: ...ELi2ELi2E...) runs 640 threads => 102
+        tall = re.search(r"prefilter_kernelILi\dELb\dELb\dELi2ELi2E", name) is not None
+        assert v["regs"] <= (102 if tall else 64), (name, v["regs"])
 
 
 def test_walk_and_helper_kernels_do_not_spill():
