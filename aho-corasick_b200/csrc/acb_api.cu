@@ -96,6 +96,11 @@ struct acg_dfa {
   int engine_override = ACG_ENGINE_AUTO;
   uint64_t pipeline_chunk = 64ull << 20;  // H2D chunk of the pipelined host path (acg_debug_set_pipeline_chunk)
   uint32_t experiment = 0;                // ACG_EXP_* kernel variants awaiting measurement (acg_debug_set_experiment)
+  // hot-row walk (ACG_EXP_WALK_HOT): flagged table copy + staged row list, built on first use
+  mutable uint32_t* d_trans_hot = nullptr;
+  mutable uint32_t* d_hot_ids = nullptr;
+  mutable uint32_t n_hot = 0, start_hot = 0;
+  mutable bool hot_tried = false;
   mutable std::mutex mu;
   mutable Workspace ws;
   mutable acg_stats stats{};
@@ -497,6 +502,44 @@ struct TupleResult {
   int sorted_buf = 0;
 };
 
+// Hot-row walk (experiment): stage the rows of the unanchored start state and of the depth-1
+// states (in row order, as many as fit in kWalkHotSmemMax) unless they are match states, and
+// derive the flagged copy of the table on the device.  Leaves n_hot == 0 when nothing qualifies.
+int ensure_hot_rows(const acg_dfa* a) {
+  if (a->hot_tried) return ACG_OK;
+  a->hot_tried = true;
+  const HostDfa& h = a->h;
+  const uint32_t s2 = h.stride2;
+  if (h.start_unanchored_id == 0 || (h.trans.size() >> 31) != 0) return ACG_OK;
+  const size_t max_rows = acb::kWalkHotSmemMax / (size_t(4) << s2);
+  const size_t rows = size_t(h.state_len);
+  std::vector<uint32_t> ids;
+  std::vector<uint16_t> hot_of_row(rows, 0);
+  auto stage = [&](uint32_t row) {
+    const uint32_t id = row << s2;
+    if (id <= h.max_match_id || ids.size() >= max_rows || ids.size() >= 0xFFFE || hot_of_row[row]) return;
+    ids.push_back(id);
+    hot_of_row[row] = uint16_t(ids.size());
+  };
+  stage(h.start_unanchored_id >> s2);
+  for (size_t r = 2; r < rows && r < a->depth16.size(); ++r)
+    if (a->depth16[r] == 1) stage(uint32_t(r));
+  if (ids.empty()) return ACG_OK;
+  uint16_t* d_hot_of_row = nullptr;
+  CK(cudaMalloc(&a->d_trans_hot, h.trans.size() * 4));
+  CK(cudaMalloc(&a->d_hot_ids, ids.size() * 4));
+  CK(cudaMalloc(&d_hot_of_row, rows * 2));
+  CK(cudaMemcpyAsync(a->d_hot_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, a->ws.stream));
+  CK(cudaMemcpyAsync(d_hot_of_row, hot_of_row.data(), rows * 2, cudaMemcpyHostToDevice, a->ws.stream));
+  CK(acb::launch_flag_table(a->d_trans, a->d_trans_hot, h.trans.size(), d_hot_of_row, s2, a->ws.stream));
+  CK(cudaStreamSynchronize(a->ws.stream));
+  cudaFree(d_hot_of_row);
+  const uint32_t start_slot = hot_of_row[h.start_unanchored_id >> s2];
+  a->start_hot = start_slot ? (acb::kWalkHotFlag | ((start_slot - 1) << s2)) : h.start_unanchored_id;
+  a->n_hot = uint32_t(ids.size());
+  return ACG_OK;
+}
+
 // K1 + K4 on a device-resident haystack; leaves `n` ordered tuples in
 // ws.d_keys[sorted_buf] / ws.d_pids[sorted_buf].
 int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start,
@@ -515,11 +558,20 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   // phase of the first shard; the kernel handles the unaligned head per lane.
   const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
   uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 256));
+  const bool hot = (a->experiment & ACG_EXP_WALK_HOT) != 0;
+  if (hot) {
+    int rc = ensure_hot_rows(a);
+    if (rc) return rc;
+  }
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
     if (rc) return rc;
     CK(cudaMemsetAsync(w.d_counter, 0, 8, w.stream));
     acb::WalkLaunch p;
+    p.trans_hot = hot ? a->d_trans_hot : nullptr;
+    p.hot_ids = hot ? a->d_hot_ids : nullptr;
+    p.n_hot = hot ? a->n_hot : 0;
+    p.start_hot = a->start_hot;
     p.hay = d_hay;
     p.span_start = span_start;
     p.span_end = span_end;
@@ -1140,6 +1192,7 @@ void acg_dfa_free(acg_dfa* a) {
     if (w.stream) cudaStreamSynchronize(w.stream);
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
     cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_amap);
+    cudaFree(a->d_trans_hot); cudaFree(a->d_hot_ids);
     for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
     cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
     cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);
@@ -1227,7 +1280,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT))) return ACG_E_INVALID_ARG;
   a->experiment = flags;
   return ACG_OK;
 }

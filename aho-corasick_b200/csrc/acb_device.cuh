@@ -53,8 +53,17 @@ struct WalkLaunch {
   uint32_t* pids;       // [cap]
   unsigned long long* counter;  // total tuples wanted (may exceed cap => overflow)
   uint64_t cap;
+  // hot-row variant (experiment; n_hot == 0: plain walk over DfaDev::trans)
+  const uint32_t* trans_hot;    // flagged copy of the table (see walk_overlapping_kernel)
+  const uint32_t* hot_ids;      // [n_hot] premultiplied ids of the staged rows, slot order
+  uint32_t n_hot;
+  uint32_t start_hot;           // id of the unanchored start state in the flagged table
 };
+constexpr uint32_t kWalkHotFlag = 0x80000000u;
+constexpr size_t kWalkHotSmemMax = 72 * 1024;  // three CTAs per SM
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s);
+cudaError_t launch_flag_table(const uint32_t* in, uint32_t* out, uint64_t n, const uint16_t* hot_of_row,
+                              uint32_t stride2, cudaStream_t s);
 
 // Single-lane restatement of FindIter (src/automaton.rs:857-936) over
 // try_find_fwd (:1259-1420): anchored inputs, automata containing the empty

@@ -60,6 +60,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 // make three values opaque to the compiler so that they stay in registers instead of being
 // re-derived (from the thread index) at every use
 __device__ __forceinline__ void keep_in_registers(uint32_t& a, uint32_t& b, uint32_t& c) {

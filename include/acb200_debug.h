@@ -41,10 +41,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 
 /* Kernel variants that are implemented and parity-tested but not yet measured against the default
  * on a B200; they never change results, only which instantiation of the prefilter kernel runs for
- * plans with the stride-2 first stage and the 128 KiB bitmap (e.g. BASELINE config 2).  The
- * default (0) is the measured kernel.  tools/ab_experiments.sh times every combination. */
+ * plans with the stride-2 first stage and the 128 KiB bitmap (e.g. BASELINE config 2), or whether
+ * the walk engine stages its hot rows.  The default (0) is the measured kernel.  tools/ab_experiments.sh times every combination. */
 #define ACG_EXP_TALL 1u /* 2 KiB tiles, 640 threads, one CTA per SM: per-step bookkeeping over twice the positions */
 #define ACG_EXP_PAIR 2u /* second stage: one first-stage hit per lane, both of its start offsets tested by that lane */
+#define ACG_EXP_WALK_HOT 4u /* walk engine (K1): rows of the start and depth-1 states in shared memory, flagged table copy */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ inline uint32_t lds32(uint32_t a) {
   std::memcpy(&v, smem_ptr(a, 4), 4);
   return v;
 }
+inline uint32_t lds8(uint32_t a) { return *smem_ptr(a, 1); }
 inline void keep_in_registers(uint32_t&, uint32_t&, uint32_t&) {}
 inline uint4 ld_nc_u4(const void* p) {
   if ((uintptr_t)p & 15) emu::die("misaligned 16-byte global load");

@@ -314,6 +314,38 @@ def test_experimental_variants_unselective_steps(flags):
     eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), flags)
 
 
+@pytest.mark.parametrize("name", ["stride2_narrow", "stride2_wide", "stride1_short_patterns", "dense"])
+def test_walk_engine_with_hot_rows(name):
+    """ACG_EXP_WALK_HOT = 4: K1 over the flagged table copy with the start / depth-1 rows staged in
+    shared memory -- same stream as the oracle and as the plain walk, incl. sub-spans and 1-byte
+    patterns (depth-1 match states are not staged)."""
+    n, seed, nbytes, kind, ci = VARIANTS[name]
+    pats, hay = workload(n, seed, min(nbytes, 256 << 10), ci)
+    if name == "stride1_short_patterns":
+        pats = [p[:3] for p in pats[:150]] + pats[150:] + [b"q", b"Z"]
+    W.plant(hay[: 32 << 10], pats, 9, period=96, window=40)
+    ac = set_experiment(build(pats, 0, ci, engine=ab.Engine.Walk), 4)
+    o = O.Oracle(pats, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    want = o.find_overlapping_iter_np(hay)
+    got, _ = ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)
+    eq(got, want, name)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
+    s, e = 4099, hay.size - 777
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size, span=(s, e))[0], o.find_overlapping_iter_np(hay, span=(s, e)), name)
+    eq(ac.try_find_overlapping_iter_np(hay), want, name + " host")
+    set_experiment(ac, 0)
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], want, name + " plain")
+
+
+def test_walk_hot_rows_with_empty_pattern_and_tiny_automata():
+    """The start state is a match state (empty pattern): it is not staged; single-pattern automata."""
+    for pats in ([b"", b"ab", b"b"], [b"abc"], [b"a"], [b"ab", b"ba", b"abab"]):
+        hay = np.frombuffer(b"xxabcabab" * 300 + b"ab", dtype=np.uint8).copy()
+        ac = set_experiment(build(pats, 0, engine=ab.Engine.Walk), 4)
+        o = O.Oracle(pats, kind=O.KIND_DFA)
+        eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), pats)
+
+
 # ---- the reference's regression tests around its memchr-class prefilters, src/tests.rs:1537-1660:
 # results only (the device engine has no such prefilters), through the product on the dry-run library
 def test_reference_regressions():

@@ -53,3 +53,21 @@ def test_experimental_prefilter_variants(cfg, kind, ci, flags):
         got, _ = ac.find_iter_dev_np(d.data_ptr(), n)
         assert_np_equal(got, want, (cfg, flags))
         assert_np_equal(ac.try_find_iter_np(hay), want, (cfg, flags, "host"))
+
+
+@pytest.mark.timeout(600)
+def test_experimental_walk_hot_rows():
+    """ACG_EXP_WALK_HOT = 4: K1 with the start / depth-1 rows in shared memory, cfg 2 at 24 MiB."""
+    import torch
+    n = 24 << 20
+    pats, hay, planted = W.make_config("cfg2", n)
+    ac = set_experiment(build(pats, 0, engine=ab.Engine.Walk, kind=ab.AhoCorasickKind.DFA), 4)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    want = o.find_overlapping_iter_np(hay)
+    d = to_device(torch.from_numpy(hay))
+    got, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n)
+    assert_np_equal(got, want, "walk hot")
+    assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
+    s, e = 4099, n - 777
+    sub, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n, span=(s, e))
+    assert_np_equal(sub, o.find_overlapping_iter_np(hay, span=(s, e)), "walk hot span")

@@ -21,3 +21,16 @@ except Exception as e:
 PY
   done
 done
+# walk engine (K1): plain vs hot rows in shared memory
+for exp in 0 4; do
+  out=gpurun_out/bench_${tag}_cfg2_walk_exp${exp}.json
+  timeout 600 python bench.py --workload cfg2 --engine 1 --experiment $exp --no-cpu-baseline --no-e2e --hay-gib 1 --steps 5 > $out 2> ${out%.json}.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open("$out").read().strip().splitlines()[-1])
+    print("cfg2 walk exp $exp scan_ms", round(d["scan_ms"], 4), "frac", round(d["roofline"]["frac"], 4), "matches", d["matches"])
+except Exception as e:
+    print("cfg2 walk exp $exp failed", e)
+PY
+done
