@@ -142,28 +142,36 @@ void derive_metadata(acg_dfa* a) {
     a->max_list_len = std::max(a->max_list_len, h.match_offsets[i + 1] - h.match_offsets[i]);
   // Trie depth of every row = BFS distance from the unanchored start row: one transition
   // deepens the longest-suffix state by at most one byte, and a state of depth d is reached by
-  // its own d bytes.
+  // its own d bytes.  The builder hands it over for tables it built; adopted tables are walked.
   const uint32_t s2 = h.stride2;
   const size_t rows = size_t(h.state_len);
-  std::vector<uint32_t> dist(rows, UINT32_MAX);
-  std::vector<uint32_t> q;
-  if (h.start_unanchored_id) {
-    dist[h.start_unanchored_id >> s2] = 0;
-    q.push_back(h.start_unanchored_id >> s2);
-  }
-  for (size_t qi = 0; qi < q.size(); ++qi) {
-    const uint32_t r = q[qi];
-    const uint32_t* row = h.trans.data() + (size_t(r) << s2);
-    for (uint32_t c = 0; c < h.alphabet_len; ++c) {
-      const uint32_t nr = row[c] >> s2;
-      if (nr == 0 || dist[nr] != UINT32_MAX) continue;
-      dist[nr] = dist[r] + 1;
-      q.push_back(nr);
+  auto bfs_depth = [&]() {
+    std::vector<uint32_t> dist(rows, UINT32_MAX);
+    std::vector<uint32_t> q;
+    if (h.start_unanchored_id) {
+      dist[h.start_unanchored_id >> s2] = 0;
+      q.push_back(h.start_unanchored_id >> s2);
     }
+    for (size_t qi = 0; qi < q.size(); ++qi) {
+      const uint32_t r = q[qi];
+      const uint32_t* row = h.trans.data() + (size_t(r) << s2);
+      for (uint32_t c = 0; c < h.alphabet_len; ++c) {
+        const uint32_t nr = row[c] >> s2;
+        if (nr == 0 || dist[nr] != UINT32_MAX) continue;
+        dist[nr] = dist[r] + 1;
+        q.push_back(nr);
+      }
+    }
+    std::vector<uint16_t> out(rows, 0xFFFF);
+    for (size_t r = 0; r < rows; ++r)
+      if (dist[r] != UINT32_MAX) out[r] = uint16_t(std::min<uint32_t>(dist[r], 0xFFFE));
+    return out;
+  };
+  if (h.row_depth.size() == rows) {
+    a->depth16 = h.row_depth;  // tests/test_adopt_tables_host.py: equals bfs_depth() of the same table
+  } else {
+    a->depth16 = bfs_depth();
   }
-  a->depth16.assign(rows, 0xFFFF);
-  for (size_t r = 0; r < rows; ++r)
-    if (dist[r] != UINT32_MAX) a->depth16[r] = uint16_t(std::min<uint32_t>(dist[r], 0xFFFE));
 
   // ---- prefilter plan ----
   PrefilterPlan& pf = a->pf;

@@ -355,6 +355,11 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
       const auto& h = t.hits[slot[pos]];
       if (!h.empty()) mlists[pos - 2] = h;
     }
+    if (!anchored) {
+      d.row_depth.assign(ns, 0xFFFF);
+      d.row_depth[newid[kRoot]] = 0;
+      for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(depth[v], 0xFFFE));
+    }
     d.max_special_id = n_max_special << s2;
     d.max_match_id = n_max_match << s2;
     d.start_unanchored_id = anchored ? kDead : (n_start_u << s2);

@@ -52,6 +52,10 @@ struct HostDfa {
   uint64_t state_len = 0;
   int prefilter_kind = kPreNone;
   PackedPlan packed;
+  // Trie depth of every table row that is reachable from the unanchored start state (0xFFFF for
+  // the others), when the builder knows it (unanchored start kind); empty otherwise.  Equals the
+  // BFS distance from the start row that acb_api.cu derives for adopted tables.
+  std::vector<uint16_t> row_depth;
 };
 
 struct PatternRef {

@@ -71,3 +71,31 @@ def test_malformed_descriptors_are_rejected():
     t = _valid(); t["match_offsets"][1] = t["match_offsets"][-1] + 7; _rejects(t)  # non-monotone CSR
     t = _valid(); t["match_kind"] = 3; _rejects(t)
     t = _valid(); t["max_pattern_len"] = 2; _rejects(t)                          # a pattern longer than the maximum
+
+
+def test_builder_row_depth_equals_the_walked_depth_of_the_same_table():
+    """The builder hands the trie depth of every row to the device engine (acb_build.hpp:
+    HostDfa::row_depth); an adopted copy of the same table has it derived by a BFS over the
+    transitions.  Both must agree row for row, for every match kind, with and without case folding,
+    with 1-byte and duplicate patterns."""
+    import random
+    from test_prefilter_plan import plan_of
+    rng = random.Random(77)
+    sets = [W.make_patterns(3000, 0xAC5000), W.make_patterns(50, 0xAC0050),
+            [b"a", b"ab", b"abc", b"b", b"bca", b"a"], [b"Sam", b"Samwise", b"sam", b"wise"]]
+    for _ in range(40):
+        n = rng.randint(1, 40)
+        sets.append([bytes(rng.choice(b"abAB") for _ in range(rng.randint(1, 6))) for _ in range(n)])
+    for pats in sets:
+        for kind in (0, 1, 2):
+            for ci in (False, True):
+                built = (ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci)
+                         .kind(ab.AhoCorasickKind.DFA).host_only(True).build(pats))
+                t = built.tables()
+                t["start_kind"] = 0
+                adopted = _adopt(t)
+                pb, pa = plan_of(built), plan_of(adopted)
+                assert pb.n_rows == pa.n_rows
+                db = np.ctypeslib.as_array(pb.depth16, shape=(pb.n_rows,))
+                da = np.ctypeslib.as_array(pa.depth16, shape=(pa.n_rows,))
+                assert np.array_equal(db, da), (pats[:5], kind, ci)
