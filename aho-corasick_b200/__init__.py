@@ -125,6 +125,7 @@ def _declare(lib):
     lib.acg_strerror.argtypes = [_i]
     lib.acg_build.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_u64), _u64, C.POINTER(_BuildOpts), C.POINTER(_vp)]
     lib.acg_build_host.argtypes = lib.acg_build.argtypes
+    lib.acg_build_on_device.argtypes = lib.acg_build.argtypes
     lib.acg_dfa_create.argtypes = [C.POINTER(_Desc), C.POINTER(_vp)]
     lib.acg_dfa_free.argtypes = [_vp]
     lib.acg_dfa_free.restype = None
@@ -329,6 +330,7 @@ class AhoCorasickBuilder:
                        ascii_case_insensitive=False, byte_classes=True, prefilter=True, kind=None,
                        dense_depth=3)
         self._host_only = False
+        self._device_fill = False
 
     def match_kind(self, kind):
         self._o["match_kind"] = MatchKind(kind)
@@ -363,6 +365,12 @@ class AhoCorasickBuilder:
         self._host_only = bool(yes)
         return self
 
+    def device_fill(self, yes=True):
+        """Produce the dense transition table on the GPU (acg_build_on_device) instead of building it on
+        the host and copying it over; same table, same results."""
+        self._device_fill = bool(yes)
+        return self
+
     def build(self, patterns):
         pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
         n = len(pats)
@@ -377,7 +385,7 @@ class AhoCorasickBuilder:
         opts = _BuildOpts(int(o["match_kind"]), int(o["start_kind"]), int(o["ascii_case_insensitive"]),
                           int(o["byte_classes"]), int(o["prefilter"]), int(o["kind"] or 0), o["dense_depth"])
         h = _vp()
-        fn = _lib.acg_build_host if self._host_only else _lib.acg_build
+        fn = _lib.acg_build_host if self._host_only else (_lib.acg_build_on_device if self._device_fill else _lib.acg_build)
         rc = fn(arr, lens, n, C.byref(opts), C.byref(h))
         if rc in (-1, -2, -3):
             raise BuildError(rc)
@@ -477,7 +485,9 @@ class AhoCorasick:
 
     def tables(self) -> dict:
         d = _Desc()
-        _lib.acg_dfa_table(self._h, C.byref(d))
+        rc = _lib.acg_dfa_table(self._h, C.byref(d))  # fetches the table of a device-filled handle
+        if rc:
+            raise DeviceError(rc)
         nms = (d.max_match_id >> d.stride2) - 1
 
         def arr(ptr, n):

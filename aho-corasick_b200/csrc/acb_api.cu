@@ -196,9 +196,24 @@ void derive_metadata(acg_dfa* a) {
   std::vector<std::vector<uint32_t>> grams(kmax + 1);
   std::vector<std::vector<Item>> level(kmax + 1);  // (row, raw bytes) of every trie path of that length
   std::vector<Item> cur{{h.start_unanchored_id >> s2, 0u}}, nxt;
+  // deferred dense fill: the table does not exist on the host; the builder's shallow trie edges
+  // (grouped by source row, bytes ascending) are the same transitions "one byte deeper"
+  std::vector<uint32_t> sh_first;  // first shallow edge of a row, +1 (0: none)
+  if (h.fill.valid) {
+    sh_first.assign(rows, 0);
+    for (size_t i = h.fill.shallow.size(); i-- > 0;) sh_first[h.fill.shallow[i].from_row] = uint32_t(i + 1);
+  }
   for (uint32_t j = 0; j < kmax; ++j) {
     nxt.clear();
     for (const Item& it : cur) {
+      if (h.fill.valid) {
+        for (size_t i = sh_first[it.row]; i != 0 && i <= h.fill.shallow.size() && h.fill.shallow[i - 1].from_row == it.row; ++i) {
+          const auto& e = h.fill.shallow[i - 1];
+          if (e.to_row == 0 || a->depth16[e.to_row] != j + 1) continue;
+          nxt.push_back(Item{e.to_row, it.gram | (e.byte << (8 * j))});
+        }
+        continue;
+      }
       const uint32_t* row = h.trans.data() + (size_t(it.row) << s2);
       for (uint32_t b = 0; b < 256; ++b) {
         const uint32_t nr = row[h.classes[b]] >> s2;
@@ -372,6 +387,54 @@ void derive_metadata(acg_dfa* a) {
   }
 }
 
+// Dense table produced on the device from the builder's DenseFillPlan (acb_build.hpp): one
+// launch per BFS level.  The plan's arrays are freed afterwards; the host never holds the table
+// unless acg_dfa_table asks for it (fetch_table).
+int fill_table_on_device(acg_dfa* a) {
+  HostDfa& h = a->h;
+  const acb::DenseFillPlan& f = h.fill;
+  const size_t n = f.row.size();
+  uint32_t *d_row = nullptr, *d_inh = nullptr, *d_fill = nullptr, *d_eoff = nullptr, *d_eto = nullptr;
+  uint8_t* d_ecls = nullptr;
+  auto release = [&]() {
+    cudaFree(d_row); cudaFree(d_inh); cudaFree(d_fill); cudaFree(d_eoff); cudaFree(d_eto); cudaFree(d_ecls);
+  };
+  auto up = [&](auto** dptr, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+    return e;
+  };
+  cudaError_t e = cudaMalloc(&a->d_trans, std::max<size_t>(size_t(h.trans_len) * 4, 16));
+  if (e == cudaSuccess) e = cudaMemset(a->d_trans, 0, size_t(h.trans_len) * 4);
+  if (e == cudaSuccess) e = up(&d_row, f.row.data(), n * 4);
+  if (e == cudaSuccess) e = up(&d_inh, f.inherit_row.data(), n * 4);
+  if (e == cudaSuccess) e = up(&d_fill, f.fill_id.data(), n * 4);
+  if (e == cudaSuccess) e = up(&d_eoff, f.edge_off.data(), f.edge_off.size() * 4);
+  if (e == cudaSuccess) e = up(&d_eto, f.edge_to.data(), f.edge_to.size() * 4);
+  if (e == cudaSuccess) e = up(&d_ecls, f.edge_class.data(), f.edge_class.size());
+  for (size_t l = 0; e == cudaSuccess && l + 1 < f.level_off.size(); ++l) {
+    const uint32_t lo = f.level_off[l], hi = f.level_off[l + 1];
+    acb::FillLaunch p;
+    p.trans = a->d_trans;
+    p.stride2 = h.stride2;
+    p.alphabet_len = h.alphabet_len;
+    p.row = d_row + lo;
+    p.inherit_row = d_inh + lo;
+    p.fill_id = d_fill + lo;
+    p.edge_off = d_eoff + lo;
+    p.edge_class = d_ecls;
+    p.edge_to = d_eto;
+    p.n = hi - lo;
+    e = acb::launch_dfa_fill_level(p, nullptr);  // default stream: levels run in order
+    a->stats.launches += 1;
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  release();
+  if (e != cudaSuccess) { cudaGetLastError(); return ACG_E_CUDA; }
+  return ACG_OK;
+}
+
 int upload(acg_dfa* a) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -387,7 +450,12 @@ int upload(acg_dfa* a) {
     if (bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
     return e;
   };
-  CK(up(&a->d_trans, h.trans.data(), h.trans.size() * 4));
+  if (h.fill.valid) {
+    int rc = fill_table_on_device(a);
+    if (rc) return rc;
+  } else {
+    CK(up(&a->d_trans, h.trans.data(), h.trans.size() * 4));
+  }
   CK(up(&a->d_classes, h.classes, 256));
   CK(up(&a->d_moff, h.match_offsets.data(), h.match_offsets.size() * 4));
   CK(up(&a->d_mpids, h.match_pids.data(), h.match_pids.size() * 4));
@@ -518,7 +586,7 @@ int ensure_hot_rows(const acg_dfa* a) {
   a->hot_tried = true;
   const HostDfa& h = a->h;
   const uint32_t s2 = h.stride2;
-  if (h.start_unanchored_id == 0 || (h.trans.size() >> 31) != 0) return ACG_OK;
+  if (h.start_unanchored_id == 0 || (h.trans_len >> 31) != 0) return ACG_OK;
   const size_t max_rows = acb::kWalkHotSmemMax / (size_t(4) << s2);
   const size_t rows = size_t(h.state_len);
   std::vector<uint32_t> ids;
@@ -534,12 +602,12 @@ int ensure_hot_rows(const acg_dfa* a) {
     if (a->depth16[r] == 1) stage(uint32_t(r));
   if (ids.empty()) return ACG_OK;
   uint16_t* d_hot_of_row = nullptr;
-  CK(cudaMalloc(&a->d_trans_hot, h.trans.size() * 4));
+  CK(cudaMalloc(&a->d_trans_hot, size_t(h.trans_len) * 4));
   CK(cudaMalloc(&a->d_hot_ids, ids.size() * 4));
   CK(cudaMalloc(&d_hot_of_row, rows * 2));
   CK(cudaMemcpyAsync(a->d_hot_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, a->ws.stream));
   CK(cudaMemcpyAsync(d_hot_of_row, hot_of_row.data(), rows * 2, cudaMemcpyHostToDevice, a->ws.stream));
-  CK(acb::launch_flag_table(a->d_trans, a->d_trans_hot, h.trans.size(), d_hot_of_row, s2, a->ws.stream));
+  CK(acb::launch_flag_table(a->d_trans, a->d_trans_hot, h.trans_len, d_hot_of_row, s2, a->ws.stream));
   CK(cudaStreamSynchronize(a->ws.stream));
   cudaFree(d_hot_of_row);
   const uint32_t start_slot = hot_of_row[h.start_unanchored_id >> s2];
@@ -1081,7 +1149,7 @@ void acg_build_opts_default(acg_build_opts* o) {
 }
 
 static int build_common(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
-                        const acg_build_opts* opts, bool to_device, acg_dfa** out) {
+                        const acg_build_opts* opts, bool to_device, acg_dfa** out, bool device_fill = false) {
   if (!out) return ACG_E_INVALID_ARG;
   *out = nullptr;
   acg_build_opts def;
@@ -1095,6 +1163,7 @@ static int build_common(const uint8_t* const* patterns, const uint64_t* lens, ui
   bo.byte_classes = opts->byte_classes != 0;
   bo.prefilter = opts->prefilter != 0;
   bo.kind = opts->kind;
+  bo.defer_dense = device_fill && to_device;
   std::vector<acb::PatternRef> pats(n);
   for (uint64_t i = 0; i < n; ++i) pats[i] = acb::PatternRef{patterns[i], lens[i]};
   acg_dfa* a = new (std::nothrow) acg_dfa();
@@ -1119,6 +1188,10 @@ int acg_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
 int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
                    const acg_build_opts* opts, acg_dfa** out) {
   return build_common(patterns, lens, n, opts, false, out);
+}
+int acg_build_on_device(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                        const acg_build_opts* opts, acg_dfa** out) {
+  return build_common(patterns, lens, n, opts, true, out, true);
 }
 
 // Structural checks of an adopted table (the layout facts of src/dfa.rs:91-132 the kernels rely
@@ -1163,6 +1236,7 @@ int acg_dfa_create(const acg_dfa_desc* d, acg_dfa** out) {
   HostDfa& h = a->h;
   try {
     h.trans.assign(d->trans, d->trans + d->trans_len);
+    h.trans_len = d->trans_len;
     h.stride2 = d->stride2;
     h.alphabet_len = d->alphabet_len;
     std::memcpy(h.classes, d->byte_classes, 256);
@@ -1218,8 +1292,29 @@ void acg_dfa_free(acg_dfa* a) {
   delete a;
 }
 
+namespace {
+// The table of a handle whose dense fill ran on the device, fetched on demand.
+int fetch_table(const acg_dfa* a) {
+  HostDfa& h = const_cast<acg_dfa*>(a)->h;
+  if (!h.fill.valid || !h.trans.empty()) return ACG_OK;
+  if (!a->d_trans) return ACG_E_NO_DEVICE;
+  std::lock_guard<std::mutex> lock(a->mu);
+  if (!h.trans.empty()) return ACG_OK;
+  DeviceGuard guard(a->device);
+  std::vector<uint32_t> t(size_t(h.trans_len));
+  if (cudaMemcpy(t.data(), a->d_trans, t.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cudaGetLastError();
+    return ACG_E_CUDA;
+  }
+  h.trans.swap(t);
+  return ACG_OK;
+}
+
+}  // namespace
+
 int acg_dfa_table(const acg_dfa* a, acg_dfa_desc* o) {
   if (!a || !o) return ACG_E_INVALID_ARG;
+  if (int rc = fetch_table(a)) return rc;
   const HostDfa& h = a->h;
   o->trans = h.trans.data();
   o->trans_len = h.trans.size();
@@ -1252,7 +1347,7 @@ uint64_t acg_max_pattern_len(const acg_dfa* a) { return a ? a->h.max_pattern_len
 uint64_t acg_memory_usage(const acg_dfa* a) {
   if (!a) return 0;  // DFA::memory_usage, src/dfa.rs:289-297 (heap of the tables)
   const HostDfa& h = a->h;
-  return h.trans.size() * 4 + (h.match_offsets.size() - 1) * 24 + h.match_pids.size() * 4 +
+  return h.trans_len * 4 + (h.match_offsets.size() - 1) * 24 + h.match_pids.size() * 4 +
          h.pattern_lens.size() * 4;
 }
 int acg_prefilter_kind(const acg_dfa* a) { return a ? a->h.prefilter_kind : 0; }

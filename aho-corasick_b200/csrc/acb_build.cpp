@@ -324,12 +324,62 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   d.state_len = both ? ns * 2 - 4 : ns;
   const uint64_t trans_len = uint64_t(d.state_len) << s2;
   if (trans_len - stride > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;  // :462-478
+  d.trans_len = trans_len;
   const size_t n_match_states = both ? size_t(n_max_match - 1) * 2 : size_t(n_max_match - 1);
   std::vector<std::vector<uint32_t>> mlists(n_match_states);
 
   auto rep_class = [&](uint8_t b) { return d.classes[b]; };
 
-  if (!both) {
+  if (!both && opts.defer_dense && opts.start_kind == kStartUnanchored) {
+    // same rows as the branch below, described instead of written
+    DenseFillPlan& f = d.fill;
+    f.valid = true;
+    const size_t n_rows = bfs.size() + 2;
+    f.row.reserve(n_rows); f.inherit_row.reserve(n_rows); f.fill_id.reserve(n_rows); f.edge_off.reserve(n_rows + 1);
+    auto add_row = [&](uint32_t node, uint32_t inherit, uint32_t fill) {
+      f.row.push_back(newid[node]);
+      f.inherit_row.push_back(inherit);
+      f.fill_id.push_back(fill);
+      f.edge_off.push_back(uint32_t(f.edge_to.size()));
+      for (const Edge& e : t.edges[node]) {
+        f.edge_class.push_back(rep_class(e.byte));
+        f.edge_to.push_back(newid[e.to] << s2);
+      }
+    };
+    f.level_off.push_back(0);
+    add_row(kRoot, UINT32_MAX, t.root_loop_closed ? kDead : (newid[kRoot] << s2));
+    add_row(kAnchoredRoot, UINT32_MAX, kDead);
+    uint32_t cur_depth = 0;
+    for (uint32_t v : bfs) {
+      if (depth[v] != cur_depth) {  // BFS order: depths never decrease
+        cur_depth = depth[v];
+        f.level_off.push_back(uint32_t(f.row.size()));
+      }
+      add_row(v, t.fail[v] != kDead ? newid[t.fail[v]] : UINT32_MAX, kDead);
+    }
+    f.level_off.push_back(uint32_t(f.row.size()));
+    f.edge_off.push_back(uint32_t(f.edge_to.size()));
+    auto add_shallow = [&](uint32_t node) {
+      for (const Edge& e : t.edges[node])
+        f.shallow.push_back(DenseFillPlan::ShallowEdge{newid[node], e.byte, newid[e.to]});
+    };
+    add_shallow(kRoot);
+    for (uint32_t v : bfs) {
+      if (depth[v] >= 4) break;
+      add_shallow(v);
+    }
+    for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos) {
+      const auto& h = t.hits[slot[pos]];
+      if (!h.empty()) mlists[pos - 2] = h;
+    }
+    d.row_depth.assign(ns, 0xFFFF);
+    d.row_depth[newid[kRoot]] = 0;
+    for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(depth[v], 0xFFFE));
+    d.max_special_id = n_max_special << s2;
+    d.max_match_id = n_max_match << s2;
+    d.start_unanchored_id = n_start_u << s2;
+    d.start_anchored_id = kDead;
+  } else if (!both) {
     const bool anchored = opts.start_kind == kStartAnchored;
     d.trans.assign(size_t(trans_len), kDead);
     uint32_t* T = d.trans.data();

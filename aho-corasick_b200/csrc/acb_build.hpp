@@ -26,6 +26,28 @@ struct BuildOptions {
   bool byte_classes = true;
   bool prefilter = true;
   int kind = 0;  // AhoCorasickKind requested (0 auto); only reported back
+  // Leave the dense table unfilled and describe it by a DenseFillPlan instead (unanchored start
+  // kind only; ignored otherwise): the rows are then produced on the device (acb_kernels.cu:
+  // dfa_fill_level_kernel), level by level.
+  bool defer_dense = false;
+};
+
+// Compact description of the dense transition table of src/dfa.rs:544-593 (finish_build_one_start:
+// every cell is delta(state, class)), in the row-inheritance form of this builder: row(v) is
+// row(fail(v)) -- complete one BFS level earlier -- overlaid with v's own trie edges.
+struct DenseFillPlan {
+  bool valid = false;
+  std::vector<uint32_t> level_off;    // [levels + 1] offsets into the per-row arrays (level 0: the two start rows)
+  std::vector<uint32_t> row;          // table row to produce
+  std::vector<uint32_t> inherit_row;  // row to copy first, UINT32_MAX: fill with fill_id instead
+  std::vector<uint32_t> fill_id;      // premultiplied id for every class when nothing is inherited
+  std::vector<uint32_t> edge_off;     // [rows + 1] CSR over the row's own edges
+  std::vector<uint8_t> edge_class;
+  std::vector<uint32_t> edge_to;      // premultiplied id
+  // trie edges that leave nodes of depth < 4, by raw byte (ascending per source row): what the
+  // device engine needs to enumerate pattern beginnings without the dense table
+  struct ShallowEdge { uint32_t from_row; uint32_t byte; uint32_t to_row; };
+  std::vector<ShallowEdge> shallow;
 };
 
 // Which packed (Teddy) searcher the reference would construct as a prefilter
@@ -56,6 +78,8 @@ struct HostDfa {
   // the others), when the builder knows it (unanchored start kind); empty otherwise.  Equals the
   // BFS distance from the start row that acb_api.cu derives for adopted tables.
   std::vector<uint16_t> row_depth;
+  uint64_t trans_len = 0;  // state_len << stride2 (== trans.size() unless the fill was deferred)
+  DenseFillPlan fill;      // valid => `trans` is empty
 };
 
 struct PatternRef {

@@ -65,6 +65,22 @@ cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cuda
 cudaError_t launch_flag_table(const uint32_t* in, uint32_t* out, uint64_t n, const uint16_t* hot_of_row,
                               uint32_t stride2, cudaStream_t s);
 
+// Dense-table construction on the device (the cells of src/dfa.rs:544-593):
+// one launch per BFS level of the trie, one warp per table row: copy the row of the failure state
+// (complete since an earlier level) or fill with a constant, then overlay the row's own edges.
+struct FillLaunch {
+  uint32_t* trans;              // [state_len << stride2], zero-initialised
+  uint32_t stride2, alphabet_len;
+  const uint32_t* row;          // per entry of this level: row to produce
+  const uint32_t* inherit_row;  // UINT32_MAX: fill with fill_id
+  const uint32_t* fill_id;
+  const uint32_t* edge_off;     // [n + 1], indexes edge_class / edge_to (absolute offsets)
+  const uint8_t* edge_class;
+  const uint32_t* edge_to;
+  uint32_t n;                   // rows in this level
+};
+cudaError_t launch_dfa_fill_level(const FillLaunch& f, cudaStream_t s);
+
 // Single-lane restatement of FindIter (src/automaton.rs:857-936) over
 // try_find_fwd (:1259-1420): anchored inputs, automata containing the empty
 // pattern, and tiny spans.  Writes (pid,start,end) triples as 3 x u64.

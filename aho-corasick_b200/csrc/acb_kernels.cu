@@ -147,6 +147,26 @@ __global__ void flag_table_kernel(const uint32_t* in, uint32_t* out, uint64_t n,
   }
 }
 
+// ---- dense-table construction (one BFS level per launch) -------------------------
+constexpr int kFillThreads = 256;
+
+__global__ void __launch_bounds__(kFillThreads) dfa_fill_level_kernel(FillLaunch f) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= f.n) return;
+  uint32_t* dst = f.trans + ((size_t)f.row[w] << f.stride2);
+  const uint32_t inherit = f.inherit_row[w];
+  if (inherit != UINT32_MAX) {
+    const uint32_t* src = f.trans + ((size_t)inherit << f.stride2);  // written by an earlier launch
+    for (uint32_t c = lane; c < f.alphabet_len; c += 32) dst[c] = src[c];
+  } else {
+    const uint32_t v = f.fill_id[w];
+    for (uint32_t c = lane; c < f.alphabet_len; c += 32) dst[c] = v;
+  }
+  __syncwarp();
+  for (uint32_t e = f.edge_off[w] + lane; e < f.edge_off[w + 1]; e += 32) dst[f.edge_class[e]] = f.edge_to[e];
+}
+
 // ---- sequential engine -------------------------------------------------------
 
 struct SeqMatch {
@@ -280,6 +300,16 @@ cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cuda
   }
   const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;
   ACB_LAUNCH(walk_overlapping_kernel<false>, (unsigned)blocks, kWalkThreads, 0, s, dfa, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dfa_fill_level(const FillLaunch& f, cudaStream_t s) {
+  if (f.n == 0) return cudaSuccess;
+#ifdef ACB_EMULATE
+  if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_dfa_fill_level rows %u\n", f.n);
+#endif
+  const uint64_t blocks = ((uint64_t)f.n * 32 + kFillThreads - 1) / kFillThreads;
+  ACB_LAUNCH(dfa_fill_level_kernel, (unsigned)blocks, kFillThreads, 0, s, f);
   return cudaGetLastError();
 }
 

@@ -67,6 +67,31 @@ class ClockSampler:
                 "reasons": sorted(self.reasons)}
 
 
+def usable_cores():
+    """Host threads this process can really run at once: the CPU count, cut by the affinity mask
+    and by a cgroup CPU quota (a container on a 128-thread host may be limited to far fewer)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = Path(path).read_text().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]) + 0.5)))
+            else:
+                quota = int(txt[0])
+                period = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+                if quota > 0:
+                    n = min(n, max(1, int(quota / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def reference_arm(args):
     """The reference's own CPU path: the scalar DFA loop (src/automaton.rs:1491-1534 over
     src/dfa.rs:218-226) as restated in oracle/ (rustc is unavailable, so kind = "port"), run on
@@ -80,7 +105,7 @@ def reference_arm(args):
     import oracle_py as O
     from aho_corasick_b200 import workload as W
     import torch
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     sample = min(int(args.hay_gib * GIB), cores * (24 << 20))
     sample -= sample % 8
     pats = W.make_patterns(5000, W.CONFIGS["cfg2"]["pattern_seed"])
@@ -128,6 +153,8 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="0 auto, 1 walk, 2 prefilter")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--device-fill", action="store_true",
+                    help="build the dense table on the GPU (acg_build_on_device); see build_s in the output")
     ap.add_argument("--experiment", type=int, default=0,
                     help="ACG_EXP_* flags (include/acb200_debug.h): kernel variants awaiting measurement; 0 = default kernel")
     args = ap.parse_args()
@@ -164,6 +191,8 @@ def main():
         b.ascii_case_insensitive(True).match_kind(ab.MatchKind.LeftmostFirst)
     if args.workload == "cfg4":
         b.match_kind(ab.MatchKind.LeftmostFirst)
+    if args.device_fill:
+        b.device_fill(True)
     t0 = time.perf_counter()
     ac = b.build(pats).set_engine(args.engine)
     build_s = time.perf_counter() - t0
@@ -313,7 +342,7 @@ def main():
                                "~1 planted pattern per 4 KiB",
                    "haystack_bytes_per_gpu": per_gpu, "global_haystack_bytes": total,
                    "l2": "input per launch is far larger than the 126 MB L2",
-                   "engine": kname, "experiment": args.experiment, "table_bytes": ac.memory_usage(), "states": ac.state_len(),
+                   "engine": kname, "experiment": args.experiment, "device_fill": bool(args.device_fill), "table_bytes": ac.memory_usage(), "states": ac.state_len(),
                    "sharding": "haystack slices, max_pattern_len-1 overlap, NCCL gather of match buffers to rank 0"
                                if world > 1 else "single GPU"},
         "matches": total_matches, "matches_per_s": total_matches * args.steps / dev_s,

@@ -114,6 +114,16 @@ int acg_build(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
  * on such a handle return ACG_E_NO_DEVICE. */
 int acg_build_host(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
                    const acg_build_opts* opts, acg_dfa** out);
+/* acg_build with the dense transition table produced on the GPU: the host
+ * runs the noncontiguous construction (trie, failure links, match lists, state permutation:
+ * src/nfa/noncontiguous.rs:963-1481) and ships that compact form; the cells of
+ * dfa::Builder::finish_build_one_start (src/dfa.rs:544-593) -- next_state for every (state, class)
+ * -- are filled by a kernel, one launch per trie level, each row inheriting the finished row of
+ * its failure state.  Same table bit for bit (acg_dfa_table fetches it back on demand); nothing of
+ * size state_len x stride is built on or copied from the host.  Applies to StartKind::Unanchored
+ * (the other start kinds take the acg_build path). */
+int acg_build_on_device(const uint8_t* const* patterns, const uint64_t* lens, uint64_t n,
+                        const acg_build_opts* opts, acg_dfa** out);
 /* Adopt a DFA built by the reference itself (pointers borrowed for the call). */
 int acg_dfa_create(const acg_dfa_desc* desc, acg_dfa** out);
 void acg_dfa_free(acg_dfa* dfa);

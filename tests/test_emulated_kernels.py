@@ -346,6 +346,89 @@ def test_walk_hot_rows_with_empty_pattern_and_tiny_automata():
         eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), pats)
 
 
+# ---- dense table produced on the "device" (acg_build_on_device) -------------
+def _builder(kind, ci, **kw):
+    b = ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci).kind(ab.AhoCorasickKind.DFA)
+    for k, v in kw.items():
+        getattr(b, k)(v)
+    return b
+
+
+def _same_tables(a, b, ctx):
+    ta, tb = a.tables(), b.tables()
+    assert set(ta) == set(tb)
+    for k in ta:
+        va, vb = ta[k], tb[k]
+        if isinstance(va, np.ndarray):
+            assert np.array_equal(va, vb), (k, ctx)
+        else:
+            assert va == vb, (k, ctx)
+
+
+def _same_plan(a, b, ctx):
+    pa, pb = plan_of(a), plan_of(b)
+    for f in ("supported", "brute", "dense", "stride", "wide", "k", "kmask", "fold", "mult", "mult3", "shift",
+              "log_bits", "bitmap_words", "amap_log", "n_rows", "dup_shift"):
+        assert getattr(pa, f) == getattr(pb, f), (f, ctx)
+    if pa.supported:
+        n = int(pa.bitmap_words)
+        assert np.array_equal(np.ctypeslib.as_array(pa.bitmap, shape=(n,)), np.ctypeslib.as_array(pb.bitmap, shape=(n,))), ctx
+        if pa.amap_log:
+            m = 1 << pa.amap_log
+            assert np.array_equal(np.ctypeslib.as_array(pa.amap, shape=(m,)), np.ctypeslib.as_array(pb.amap, shape=(m,))), ctx
+    assert np.array_equal(np.ctypeslib.as_array(pa.depth16, shape=(int(pa.n_rows),)),
+                          np.ctypeslib.as_array(pb.depth16, shape=(int(pb.n_rows),))), ctx
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("ci", [False, True])
+def test_device_fill_reproduces_the_host_table(kind, ci):
+    """Table, derived prefilter plan and search results of acg_build_on_device == acg_build, on the
+    golden-style corner sets (1-byte patterns, duplicates, prefixes, empty pattern) and random sets."""
+    import random
+    rng = random.Random(1000 + kind * 2 + ci)
+    sets = [[b"apple", b"maple", b"Snapple"], [b"a", b"ab", b"abc", b"b", b"bca", b"a"], [b"", b"ab", b"b"], [b"x"],
+            [b"append", b"appendage", b"app"], W.make_patterns(400, 3), W.make_patterns(60, 4, lo=1, hi=5)]
+    for _ in range(25):
+        sets.append([bytes(rng.choice(b"abAB") for _ in range(rng.randint(1, 7))) for _ in range(rng.randint(1, 40))])
+    for pats in sets:
+        host = _builder(kind, ci).build(pats)
+        dev = _builder(kind, ci, device_fill=True).build(pats)
+        ctx = (pats[:4], kind, ci)
+        _same_plan(host, dev, ctx)     # before the table is fetched: derived from the trie alone
+        _same_tables(host, dev, ctx)   # acg_dfa_table fetches the device-built table
+        assert host.memory_usage() == dev.memory_usage()
+        hay = np.frombuffer(b"xxabcaBAbab Snapple appendage maple" * 40 + bytes(rng.choice(b"abAB") for _ in range(3000)),
+                            dtype=np.uint8).copy()
+        o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+        eq(dev.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), ctx)
+        if kind == 0:
+            eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), ctx)
+
+
+def test_device_fill_on_the_baseline_pattern_sets():
+    for n, seed, kind, ci in ((5000, 0xAC5000, 0, False), (5000, 0xAC5000, 1, True), (50, 0xAC0050, 1, False),
+                              (20000, 0xAC1000, 0, False)):
+        pats, hay = workload(n, seed, 192 << 10, ci)
+        host = _builder(kind, ci).build(pats)
+        dev = _builder(kind, ci, device_fill=True).build(pats)
+        _same_plan(host, dev, n)
+        o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+        eq(dev.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), n)
+        if kind == 0:   # both engines read the device-built table
+            eq(dev.set_engine(ab.Engine.Walk).find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0],
+               o.find_overlapping_iter_np(hay), n)
+        _same_tables(host, dev, n)
+
+
+def test_device_fill_falls_back_for_other_start_kinds():
+    pats = [b"abcd", b"bcd", b"cd", b"b"]
+    for sk in (ab.StartKind.Both, ab.StartKind.Anchored):
+        host = _builder(1, False, start_kind=sk).build(pats)
+        dev = _builder(1, False, start_kind=sk, device_fill=True).build(pats)
+        _same_tables(host, dev, sk)
+
+
 # ---- the reference's regression tests around its memchr-class prefilters, src/tests.rs:1537-1660:
 # results only (the device engine has no such prefilters), through the product on the dry-run library
 def test_reference_regressions():

@@ -34,3 +34,16 @@ except Exception as e:
     print("cfg2 walk exp $exp failed", e)
 PY
 done
+# dense table built on the host (+ H2D) vs on the device: build_s of the 100 000-pattern automaton
+for flag in "" "--device-fill"; do
+  out=gpurun_out/bench_${tag}_cfg5_build${flag:+_devfill}.json
+  timeout 900 python bench.py --workload cfg5 $flag --no-cpu-baseline --no-e2e --hay-gib 1 --steps 3 > $out 2> ${out%.json}.err
+  python - <<PY
+import json
+try:
+    d = json.loads(open("$out").read().strip().splitlines()[-1])
+    print("cfg5 build ${flag:-host}", "build_s", round(d["build_s"], 3), "scan_ms", round(d["scan_ms"], 4), "matches", d["matches"])
+except Exception as e:
+    print("cfg5 build ${flag:-host} failed", e)
+PY
+done
