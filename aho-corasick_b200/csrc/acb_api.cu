@@ -63,6 +63,8 @@ struct PrefilterPlan {
   bool supported = false;
   uint32_t k = 0, kmask = 0, fold = 0, mult = 1, mult3 = 1, shift = 0, log_bits = 0;
   uint32_t stride = 1;
+  uint32_t key_shift = 8;  // stride 2: first-stage hash = window * (mult3 << key_shift); 5: the key also
+                           // holds the low 3 bits of the window's fourth byte (ACG_EXP_KEY27)
   bool wide = false;
   bool brute = false;
   uint32_t dup_shift = 0;
@@ -290,6 +292,7 @@ void derive_metadata(acg_dfa* a) {
   // every occurrence (a pattern that starts at an odd offset shows its second fingerprint at the
   // next even one) and halves the per-position probe work.  Worth it while those 3-grams stay rare.
   if (!pf.brute && pf.k == 4 && best_set.size() <= 8192) {
+    const std::vector<Item>& paths4 = level[4];
     std::vector<uint32_t> g3;
     g3.reserve(best_set.size() * 2);
     const uint32_t f3 = pf.fold & 0x00FFFFFFu;
@@ -333,6 +336,44 @@ void derive_metadata(acg_dfa* a) {
       // the byte from the fingerprint's own low bits.  A multiplicative hash of such short keys is
       // sensitive to the constant, so pick the candidate that lets through the fewest fingerprints
       // drawn from the bytes the patterns use at each position.
+      // First-stage keys.  Default: the 3-byte fingerprints.  ACG_EXP_KEY27 (experiment): 27-bit keys
+      // -- the 3 bytes plus the low 3 bits of the window's fourth byte, which a shift of 5 instead
+      // of 8 in the multiplier keeps at no cost in the kernel.  For a pattern that starts at the
+      // probed (even) offset the fourth byte is its own fourth byte; for one that starts one byte
+      // earlier it is the pattern's fifth byte -- any of the 8 values if the pattern ends after four
+      // bytes.  Genuine 3-byte prefix hits (the bulk of the first-stage hits of cfg 2) drop 8-fold.
+      const bool key27 = (a->experiment & ACG_EXP_KEY27) != 0;
+      pf.key_shift = key27 ? 5 : 8;
+      std::vector<uint32_t> keys1;
+      if (!key27) {
+        keys1 = g3;
+      } else {
+        for (const Item& it : paths4) {
+          const uint32_t g = it.gram;
+          keys1.push_back(((g & 0x00FFFFFFu) | f3) | (((g >> 24) & 7u) << 24));
+          uint32_t xs = 0;  // bit x: some pattern through this 4-gram continues with a byte whose low bits are x
+          if (it.row >= 2 && (it.row << s2) <= h.max_match_id) {
+            const uint32_t lo = h.match_offsets[it.row - 2], hi = h.match_offsets[it.row - 1];
+            if (lo < hi && h.pattern_lens[h.match_pids[lo]] == 4) xs = 0xFF;  // a 4-byte pattern ends here
+          }
+          if (xs != 0xFF) {
+            if (h.fill.valid) {
+              for (size_t i = sh_first[it.row]; i != 0 && i <= h.fill.shallow.size() && h.fill.shallow[i - 1].from_row == it.row; ++i)
+                if (a->depth16[h.fill.shallow[i - 1].to_row] == 5) xs |= 1u << (h.fill.shallow[i - 1].byte & 7);
+            } else {
+              const uint32_t* row = h.trans.data() + (size_t(it.row) << s2);
+              for (uint32_t b = 0; b < 256; ++b) {
+                const uint32_t nr = row[h.classes[b]] >> s2;
+                if (nr != 0 && a->depth16[nr] == 5) xs |= 1u << (b & 7);
+              }
+            }
+          }
+          for (uint32_t x = 0; x < 8; ++x)
+            if (xs >> x & 1) keys1.push_back(((g >> 8) | f3) | (x << 24));
+        }
+        std::sort(keys1.begin(), keys1.end());
+        keys1.erase(std::unique(keys1.begin(), keys1.end()), keys1.end());
+      }
       static const uint32_t kCand[] = {0x1B873593u, 0x27D4EB2Fu, 0x165667B1u, 0x9E3779B1u, 0x2C1B3C6Du,
                                        0xB5297A4Du, 0x85EBCA6Bu, 0x5BD1E995u, 0x7FEB352Du, 0xCC9E2D51u,
                                        0x1B56C4E9u, 0xC2B2AE35u};
@@ -342,29 +383,31 @@ void derive_metadata(acg_dfa* a) {
         for (uint32_t g : g3) seen[(g >> (8 * j)) & 0xFF] = true;
         for (uint32_t b = 0; b < 256; ++b) if (seen[b]) alpha[j].push_back(uint8_t(b));
       }
+      const uint32_t ks = pf.key_shift;
       auto bit_of = [&](uint32_t g, uint32_t m) -> uint32_t {
-        return ((g * (m << 8)) >> pf.shift) * 8 + (g & 7);
+        return ((g * (m << ks)) >> pf.shift) * 8 + (g & 7);
       };
       uint32_t best_m = kCand[0];
       uint64_t best_pass = UINT64_MAX;
       std::vector<uint32_t> trial;
       for (uint32_t m : kCand) {
         trial = pf.bitmap;
-        for (uint32_t g : g3) { const uint32_t bit = bit_of(g, m); trial[bit >> 5] |= 1u << (bit & 31); }
+        for (uint32_t g : keys1) { const uint32_t bit = bit_of(g, m); trial[bit >> 5] |= 1u << (bit & 31); }
         uint64_t pass = 0, x = 0x9E3779B97F4A7C15ull;
         for (int i = 0; i < 65536; ++i) {
           x = x * 6364136223846793005ull + 1442695040888963407ull;
           const uint32_t r = uint32_t(x >> 33);
-          const uint32_t g = uint32_t(alpha[0][r % alpha[0].size()]) |
-                             uint32_t(alpha[1][(r >> 10) % alpha[1].size()]) << 8 |
-                             uint32_t(alpha[2][(r >> 20) % alpha[2].size()]) << 16;
+          uint32_t g = uint32_t(alpha[0][r % alpha[0].size()]) |
+                       uint32_t(alpha[1][(r >> 10) % alpha[1].size()]) << 8 |
+                       uint32_t(alpha[2][(r >> 20) % alpha[2].size()]) << 16;
+          if (key27) g |= uint32_t((x >> 20) & 7) << 24;
           const uint32_t bit = bit_of(g, m);
           pass += (trial[bit >> 5] >> (bit & 31)) & 1u;
         }
         if (pass < best_pass) { best_pass = pass; best_m = m; }
       }
       pf.mult3 = best_m;
-      for (uint32_t g : g3) {
+      for (uint32_t g : keys1) {
         const uint32_t bit = bit_of(g, best_m);
         pf.bitmap[bit >> 5] |= 1u << (bit & 31);
       }
@@ -720,6 +763,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.fold = pf.fold;
   p.mult = pf.mult;
   p.mult3 = pf.mult3;
+  p.key_shift = pf.key_shift;
   p.shift = pf.shift;
   p.dense = pf.dense ? 1 : 0;
   p.brute = pf.brute ? 1 : 0;
@@ -1368,7 +1412,7 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
   out->stride = int32_t(pf.stride);
   out->wide = pf.wide ? 1 : 0;
   out->k = pf.k; out->kmask = pf.kmask; out->fold = pf.fold;
-  out->mult = pf.mult; out->mult3 = pf.mult3; out->shift = pf.shift; out->log_bits = pf.log_bits;
+  out->mult = pf.mult; out->mult3 = pf.mult3; out->key_shift = pf.key_shift; out->shift = pf.shift; out->log_bits = pf.log_bits;
   out->bitmap = pf.bitmap.data(); out->bitmap_words = pf.bitmap.size();
   out->amap = pf.amap.data(); out->amap_log = pf.amap_log;
   out->depth16 = a->depth16.data(); out->n_rows = a->depth16.size();
@@ -1383,8 +1427,23 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT | ACG_EXP_KEY27))) return ACG_E_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(a->mu);
+  const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;
+  if (changed & ACG_EXP_KEY27) {
+    // the first-stage keys are part of the plan: rebuild it and refresh the device copy of the bitmap
+    const size_t old_words = a->pf.bitmap.size();
+    derive_metadata(a);
+    if (a->on_device && a->d_bitmap && a->pf.supported) {
+      if (a->pf.bitmap.size() != old_words) return ACG_E_INVALID_ARG;  // the geometry does not depend on the keys
+      DeviceGuard guard(a->device);
+      if (cudaMemcpy(a->d_bitmap, a->pf.bitmap.data(), old_words * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        return ACG_E_CUDA;
+      }
+    }
+  }
   return ACG_OK;
 }
 

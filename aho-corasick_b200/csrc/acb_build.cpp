@@ -365,7 +365,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     };
     add_shallow(kRoot);
     for (uint32_t v : bfs) {
-      if (depth[v] >= 4) break;
+      if (depth[v] >= 5) break;
       add_shallow(v);
     }
     for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos) {

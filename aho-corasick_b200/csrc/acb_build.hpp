@@ -44,7 +44,7 @@ struct DenseFillPlan {
   std::vector<uint32_t> edge_off;     // [rows + 1] CSR over the row's own edges
   std::vector<uint8_t> edge_class;
   std::vector<uint32_t> edge_to;      // premultiplied id
-  // trie edges that leave nodes of depth < 4, by raw byte (ascending per source row): what the
+  // trie edges that leave nodes of depth < 5, by raw byte (ascending per source row): what the
   // device engine needs to enumerate pattern beginnings without the dense table
   struct ShallowEdge { uint32_t from_row; uint32_t byte; uint32_t to_row; };
   std::vector<ShallowEdge> shallow;

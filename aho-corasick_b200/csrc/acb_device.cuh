@@ -135,6 +135,9 @@ struct PrefilterLaunch {
   uint32_t* pids;
   unsigned long long* counter;  // [0] tuples, [1] candidates
   uint64_t cap;
+  uint32_t key_shift;           // stride 2: first-stage hash = window * (mult3 << key_shift).  8: the fourth window
+                                // byte drops out (3-byte keys); 5: its low 3 bits stay in the key (experiment).
+                                // Last member, so that the layout of the measured kernels' parameters is unchanged.
 };
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s);
 

@@ -279,7 +279,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint32_t fold1 = p.fold & 0x00FFFFFFu;  // stride 2: the first stage fingerprints 3 bytes
   // stride 2: multiplying by (mult << 8) drops the window's fourth byte for free; the bit inside
   // the bitmap byte then comes from the fingerprint's own low bits (the product's are zero)
-  const uint32_t mult8 = p.mult3 << 8;
+  const uint32_t mult8 = p.mult3 << p.key_shift;  // 8: 24-bit keys; 5: 27-bit keys (experiment)
   // queue offsets are relative to chunk_base: a stride-2 probe at the first byte of the chunk
   // also owns the start one byte before it
   const uint64_t chunk_base = chunk_lo - (uint64_t)(STRIDE - 1) * (chunk_lo > 0 ? 1 : 0);

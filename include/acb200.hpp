@@ -210,10 +210,14 @@ class AhoCorasickBuilder {
   AhoCorasickBuilder& prefilter(bool yes) { o_.prefilter = yes; return *this; }
   AhoCorasickBuilder& dense_depth(uint64_t d) { o_.dense_depth = int64_t(d); return *this; }
   AhoCorasickBuilder& byte_classes(bool yes) { o_.byte_classes = yes; return *this; }
+  // device-side knob with no counterpart in the reference: fill the dense table on the GPU
+  // (acg_build_on_device) instead of on the host; same table, same results
+  AhoCorasickBuilder& device_fill(bool yes) { device_fill_ = yes; return *this; }
   template <class Patterns>
   AhoCorasick build(const Patterns& patterns) const;
  private:
   acg_build_opts o_;
+  bool device_fill_ = false;
 };
 
 // `AhoCorasick`, src/ahocorasick.rs:177-2082 (search surface)
@@ -372,7 +376,7 @@ AhoCorasick AhoCorasickBuilder::build(const Patterns& patterns) const {
     lens.push_back(v.size());
   }
   acg_dfa* h = nullptr;
-  int rc = acg_build(ptrs.data(), lens.data(), ptrs.size(), &o_, &h);
+  int rc = (device_fill_ ? acg_build_on_device : acg_build)(ptrs.data(), lens.data(), ptrs.size(), &o_, &h);
   if (rc == ACG_E_STATE_ID_OVERFLOW || rc == ACG_E_PATTERN_ID_OVERFLOW || rc == ACG_E_PATTERN_TOO_LONG)
     throw BuildError(rc);
   if (rc) throw DeviceError(rc);

@@ -30,6 +30,7 @@ typedef struct {
   const uint16_t* depth16; /* trie depth per table row */
   uint64_t n_rows;
   uint32_t dup_shift;      /* tie-break layout: (max_len - len) << dup_shift | index among equal patterns */
+  uint32_t key_shift;      /* stride 2: first-stage hash = window * (mult3 << key_shift); 8, or 5 with ACG_EXP_KEY27 */
 } acg_prefilter_plan;
 
 /* Fills *out with views of the handle's derived tables.  Works on host-only handles. */
@@ -46,6 +47,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 #define ACG_EXP_TALL 1u /* 2 KiB tiles, 640 threads, one CTA per SM: per-step bookkeeping over twice the positions */
 #define ACG_EXP_PAIR 2u /* second stage: one first-stage hit per lane, both of its start offsets tested by that lane */
 #define ACG_EXP_WALK_HOT 4u /* walk engine (K1): rows of the start and depth-1 states in shared memory, flagged table copy */
+#define ACG_EXP_KEY27 8u /* stride-2 first stage keyed by 27 bits (3 bytes + low 3 bits of the fourth): rebuilds the bitmap */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

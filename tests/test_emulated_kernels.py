@@ -251,14 +251,15 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- kernel variants awaiting a measurement (include/acb200_debug.h: ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2)
+# ---- kernel variants awaiting a measurement (include/acb200_debug.h: ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2,
+# ACG_EXP_WALK_HOT = 4, ACG_EXP_KEY27 = 8)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
     return ac
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("flags", [1, 2, 3, 8, 10, 11])
 @pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
 def test_experimental_variants_match_the_oracle(name, flags):
     """The tall geometry and the paired second stage on the cfg 2 / cfg 3 pattern sets: overlapping,
@@ -285,7 +286,7 @@ def test_experimental_variants_match_the_oracle(name, flags):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11])
 def test_experimental_variants_at_every_alignment(flags):
     """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
     paired second stage, the 2 KiB tiles of the tall geometry) at 18 pointer phases x 8 span ends."""
@@ -301,6 +302,24 @@ def test_experimental_variants_at_every_alignment(flags):
         for cut in (0, 1, 2, 3, 15, 16, 17, 33):
             sub = view[:hay.size - cut]
             eq(ac.find_overlapping_iter_dev_np(sub.ctypes.data, sub.size)[0], o.find_overlapping_iter_np(sub), (flags, phase, cut))
+
+
+def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
+    """ACG_EXP_KEY27 with the 16 KiB bitmap (cfg 4's plan), and 4-byte patterns at odd offsets followed
+    by every possible byte."""
+    n, seed, nbytes, kind, ci = VARIANTS["stride2_wide"]
+    pats, hay = workload(n, seed, 256 << 10, ci)
+    ac = set_experiment(build(pats, kind, ci), 8)
+    assert plan_of(ac).wide and plan_of(ac).key_shift == 5
+    o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA)
+    eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), "wide key27")
+    pats = [b"abcd", b"bcde", b"wxyz", b"abcdq"] + W.make_patterns(5000, 0xAC5000)
+    body = b"".join(b" " * (i % 2) + p + bytes([x]) for i, p in enumerate(pats[:4] * 64) for x in (i * 37 % 256,))
+    hay = np.frombuffer(body + bytes(range(256)) * 4, dtype=np.uint8).copy()
+    ac = set_experiment(build(pats, 0), 8)
+    assert plan_of(ac).stride == 2 and plan_of(ac).key_shift == 5
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
 
 
 @pytest.mark.parametrize("flags", [1, 2, 3])

@@ -29,7 +29,8 @@ class Plan(C.Structure):
                 ("mult", C.c_uint32), ("mult3", C.c_uint32), ("shift", C.c_uint32), ("log_bits", C.c_uint32),
                 ("bitmap", C.POINTER(C.c_uint32)), ("bitmap_words", C.c_uint64),
                 ("amap", C.POINTER(C.c_uint64)), ("amap_log", C.c_uint32),
-                ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64), ("dup_shift", C.c_uint32)]
+                ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64), ("dup_shift", C.c_uint32),
+                ("key_shift", C.c_uint32)]
 
 
 def plan_of(ac):
@@ -73,7 +74,7 @@ def first_stage_hit(p, window):
     """The per-position probe of prefilter_kernel for a 4-byte little-endian window."""
     if p.stride == 2:
         gm = (window | (p.fold & 0x00FFFFFF)) & M32
-        h = (gm * ((p.mult3 << 8) & M32)) & M32
+        h = (gm * ((p.mult3 << p.key_shift) & M32)) & M32   # key_shift 8: 3-byte key; 5: + 3 bits of the 4th byte
         return bit_set(p, h >> p.shift, gm & 7)
     gm = (window | p.fold) & p.kmask
     h = (gm * p.mult) & M32
@@ -122,12 +123,19 @@ def case_variants(rng, b, n):
     return out
 
 
-def check(pats, **knobs):
+def set_experiment(ac, flags):
+    ab._lib.acg_debug_set_experiment.argtypes = [C.c_void_p, C.c_uint32]
+    assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
+    return ac
+
+
+def check(pats, experiment=0, **knobs):
     b = ab.AhoCorasick.builder().host_only().kind(ab.AhoCorasickKind.DFA)
     for k, v in knobs.items():
         getattr(b, k)(v)
-    ac = b.build(pats)
+    ac = set_experiment(b.build(pats), experiment)
     p = plan_of(ac)
+    assert p.key_shift == (5 if (experiment & 8 and p.stride == 2) else 8)
     t = ac.tables()
     ci = bool(knobs.get("ascii_case_insensitive"))
     if not p.supported:
@@ -144,8 +152,12 @@ def check(pats, **knobs):
             if not p.brute:
                 if p.stride == 2:
                     assert p.k == 4
-                    assert first_stage_hit(p, w0)        # start at an even offset: bytes [0,3)
-                    assert first_stage_hit(p, w0 >> 8)   # start at an odd offset: bytes [1,4) at the next even one
+                    assert first_stage_hit(p, w0)        # start at an even offset: bytes [0,3) (+ the pattern's 4th)
+                    # start at an odd offset: bytes [1,4) at the next even one, followed by the pattern's
+                    # fifth byte -- or by any text if the pattern ends there
+                    tails = [v[4:5]] if len(v) > 4 else [bytes([x]) for x in (0, 0x41, 0x7A, 0x20, 0xFF, 3, 0x35, 0x66)]
+                    for tail in tails:
+                        assert first_stage_hit(p, le32(v[1:4] + tail))
                 else:
                     assert first_stage_hit(p, w0)
                 assert second_stage_hit(p, w0)
@@ -228,3 +240,32 @@ def test_first_stage_pass_rate_is_low_on_random_text():
     wins = txt[:, 0] | (txt[:, 1] << 8) | (txt[:, 2] << 16) | (txt[:, 3] << 24)
     hits = sum(first_stage_hit(p, int(w)) for w in wins)
     assert hits / len(wins) < 0.05
+
+
+@pytest.mark.parametrize("knobs", [dict(), dict(match_kind=ab.MatchKind.LeftmostFirst, ascii_case_insensitive=True),
+                                   dict(match_kind=ab.MatchKind.LeftmostLongest)])
+def test_plan_with_27_bit_first_stage_keys(knobs):
+    """ACG_EXP_KEY27 = 8: the first-stage key also holds the low 3 bits of the window's fourth byte.
+    No false negatives at either alignment, whatever follows a 4-byte pattern; fewer random hits."""
+    for pats in (W.make_patterns(5000, 0xAC5000), W.make_patterns(50, 0xAC0050),
+                 [b"abcd", b"bcde", b"cdef", b"abcdefgh", b"xyzw", b"abcdX", b"abcdY"],
+                 W.make_patterns(700, 11, lo=4, hi=5)):
+        p = check(pats, experiment=8, **knobs)
+        assert p.stride == 2 and p.key_shift == 5
+
+
+def test_27_bit_keys_cut_the_first_stage_pass_rate():
+    pats = W.make_patterns(5000, 0xAC5000)
+    ac = ab.AhoCorasick.builder().host_only().kind(ab.AhoCorasickKind.DFA).build(pats)
+    rng = np.random.default_rng(3)
+    txt = rng.integers(0x20, 0x7F, size=(40000, 4), dtype=np.uint32)
+    wins = txt[:, 0] | (txt[:, 1] << 8) | (txt[:, 2] << 16) | (txt[:, 3] << 24)
+    base = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
+    set_experiment(ac, 8)
+    k27 = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
+    set_experiment(ac, 0)
+    again = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
+    print("first-stage pass rate on random printable text: 24-bit keys %.4f, 27-bit keys %.4f" % (base / len(wins), k27 / len(wins)))
+    # the genuine 3-byte prefix hits (10 000 fingerprints in 95^3) all but disappear; what remains are the
+    # Bloom false positives of a bitmap that also carries the second stage's two bits per 4-gram
+    assert again == base and k27 < base * 0.97

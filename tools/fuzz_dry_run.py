@@ -65,7 +65,12 @@ def one(rng, it):
     bc = rng.random() > 0.15
     b = (ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci).start_kind(start_kind)
          .byte_classes(bc).kind(ab.AhoCorasickKind.DFA))
+    device_fill = rng.random() < 0.4   # dense table filled by dfa_fill_level_kernel (unanchored start kind)
+    if device_fill:
+        b.device_fill(True)
     ac = b.build(pats)
+    experiment = rng.choice([0, 0] + list(range(16)))   # ACG_EXP_* kernel variants (acb200_debug.h)
+    assert ab._lib.acg_debug_set_experiment(ac._h, experiment) == 0
     o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, start_kind=start_kind, byte_classes=bc, kind=O.KIND_DFA)
     if rng.random() < 0.3:
         ab._lib.acg_debug_set_pipeline_chunk(ac._h, rng.choice([4096, 8192, 64 << 10]))
@@ -73,7 +78,7 @@ def one(rng, it):
     hi = rng.randrange(lo, n + 1)
     spans = [(0, n), (lo, hi)]
     ptr = hay.ctypes.data if n else 0
-    ctx = (it, len(pats), n, kind, ci, start_kind, bc)
+    ctx = (it, len(pats), n, kind, ci, start_kind, bc, device_fill, experiment)
     for span in spans:
         for anchored in ([False] if start_kind == 0 else [True] if start_kind == 1 else [False, True]):
             a = ab.Anchored.Yes if anchored else ab.Anchored.No
@@ -118,6 +123,7 @@ def main():
     ab._declare(lib)
     packed._declare(lib)
     lib.acg_debug_set_pipeline_chunk.argtypes = [ctypes.c_void_p, ctypes.c_uint64]
+    lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     ab._lib = packed._lib = lib
     rng = random.Random(args.seed)
     t0, it = time.time(), 0
