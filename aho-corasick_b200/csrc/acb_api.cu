@@ -758,7 +758,8 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   // kernel geometry: narrow / wide as planned; the tall geometry and the paired second stage are
   // opt-in experiments for plans that would otherwise run the narrow stride-2 kernel
   p.geom = pf.wide ? 1 : ((pf.stride == 2 && (a->experiment & ACG_EXP_TALL)) ? 2 : 0);
-  p.pair = (pf.stride == 2 && !pf.wide && (a->experiment & ACG_EXP_PAIR)) ? 1 : 0;
+  p.pair = 0;
+  if (pf.stride == 2 && !pf.wide) p.pair = (a->experiment & ACG_EXP_LOCAL2) ? 2 : ((a->experiment & ACG_EXP_PAIR) ? 1 : 0);
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
@@ -1427,7 +1428,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT | ACG_EXP_KEY27))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT | ACG_EXP_KEY27 | ACG_EXP_LOCAL2))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;

@@ -115,7 +115,8 @@ struct PrefilterLaunch {
                                 // 3-byte fingerprints of pattern bytes [0,3) and [1,4) (k == 4 only)
   uint16_t geom;                // stride 2 only: 0 narrow, 1 wide (2 KiB tiles / 512 threads / 16 KiB bitmap: rare
                                 // first-stage hits), 2 tall (2 KiB tiles / 640 threads / 128 KiB bitmap; experiment)
-  uint16_t pair;                // stride 2, narrow / tall: paired second stage (experiment); shares a word with
+  uint16_t pair;                // stride 2, narrow / tall: second-stage organisation -- 0 compacted items, 1 paired,
+                                // 2 lane-local (1, 2: experiments); shares a word with
                                 // `geom` so that the layout (and the SASS of the measured kernels) stays as it was
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)

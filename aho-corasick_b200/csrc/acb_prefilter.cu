@@ -208,15 +208,22 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-// PAIR (experiment, stride 2 only): the second stage gives each lane one first-stage hit and lets
-// it test both start offsets the hit owns, instead of one (hit, start) item per lane -- half the
-// second-stage passes per step.
-template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, bool PAIR = false>
+// Second-stage organisation S2 (1 and 2 are experiments, stride 2 only):
+//   0  compacted (hit, start offset) items, one per lane: ballot prefix sum, per-warp slot queue
+//   1  PAIR: compacted hits, one per lane; the lane tests both start offsets the hit owns -- half
+//      the second-stage passes per step
+//   2  LOCAL: no compaction at all -- every lane walks its own hit mask, both start offsets per
+//      hit; the warp loops while any lane has a hit left (about twice per step on cfg 2).  Drops
+//      the ballot prefix sum, the slot queue and its decode; pays with idle lanes.
+enum : int { kS2Compact = 0, kS2Pair = 1, kS2Local = 2 };
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact>
 __global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
-  static_assert(!PAIR || (STRIDE == 2 && !DENSE), "the paired second stage belongs to the stride-2 first stage");
+  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the paired / lane-local second stages belong to the stride-2 first stage");
+  constexpr bool PAIR = S2 == kS2Pair;
+  constexpr bool LOCAL = S2 == kS2Local;
   constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
   constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
   constexpr int kPfTile = PfGeom<GEOM>::kTile;
@@ -436,12 +443,14 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     const uint32_t lt = (1u << lane) - 1;
     constexpr int kPlanes = DENSE ? 6 : 3;  // dense sets: up to 32 hits per lane are normal
     uint32_t slot = 0, total = 0;
+    constexpr int kSumPlanes = LOCAL ? 0 : kPlanes;  // the lane-local second stage needs no slots
 #pragma unroll
-    for (int b = 0; b < kPlanes; ++b) {
+    for (int b = 0; b < kSumPlanes; ++b) {
       const uint32_t bl = __ballot_sync(0xffffffffu, (cnt >> b) & 1u);
       slot += __popc(bl & lt) << b;
       total += __popc(bl) << b;
     }
+    if constexpr (LOCAL) total = __any_sync(0xffffffffu, mask != 0) ? 1u : 0u;  // only "is there anything to do"
     if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
       // the very first probe of the region has no start before it
@@ -459,6 +468,57 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         }
         cand_total += __reduce_add_sync(0xffffffffu, nver);
       } else {
+        // PAIR / LOCAL: both start offsets of the hit at tile offset e (even), tested by one lane
+        auto survives = [&](uint32_t gram) -> bool {
+          if (MASKED) gram = (gram | fold) & kmask;
+          return bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
+        };
+        auto test_hit = [&](uint32_t e, bool& pass0, bool& pass1) {
+          if (e == 0) {
+            // the odd start lies one byte before the tile (at most one hit per step): no second
+            // probe, the verifier decides -- unless it would fall before the filter region
+            pass0 = survives(ptx::lds32(tile_a));
+            pass1 = !region_first;
+          } else {
+            // e is even: the bytes e-1 .. e+3 lie in the two words around (e-1) & ~3
+            const uint32_t o1 = e - 1;
+            const uint32_t sa = tile_a + (o1 & ~3u);
+            const uint32_t lo = ptx::lds32(sa), hi = ptx::lds32(sa + 4);
+            const uint32_t sh = (o1 & 3u) * 8;  // 8 or 24
+            pass1 = survives(__funnelshift_r(lo, hi, sh));
+            pass0 = survives(__funnelshift_rc(lo, hi, sh + 8));  // shift 32 (e word aligned) -> hi
+          }
+        };
+        auto queue_pair = [&](uint32_t wrel, uint32_t e, bool pass0, bool pass1) {  // warp-uniform call
+          if constexpr (!DENSE) {
+            const uint32_t bal0 = __ballot_sync(0xffffffffu, pass0);
+            const uint32_t bal1 = __ballot_sync(0xffffffffu, pass1);
+            if (bal0) {
+              if (pass0) q2[q2len + __popc(bal0 & lt)] = wrel + e;
+              q2len += __popc(bal0);
+              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            }
+            if (bal1) {
+              if (pass1) q2[q2len + __popc(bal1 & lt)] = wrel + e - 1;
+              q2len += __popc(bal1);
+              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+            }
+          }
+        };
+        if constexpr (LOCAL) {
+          // every lane walks its own hits; the warp iterates while any lane has one left
+          while (__any_sync(0xffffffffu, mask != 0)) {
+            bool pass0 = false, pass1 = false;
+            uint32_t e = 0;
+            if (mask) {
+              const uint32_t b = (uint32_t)__ffs(mask) - 1;
+              mask &= mask - 1;
+              e = hit_offset(b, (uint32_t)lane);
+              test_hit(e, pass0, pass1);
+            }
+            queue_pair((uint32_t)(wbase - chunk_lo) + rel_bias, e, pass0, pass1);
+          }
+        } else {
         // hit t of the step is recorded as (lane << 5 | bit); the consumer decodes the offset
         {
           uint16_t* sp = slots + slot;
@@ -477,10 +537,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         const uint32_t n_items = total * STRIDE;
         if constexpr (PAIR) {
           // one hit per lane; the lane tests the probed (even) offset e and the odd offset e-1
-          auto survives = [&](uint32_t gram) -> bool {
-            if (MASKED) gram = (gram | fold) & kmask;
-            return bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
-          };
           for (uint32_t base = 0; base < total; base += 32) {
             const uint32_t w = base + lane;
             bool pass0 = false, pass1 = false;
@@ -488,33 +544,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
             if (w < total) {
               const uint32_t raw = slots[w];
               e = hit_offset(raw & 31u, raw >> 5);
-              if (e == 0) {
-                // the odd start lies one byte before the tile (at most one hit per step): no second
-                // probe, the verifier decides -- unless it would fall before the filter region
-                pass0 = survives(ptx::lds32(tile_a));
-                pass1 = !region_first;
-              } else {
-                // e is even: the bytes e-1 .. e+3 lie in the two words around (e-1) & ~3
-                const uint32_t o1 = e - 1;
-                const uint32_t sa = tile_a + (o1 & ~3u);
-                const uint32_t lo = ptx::lds32(sa), hi = ptx::lds32(sa + 4);
-                const uint32_t sh = (o1 & 3u) * 8;  // 8 or 24
-                pass1 = survives(__funnelshift_r(lo, hi, sh));
-                pass0 = survives(__funnelshift_rc(lo, hi, sh + 8));  // shift 32 (e word aligned) -> hi
-              }
+              test_hit(e, pass0, pass1);
             }
-            const uint32_t bal0 = __ballot_sync(0xffffffffu, pass0);
-            const uint32_t bal1 = __ballot_sync(0xffffffffu, pass1);
-            if (bal0) {
-              if (pass0) q2[q2len + __popc(bal0 & lt)] = wrel + e;
-              q2len += __popc(bal0);
-              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
-            }
-            if (bal1) {
-              if (pass1) q2[q2len + __popc(bal1 & lt)] = wrel + e - 1;
-              q2len += __popc(bal1);
-              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
-            }
+            queue_pair(wrel, e, pass0, pass1);
           }
         } else
         for (uint32_t base = 0; base < n_items; base += 32) {
@@ -552,6 +584,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
             if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
           }
         }
+        }  // !LOCAL
       }
     }
     __syncwarp();  // every lane is done with this stage: refill it with the tile two steps ahead
@@ -612,7 +645,8 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const bool dense = p.dense != 0;
   const int geom = p.stride == 2 ? p.geom : kGeomNarrow;
   if (geom < kGeomNarrow || geom > kGeomTall) return cudaErrorInvalidValue;
-  const bool pair = p.stride == 2 && p.pair && geom != kGeomWide;
+  const int s2 = (p.stride == 2 && geom != kGeomWide) ? p.pair : kS2Compact;  // second-stage organisation
+  if (s2 < kS2Compact || s2 > kS2Local) return cudaErrorInvalidValue;
   const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
@@ -630,19 +664,21 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
   // [mode][masked][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
-  // 4 stride 2 tall, 5 stride 2 narrow + paired second stage, 6 stride 2 tall + paired second stage
-  // (stride 2 is never combined with the dense variant; 4-6 are experiments, acb200_debug.h)
+  // 4 stride 2 tall, 5 / 6 narrow / tall + paired second stage, 7 / 8 narrow / tall + lane-local
+  // second stage (stride 2 is never combined with the dense variant; 4-8 are experiments, acb200_debug.h)
 #define ACB_PF_ROW(M, K)                                                                              \
   {prefilter_kernel<M, K, false, 1, kGeomNarrow>, prefilter_kernel<M, K, true, 1, kGeomNarrow>,          \
    prefilter_kernel<M, K, false, 2, kGeomNarrow>, prefilter_kernel<M, K, false, 2, kGeomWide>,           \
-   prefilter_kernel<M, K, false, 2, kGeomTall>, prefilter_kernel<M, K, false, 2, kGeomNarrow, true>,     \
-   prefilter_kernel<M, K, false, 2, kGeomTall, true>}
-  static const KernT table[2][2][7] = {{ACB_PF_ROW(0, false), ACB_PF_ROW(0, true)},
+   prefilter_kernel<M, K, false, 2, kGeomTall>, prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Pair>,  \
+   prefilter_kernel<M, K, false, 2, kGeomTall, kS2Pair>, prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Local>, \
+   prefilter_kernel<M, K, false, 2, kGeomTall, kS2Local>}
+  static const KernT table[2][2][9] = {{ACB_PF_ROW(0, false), ACB_PF_ROW(0, true)},
                                        {ACB_PF_ROW(1, false), ACB_PF_ROW(1, true)}};
 #undef ACB_PF_ROW
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
   int variant = dense ? 1 : 0;
-  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (geom == kGeomTall ? (pair ? 6 : 4) : (pair ? 5 : 2));
+  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (geom == kGeomTall ? (s2 == kS2Local ? 8 : s2 == kS2Pair ? 6 : 4)
+                                                                            : (s2 == kS2Local ? 7 : s2 == kS2Pair ? 5 : 2));
   KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][variant];
 #ifdef ACB_EMULATE
   if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d threads %d smem %zu\n", variant, threads, smem);

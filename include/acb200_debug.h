@@ -48,6 +48,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 #define ACG_EXP_PAIR 2u /* second stage: one first-stage hit per lane, both of its start offsets tested by that lane */
 #define ACG_EXP_WALK_HOT 4u /* walk engine (K1): rows of the start and depth-1 states in shared memory, flagged table copy */
 #define ACG_EXP_KEY27 8u /* stride-2 first stage keyed by 27 bits (3 bytes + low 3 bits of the fourth): rebuilds the bitmap */
+#define ACG_EXP_LOCAL2 16u /* second stage without compaction: every lane walks its own hits (overrides ACG_EXP_PAIR) */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

@@ -252,14 +252,14 @@ def test_unselective_steps_verify_in_place(kind):
 
 
 # ---- kernel variants awaiting a measurement (include/acb200_debug.h: ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2,
-# ACG_EXP_WALK_HOT = 4, ACG_EXP_KEY27 = 8)
+# ACG_EXP_WALK_HOT = 4, ACG_EXP_KEY27 = 8, ACG_EXP_LOCAL2 = 16)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
     return ac
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 8, 10, 11])
+@pytest.mark.parametrize("flags", [1, 2, 3, 8, 10, 11, 16, 17, 25])
 @pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
 def test_experimental_variants_match_the_oracle(name, flags):
     """The tall geometry and the paired second stage on the cfg 2 / cfg 3 pattern sets: overlapping,
@@ -286,7 +286,7 @@ def test_experimental_variants_match_the_oracle(name, flags):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11])
+@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11, 16, 17, 24])
 def test_experimental_variants_at_every_alignment(flags):
     """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
     paired second stage, the 2 KiB tiles of the tall geometry) at 18 pointer phases x 8 span ends."""
@@ -322,7 +322,7 @@ def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("flags", [1, 2, 3, 16, 17])
 def test_experimental_variants_unselective_steps(flags):
     pats = [b"abab", b"baba", b"ababab"] + W.make_patterns(5000, 0xAC5000)
     ac = set_experiment(build(pats, 0), flags)

@@ -21,7 +21,7 @@ def set_experiment(ac, flags):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11])
+@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11, 16, 17, 25])
 @pytest.mark.parametrize("cfg,kind,ci", [("cfg2", 0, False), ("cfg3", 1, True)])
 def test_experimental_prefilter_variants(cfg, kind, ci, flags):
     import torch

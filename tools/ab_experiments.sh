@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of the prefilter-kernel variants that were written without a GPU (include/acb200_debug.h:
-# ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2, ACG_EXP_KEY27 = 8; ACG_EXP_WALK_HOT = 4 further down) against the measured default, on the bench workloads whose
+# ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2, ACG_EXP_KEY27 = 8, ACG_EXP_LOCAL2 = 16; ACG_EXP_WALK_HOT = 4 further down) against the measured default, on the bench workloads whose
 # plan they apply to (stride-2 first stage with the 128 KiB bitmap: cfg2, cfg3).
 # usage (through gpurun): bash tools/ab_experiments.sh [tag]
 tag=${1:-ab}
@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_zzz_experiments.py -x -q > gpurun_out/pytest_${tag}_experiments.log 2>&1
 tail -2 gpurun_out/pytest_${tag}_experiments.log
 for cfg in cfg2 cfg3; do
-  for exp in 0 1 2 3 8 10 11; do
+  for exp in 0 1 2 3 8 16 17 24 25 11; do
     out=gpurun_out/bench_${tag}_${cfg}_exp${exp}.json
     timeout 600 python bench.py --workload $cfg --experiment $exp --no-cpu-baseline --no-e2e --steps 10 > $out 2> ${out%.json}.err
     python - <<PY

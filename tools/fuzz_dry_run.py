@@ -69,7 +69,7 @@ def one(rng, it):
     if device_fill:
         b.device_fill(True)
     ac = b.build(pats)
-    experiment = rng.choice([0, 0] + list(range(16)))   # ACG_EXP_* kernel variants (acb200_debug.h)
+    experiment = rng.choice([0, 0] + list(range(32)))   # ACG_EXP_* kernel variants (acb200_debug.h)
     assert ab._lib.acg_debug_set_experiment(ac._h, experiment) == 0
     o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, start_kind=start_kind, byte_classes=bc, kind=O.KIND_DFA)
     if rng.random() < 0.3:
