@@ -475,6 +475,15 @@ int fill_table_on_device(acg_dfa* a) {
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   release();
   if (e != cudaSuccess) { cudaGetLastError(); return ACG_E_CUDA; }
+  // the per-row arrays have served their purpose; `shallow` stays (the plan can be re-derived)
+  acb::DenseFillPlan& fp = h.fill;
+  std::vector<uint32_t>().swap(fp.level_off);
+  std::vector<uint32_t>().swap(fp.row);
+  std::vector<uint32_t>().swap(fp.inherit_row);
+  std::vector<uint32_t>().swap(fp.fill_id);
+  std::vector<uint32_t>().swap(fp.edge_off);
+  std::vector<uint8_t>().swap(fp.edge_class);
+  std::vector<uint32_t>().swap(fp.edge_to);
   return ACG_OK;
 }
 

@@ -440,6 +440,21 @@ def test_device_fill_on_the_baseline_pattern_sets():
         _same_tables(host, dev, n)
 
 
+def test_device_fill_with_a_rebuilt_plan():
+    """ACG_EXP_KEY27 re-derives the prefilter plan after the build: on a device-filled handle that runs
+    off the builder's shallow trie edges (the fill plan's per-row arrays are gone by then)."""
+    pats, hay = workload(5000, 0xAC5000, 192 << 10)
+    host = set_experiment(_builder(0, False).build(pats), 8)
+    dev = set_experiment(_builder(0, False, device_fill=True).build(pats), 8)
+    assert plan_of(dev).key_shift == 5
+    _same_plan(host, dev, "key27")
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "key27 dev fill")
+    set_experiment(dev, 0)
+    _same_plan(set_experiment(host, 0), dev, "back to 24-bit keys")
+    eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "default dev fill")
+
+
 def test_device_fill_falls_back_for_other_start_kinds():
     pats = [b"abcd", b"bcd", b"cd", b"b"]
     for sk in (ab.StartKind.Both, ab.StartKind.Anchored):
