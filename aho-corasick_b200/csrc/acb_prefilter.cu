@@ -37,8 +37,10 @@ namespace {
 // full 128 KiB bitmap -- 640 threads, one CTA per SM (the most warps whose rings fit beside the
 // bitmap): the wide geometry's amortisation for pattern sets that need the large bitmap.
 enum : int { kGeomNarrow = 0, kGeomWide = 1, kGeomTall = 2 };
-template <int GEOM> struct PfGeom {
-  static constexpr int kThreads = GEOM == kGeomNarrow ? 1024 : (GEOM == kGeomWide ? 512 : 640);
+// NOSLOTS: the lane-local second stage keeps no per-warp slot queue, which lets the tall geometry
+// fit two more warps beside the bitmap (22 x 4 528 B + 128 KiB <= 227 KB).
+template <int GEOM, bool NOSLOTS = false> struct PfGeom {
+  static constexpr int kThreads = GEOM == kGeomNarrow ? 1024 : (GEOM == kGeomWide ? 512 : (NOSLOTS ? 704 : 640));
   static constexpr int kWarps = kThreads / 32;
   static constexpr int kGroups = GEOM == kGeomNarrow ? 2 : 4;  // 16-byte groups per lane and step
   static constexpr int kTile = kGroups * 512;           // haystack bytes per warp step
@@ -217,19 +219,20 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 //      the ballot prefix sum, the slot queue and its decode; pays with idle lanes.
 enum : int { kS2Compact = 0, kS2Pair = 1, kS2Local = 2 };
 template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact>
-__global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
+__global__ void __launch_bounds__(PfGeom<GEOM, S2 == 2>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
   static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the paired / lane-local second stages belong to the stride-2 first stage");
   constexpr bool PAIR = S2 == kS2Pair;
   constexpr bool LOCAL = S2 == kS2Local;
-  constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
-  constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
+  constexpr int kPfThreads = PfGeom<GEOM, S2 == 2>::kThreads;
+  constexpr int kPfWarps = PfGeom<GEOM, S2 == 2>::kWarps;
   constexpr int kPfTile = PfGeom<GEOM>::kTile;
   constexpr int kPfStageBytes = PfGeom<GEOM>::kStageBytes;
   constexpr int kGroups = PfGeom<GEOM>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
+  constexpr int kSlotsAlloc = LOCAL ? 0 : kPfSlots;  // the lane-local second stage keeps no slot queue
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   constexpr uint32_t kBloomShift = PfBloom<GEOM>::kShift;
   using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
@@ -237,8 +240,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
   uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
   Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_bars + kPfWarps * kPfStages);  // [kPfWarps][kPfQ2]
-  uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kPfSlots]
-  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kPfSlots);
+  uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kSlotsAlloc]
+  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kSlotsAlloc);
   __shared__ uint8_t s_cls[256];
 
   const int tid = threadIdx.x;
@@ -294,7 +297,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   unsigned char* ring = s_ring + warp * (kPfStages * kPfStageBytes);
   uint64_t* bars = s_bars + warp * kPfStages;
-  uint16_t* slots = s_slots + warp * kPfSlots;
+  uint16_t* slots = s_slots + warp * kSlotsAlloc;
   Q2Entry* q2 = s_queue2 + warp * kPfQ2;
   uint32_t q2len = 0;  // warp-uniform
 
@@ -650,7 +653,8 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  static const int kThreadsOf[3] = {PfGeom<0>::kThreads, PfGeom<1>::kThreads, PfGeom<2>::kThreads};
+  const int kThreadsOf[3] = {PfGeom<0>::kThreads, PfGeom<1>::kThreads,
+                             s2 == kS2Local ? PfGeom<2, true>::kThreads : PfGeom<2>::kThreads};
   static const int kStageOf[3] = {PfGeom<0>::kStageBytes, PfGeom<1>::kStageBytes, PfGeom<2>::kStageBytes};
   static const int kTileOf[3] = {PfGeom<0>::kTile, PfGeom<1>::kTile, PfGeom<2>::kTile};
   const int threads = kThreadsOf[geom];
@@ -658,8 +662,8 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int stage_bytes = kStageOf[geom];
   const int tile = kTileOf[geom];
   const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
-  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 + q2_bytes +
-                                       (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2) + bitmap_bytes;
+  const int slot_bytes = s2 == kS2Local ? 0 : (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2;
+  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 + q2_bytes + slot_bytes) + bitmap_bytes;
   if (smem > 227 * 1024 - 256) return cudaErrorInvalidValue;  // 256 B of static shared memory (byte classes)
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);

@@ -46,7 +46,8 @@ def test_prefilter_kernel_register_budget():
         # 65 536 registers per SM: 1 024 threads (narrow) or 2 x 512 threads (wide) => 64 per thread;
         # the tall geometry (template argument GEOM = 2: ...ELi2ELi2E...) runs 640 threads => 102
         tall = re.search(r"prefilter_kernelILi\dELb\dELb\dELi2ELi2E", name) is not None
-        assert v["regs"] <= (102 if tall else 64), (name, v["regs"])
+        tall_local = re.search(r"prefilter_kernelILi\dELb\dELb\dELi2ELi2ELi2E", name) is not None   # 704 threads
+        assert v["regs"] <= (93 if tall_local else 102 if tall else 64), (name, v["regs"])
 
 
 def test_walk_and_helper_kernels_do_not_spill():
