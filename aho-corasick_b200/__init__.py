@@ -150,6 +150,19 @@ def _declare(lib):
     lib.acg_find_overlapping_devout.argtypes = [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _u64,
                                                  C.POINTER(_u64), C.POINTER(C.c_float)]
     lib.acg_device_count.argtypes = []
+    # multi-GPU (include/acb200.h)
+    lib.acg_comm_unique_id.argtypes = [_vp]
+    lib.acg_comm_init.argtypes = [_vp, _i, _i, C.POINTER(_vp)]
+    lib.acg_comm_free.argtypes = [_vp]
+    lib.acg_comm_free.restype = None
+    lib.acg_comm_rank.argtypes = [_vp]
+    lib.acg_comm_size.argtypes = [_vp]
+    lib.acg_comm_transport.argtypes = [_vp]
+    lib.acg_shard_plan.argtypes = [_u64, _u64, _i, _i, _u64, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]
+    lib.acg_find_overlapping_sharded.argtypes = [_vp, _vp, _vp, _i, _u64, _u64, _u64, _u64, C.POINTER(_vp),
+                                                  C.POINTER(_u64), _vp, _u64, _vp]
+    lib.acg_comm_fetch.argtypes = [_vp, _vp, _u64, C.POINTER(_u64)]
+    lib.acg_comm_checksum.argtypes = [_vp, C.POINTER(_u64), C.POINTER(_u64)]
 
 
 _declare(_lib)

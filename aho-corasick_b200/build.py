@@ -7,8 +7,8 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libacb200.so"
-SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_prefilter.cu", "acb_api.cu"]
-HEADERS = ["acb_build.hpp", "acb_device.cuh", "acb_ptx.cuh", "../../include/acb200.h", "../../include/acb200_debug.h"]
+SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_prefilter.cu", "acb_comm.cu", "acb_api.cu"]
+HEADERS = ["acb_build.hpp", "acb_comm.hpp", "acb_device.cuh", "acb_ptx.cuh", "../../include/acb200.h", "../../include/acb200_debug.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "--expt-relaxed-constexpr",

@@ -12,6 +12,7 @@
 #include "../../include/acb200.h"
 #include "../../include/acb200_debug.h"
 #include "acb_build.hpp"
+#include "acb_comm.hpp"
 #include "acb_device.cuh"
 
 using acb::DfaDev;
@@ -98,11 +99,6 @@ struct acg_dfa {
   int engine_override = ACG_ENGINE_AUTO;
   uint64_t pipeline_chunk = 64ull << 20;  // H2D chunk of the pipelined host path (acg_debug_set_pipeline_chunk)
   uint32_t experiment = 0;                // ACG_EXP_* kernel variants awaiting measurement (acg_debug_set_experiment)
-  // hot-row walk (ACG_EXP_WALK_HOT): flagged table copy + staged row list, built on first use
-  mutable uint32_t* d_trans_hot = nullptr;
-  mutable uint32_t* d_hot_ids = nullptr;
-  mutable uint32_t n_hot = 0, start_hot = 0;
-  mutable bool hot_tried = false;
   mutable std::mutex mu;
   mutable Workspace ws;
   mutable acg_stats stats{};
@@ -630,44 +626,6 @@ struct TupleResult {
   int sorted_buf = 0;
 };
 
-// Hot-row walk (experiment): stage the rows of the unanchored start state and of the depth-1
-// states (in row order, as many as fit in kWalkHotSmemMax) unless they are match states, and
-// derive the flagged copy of the table on the device.  Leaves n_hot == 0 when nothing qualifies.
-int ensure_hot_rows(const acg_dfa* a) {
-  if (a->hot_tried) return ACG_OK;
-  a->hot_tried = true;
-  const HostDfa& h = a->h;
-  const uint32_t s2 = h.stride2;
-  if (h.start_unanchored_id == 0 || (h.trans_len >> 31) != 0) return ACG_OK;
-  const size_t max_rows = acb::kWalkHotSmemMax / (size_t(4) << s2);
-  const size_t rows = size_t(h.state_len);
-  std::vector<uint32_t> ids;
-  std::vector<uint16_t> hot_of_row(rows, 0);
-  auto stage = [&](uint32_t row) {
-    const uint32_t id = row << s2;
-    if (id <= h.max_match_id || ids.size() >= max_rows || ids.size() >= 0xFFFE || hot_of_row[row]) return;
-    ids.push_back(id);
-    hot_of_row[row] = uint16_t(ids.size());
-  };
-  stage(h.start_unanchored_id >> s2);
-  for (size_t r = 2; r < rows && r < a->depth16.size(); ++r)
-    if (a->depth16[r] == 1) stage(uint32_t(r));
-  if (ids.empty()) return ACG_OK;
-  uint16_t* d_hot_of_row = nullptr;
-  CK(cudaMalloc(&a->d_trans_hot, size_t(h.trans_len) * 4));
-  CK(cudaMalloc(&a->d_hot_ids, ids.size() * 4));
-  CK(cudaMalloc(&d_hot_of_row, rows * 2));
-  CK(cudaMemcpyAsync(a->d_hot_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, a->ws.stream));
-  CK(cudaMemcpyAsync(d_hot_of_row, hot_of_row.data(), rows * 2, cudaMemcpyHostToDevice, a->ws.stream));
-  CK(acb::launch_flag_table(a->d_trans, a->d_trans_hot, h.trans_len, d_hot_of_row, s2, a->ws.stream));
-  CK(cudaStreamSynchronize(a->ws.stream));
-  cudaFree(d_hot_of_row);
-  const uint32_t start_slot = hot_of_row[h.start_unanchored_id >> s2];
-  a->start_hot = start_slot ? (acb::kWalkHotFlag | ((start_slot - 1) << s2)) : h.start_unanchored_id;
-  a->n_hot = uint32_t(ids.size());
-  return ACG_OK;
-}
-
 // K1 + K4 on a device-resident haystack; leaves `n` ordered tuples in
 // ws.d_keys[sorted_buf] / ws.d_pids[sorted_buf].
 int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start,
@@ -686,20 +644,11 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   // phase of the first shard; the kernel handles the unaligned head per lane.
   const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
   uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 256));
-  const bool hot = (a->experiment & ACG_EXP_WALK_HOT) != 0;
-  if (hot) {
-    int rc = ensure_hot_rows(a);
-    if (rc) return rc;
-  }
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
     if (rc) return rc;
     CK(cudaMemsetAsync(w.d_counter, 0, 8, w.stream));
     acb::WalkLaunch p;
-    p.trans_hot = hot ? a->d_trans_hot : nullptr;
-    p.hot_ids = hot ? a->d_hot_ids : nullptr;
-    p.n_hot = hot ? a->n_hot : 0;
-    p.start_hot = a->start_hot;
     p.hay = d_hay;
     p.span_start = span_start;
     p.span_end = span_end;
@@ -764,11 +713,10 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.log_bits = pf.log_bits;
   p.k = pf.k;
   p.stride = pf.stride;
-  // kernel geometry: narrow / wide as planned; the tall geometry and the paired second stage are
-  // opt-in experiments for plans that would otherwise run the narrow stride-2 kernel
-  p.geom = pf.wide ? 1 : ((pf.stride == 2 && (a->experiment & ACG_EXP_TALL)) ? 2 : 0);
-  p.pair = 0;
-  if (pf.stride == 2 && !pf.wide) p.pair = (a->experiment & ACG_EXP_LOCAL2) ? 2 : ((a->experiment & ACG_EXP_PAIR) ? 1 : 0);
+  // kernel geometry as planned; second-stage organisation and tile distribution: see prefilter_kernel
+  p.geom = pf.wide ? 1 : 0;
+  p.pair = (pf.stride == 2 && !pf.wide && (a->experiment & ACG_EXP_LOCAL2)) ? 2 : 0;
+  p.dyn = (a->experiment & ACG_EXP_DYN) ? 1 : 0;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
@@ -1147,6 +1095,145 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   return drain_tuples(a, r, span_start, out, cap, n_out, fnv);
 }
 
+// acg_shard_plan: the slice arithmetic shared by every rank.  Interior
+// boundaries are rounded down to 64 bytes relative to the span start so device loads stay vectorisable.
+void shard_plan(uint64_t span_start, uint64_t span_end, int nranks, int rank, uint64_t max_pattern_len,
+                uint64_t* own_lo, uint64_t* own_hi, uint64_t* read_lo) {
+  const uint64_t n = span_end - span_start;
+  const uint64_t back = max_pattern_len ? max_pattern_len - 1 : 0;
+  auto cut = [&](int g) -> uint64_t {
+    if (g <= 0) return span_start;
+    if (g >= nranks) return span_end;
+    const unsigned __int128 q = (unsigned __int128)n * (unsigned)g / (unsigned)nranks;
+    return span_start + (uint64_t(q) & ~63ull);
+  };
+  *own_lo = cut(rank);
+  *own_hi = cut(rank + 1);
+  *read_lo = (*own_lo - span_start > back) ? *own_lo - back : span_start;
+}
+
+// The sharded overlapping search of one rank: scan the slice, keep the matches this rank owns,
+// learn the global offsets, and store the records into rank 0's buffer.
+int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
+                 uint64_t hay_off, uint64_t span_start, uint64_t span_end, const acg_match** d_matches,
+                 uint64_t* n_total, acg_match* h_out, uint64_t h_cap, acg_shard_stats* st) {
+  if (!a || !c || !n_total) return ACG_E_INVALID_ARG;
+  *n_total = 0;
+  if (d_matches) *d_matches = nullptr;
+  if (st) *st = acg_shard_stats{};
+  // checks that do not depend on the rank come first, so that all ranks fail together
+  if (span_start > span_end) return ACG_E_INVALID_SPAN;
+  if (a->h.match_kind != ACG_STANDARD) return ACG_E_UNSUPPORTED_OVERLAPPING;
+  int rc = check_anchored(a->h.start_kind, 0);
+  if (rc) return rc;
+  if ((rc = check_start(a->h, 0))) return rc;
+  if (!a->on_device) return ACG_E_NO_DEVICE;
+  if (a->device != c->device) return ACG_E_INVALID_ARG;
+  uint64_t own_lo, own_hi, read_lo;
+  shard_plan(span_start, span_end, c->nranks, c->rank, a->h.max_pattern_len, &own_lo, &own_hi, &read_lo);
+  // an empty slice (more ranks than 64-byte blocks) still takes part in the collectives
+  const bool covered = own_hi == own_lo || (read_lo >= hay_off && own_hi <= hay_off + hay_len);
+  // the local scan, in local offsets: span [read_lo, own_hi) - hay_off
+  TupleResult r;
+  uint64_t first = 0;
+  uint64_t lspan_s = 0;
+  {
+    std::lock_guard<std::mutex> lock(a->mu);
+    DeviceGuard guard(a->device);
+    a->stats = acg_stats{};
+    if (covered && own_hi > own_lo) {
+      lspan_s = read_lo - hay_off;
+      const uint64_t lspan_e = own_hi - hay_off;
+      int engine = a->engine_override;
+      if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) engine = ACG_ENGINE_AUTO;
+      if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
+        engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
+      a->stats.engine = engine;
+      const uint8_t* d_base = hay;
+      uint64_t readable = hay_len;
+      const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
+      if (!hay_on_device) {
+        rc = stage_host_span(a, hay, lspan_s, lspan_e, &d_base, pipelined);
+        readable = lspan_e + 32;
+      }
+      if (!rc) {
+        if (engine == ACG_ENGINE_PREFILTER)
+          rc = run_prefilter(a, d_base, readable, lspan_s, lspan_e, 0, &r, pipelined ? hay : nullptr);
+        else rc = run_walk_overlapping(a, d_base, lspan_s, lspan_e, &r);
+      }
+      if (!rc && r.n && own_lo > read_lo) {
+        // ends <= own_lo belong to the previous rank: first key with end > own_lo
+        Workspace& w = a->ws;
+        const uint64_t bound_key = (own_lo - read_lo + 1) << acb::kTieBits;
+        cudaError_t e = acb::launch_lower_bound(w.d_keys[r.sorted_buf], r.n, bound_key, w.d_counter, w.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+        if (e != cudaSuccess) { cudaGetLastError(); rc = ACG_E_CUDA; }
+        else first = *w.h_counter;
+      }
+    }
+    if (!covered) rc = ACG_E_INVALID_SPAN;
+    // a failed rank still joins the exchange (with the error flag in the top bit) so that nobody hangs
+    const uint64_t mine = rc ? 0 : r.n - first;
+    DeviceGuard cguard(c->device);
+    cudaEventRecord(c->ev0, c->stream);
+    uint64_t total = 0, my_off = 0;
+    int rc2 = acb::comm_exchange_counts(c, mine | (rc ? (1ull << 63) : 0), &total, &my_off);
+    if (rc2) return rc ? rc : rc2;
+    bool any_failed = false;
+    total = 0; my_off = 0;
+    for (int g = 0; g < c->nranks; ++g) {
+      if (c->counts[size_t(g)] >> 63) any_failed = true;
+      c->counts[size_t(g)] &= ~(1ull << 63);
+      if (g < c->rank) my_off += c->counts[size_t(g)];
+      total += c->counts[size_t(g)];
+    }
+    if (any_failed) return rc ? rc : ACG_E_CUDA;  // some other rank failed: nothing was gathered
+    if ((rc = acb::comm_ensure_recv(c, total))) return rc;
+    uint8_t* target = nullptr;
+    if ((rc = acb::comm_record_target(c, my_off, mine, &target))) return rc;
+    if (mine) {
+      Workspace& w = a->ws;
+      acb::ExpandLaunch e;
+      e.keys = w.d_keys[r.sorted_buf];
+      e.pids = w.d_pids[r.sorted_buf];
+      e.pattern_lens = a->d_plens;
+      e.n = r.n;
+      e.first = first;
+      e.span_start = lspan_s;
+      e.offset_add = hay_off;
+      e.out = reinterpret_cast<uint64_t*>(target);
+      CK(acb::launch_expand(e, c->stream));
+    }
+    if ((rc = acb::comm_finish_gather(c, my_off, mine))) return rc;
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float gms = 0;
+    cudaEventElapsedTime(&gms, c->ev0, c->ev1);
+    c->last_gather_ms = gms;
+    a->stats.launches += 3;
+    *n_total = total;
+    if (st) {
+      st->local_matches = mine;
+      st->total_matches = total;
+      st->candidates = a->stats.candidates;
+      st->scan_ms = a->stats.scan_ms;
+      st->order_ms = a->stats.order_ms;
+      st->gather_ms = gms;
+      st->transport = c->transport;
+      st->launches = a->stats.launches;
+    }
+    if (c->rank == 0) {
+      if (d_matches) *d_matches = reinterpret_cast<const acg_match*>(c->recv_own);
+      if (h_out) {
+        if (total > h_cap) return ACG_E_OVERFLOW;
+        if (total) CK(cudaMemcpy(h_out, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+      }
+    }
+  }
+  return ACG_OK;
+}
+
 int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
                    uint64_t span_start, uint64_t span_end, int anchored, acg_match* out,
                    uint64_t cap, uint64_t* n_out, float* kernel_ms) {
@@ -1260,14 +1347,18 @@ static bool desc_is_consistent(const acg_dfa_desc* d) {
   if (d->match_kind > ACG_LEFTMOST_LONGEST || d->start_kind > ACG_START_BOTH) return false;
   for (int b = 0; b < 256; ++b)
     if (d->byte_classes[b] >= d->alphabet_len) return false;
+  // Row 1 is the FAIL sentinel of the noncontiguous NFA (src/dfa.rs:101-108): it is never the target
+  // of a DFA transition nor a start state.  Its id is non-zero and <= max_match_id, so a kernel
+  // would take it for a match state and index match_offsets[row - 2] out of bounds.
   auto id_ok = [&](uint32_t id) { return (id & (stride - 1)) == 0 && id < d->trans_len; };
-  if (!id_ok(d->max_match_id) || !id_ok(d->start_unanchored_id) || !id_ok(d->start_anchored_id) ||
+  auto target_ok = [&](uint32_t id) { return id_ok(id) && id != stride; };
+  if (!id_ok(d->max_match_id) || !target_ok(d->start_unanchored_id) || !target_ok(d->start_anchored_id) ||
       !id_ok(d->max_special_id))
     return false;
   const uint64_t max_match_row = d->max_match_id >> d->stride2;
   if (max_match_row < 1 || max_match_row >= rows) return false;
   for (uint64_t i = 0; i < d->trans_len; ++i)
-    if (!id_ok(d->trans[i])) return false;
+    if (!target_ok(d->trans[i])) return false;
   const uint64_t nms = max_match_row - 1;  // match rows are 2 ..= max_match_row
   if (d->match_offsets[0] != 0) return false;
   for (uint64_t m = 0; m < nms; ++m)
@@ -1328,7 +1419,6 @@ void acg_dfa_free(acg_dfa* a) {
     if (w.stream) cudaStreamSynchronize(w.stream);
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
     cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_amap);
-    cudaFree(a->d_trans_hot); cudaFree(a->d_hot_ids);
     for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
     cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
     cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);
@@ -1437,7 +1527,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_TALL | ACG_EXP_PAIR | ACG_EXP_WALK_HOT | ACG_EXP_KEY27 | ACG_EXP_LOCAL2))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_KEY27 | ACG_EXP_LOCAL2 | ACG_EXP_DYN))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;
@@ -1722,6 +1812,67 @@ int acg_packed_searcher_variant(const acg_packed* s, int* fat, int* mask_len, in
   if (mask_len) *mask_len = s->mask_len;
   if (vector_bytes) *vector_bytes = s->vector_bytes;
   return 1;
+}
+
+// ---- multi-GPU ---------------------------------------------------------
+
+int acg_comm_unique_id(uint8_t id[ACG_COMM_ID_BYTES]) { return acb::comm_unique_id(id); }
+int acg_comm_init(const uint8_t id[ACG_COMM_ID_BYTES], int rank, int nranks, acg_comm** out) {
+  return acb::comm_create(id, rank, nranks, out);
+}
+void acg_comm_free(acg_comm* c) { acb::comm_destroy(c); }
+int acg_comm_rank(const acg_comm* c) { return c ? c->rank : -1; }
+int acg_comm_size(const acg_comm* c) { return c ? c->nranks : 0; }
+int acg_comm_transport(const acg_comm* c) { return c ? c->transport : ACG_TRANSPORT_NONE; }
+
+int acg_shard_plan(uint64_t span_start, uint64_t span_end, int nranks, int rank, uint64_t max_pattern_len,
+                   uint64_t* own_lo, uint64_t* own_hi, uint64_t* read_lo) {
+  if (!own_lo || !own_hi || !read_lo || nranks < 1 || rank < 0 || rank >= nranks || span_start > span_end)
+    return ACG_E_INVALID_ARG;
+  shard_plan(span_start, span_end, nranks, rank, max_pattern_len, own_lo, own_hi, read_lo);
+  return ACG_OK;
+}
+
+int acg_find_overlapping_sharded(const acg_dfa* a, acg_comm* c, const void* hay, int hay_on_device,
+                                 uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
+                                 uint64_t span_end, const acg_match** d_matches, uint64_t* n_total,
+                                 acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats) {
+  return sharded_impl(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
+                      span_start, span_end, d_matches, n_total, h_out, h_cap, stats);
+}
+
+int acg_comm_fetch(const acg_comm* c, acg_match* out, uint64_t cap, uint64_t* n_out) {
+  if (!c || !n_out) return ACG_E_INVALID_ARG;
+  uint64_t total = 0;
+  for (uint64_t v : c->counts) total += v;
+  *n_out = total;
+  if (c->rank != 0) return ACG_E_INVALID_ARG;
+  if (total > cap || (total && !out)) return ACG_E_OVERFLOW;
+  DeviceGuard guard(c->device);
+  if (total) CK(cudaMemcpy(out, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+  return ACG_OK;
+}
+
+int acg_comm_checksum(const acg_comm* c, uint64_t* n_out, uint64_t* fnv) {
+  if (!c || !n_out || !fnv || c->rank != 0) return ACG_E_INVALID_ARG;
+  uint64_t total = 0;
+  for (uint64_t v : c->counts) total += v;
+  *n_out = total;
+  uint64_t hsh = 0xcbf29ce484222325ull;
+  auto mix = [&](uint64_t v) {
+    for (int k = 0; k < 8; ++k) { hsh ^= (v >> (8 * k)) & 0xFF; hsh *= 0x100000001b3ull; }
+  };
+  DeviceGuard guard(c->device);
+  std::vector<acg_match> buf;
+  const uint64_t chunk = 1 << 20;
+  try { buf.resize(size_t(std::min<uint64_t>(chunk, std::max<uint64_t>(total, 1)))); } catch (const std::bad_alloc&) { return ACG_E_NOMEM; }
+  for (uint64_t i = 0; i < total; i += chunk) {
+    const uint64_t m = std::min(chunk, total - i);
+    CK(cudaMemcpy(buf.data(), c->recv_own + i * sizeof(acg_match), size_t(m) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+    for (uint64_t j = 0; j < m; ++j) { mix(buf[j].pid); mix(buf[j].start); mix(buf[j].end); }
+  }
+  *fnv = hsh;
+  return ACG_OK;
 }
 
 const char* acg_strerror(int code) {

@@ -53,17 +53,8 @@ struct WalkLaunch {
   uint32_t* pids;       // [cap]
   unsigned long long* counter;  // total tuples wanted (may exceed cap => overflow)
   uint64_t cap;
-  // hot-row variant (experiment; n_hot == 0: plain walk over DfaDev::trans)
-  const uint32_t* trans_hot;    // flagged copy of the table (see walk_overlapping_kernel)
-  const uint32_t* hot_ids;      // [n_hot] premultiplied ids of the staged rows, slot order
-  uint32_t n_hot;
-  uint32_t start_hot;           // id of the unanchored start state in the flagged table
 };
-constexpr uint32_t kWalkHotFlag = 0x80000000u;
-constexpr size_t kWalkHotSmemMax = 72 * 1024;  // three CTAs per SM
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s);
-cudaError_t launch_flag_table(const uint32_t* in, uint32_t* out, uint64_t n, const uint16_t* hot_of_row,
-                              uint32_t stride2, cudaStream_t s);
 
 // Dense-table construction on the device (the cells of src/dfa.rs:544-593):
 // one launch per BFS level of the trie, one warp per table row: copy the row of the failure state
@@ -114,10 +105,8 @@ struct PrefilterLaunch {
   uint32_t stride;              // 1: probe every offset with the k-gram; 2: probe even offsets with
                                 // 3-byte fingerprints of pattern bytes [0,3) and [1,4) (k == 4 only)
   uint16_t geom;                // stride 2 only: 0 narrow, 1 wide (2 KiB tiles / 512 threads / 16 KiB bitmap: rare
-                                // first-stage hits), 2 tall (2 KiB tiles / 640 threads / 128 KiB bitmap; experiment)
-  uint16_t pair;                // stride 2, narrow / tall: second-stage organisation -- 0 compacted items, 1 paired,
-                                // 2 lane-local (1, 2: experiments); shares a word with
-                                // `geom` so that the layout (and the SASS of the measured kernels) stays as it was
+                                // first-stage hits)
+  uint16_t pair;                // stride 2, narrow: second-stage organisation -- 0 compacted items, 2 lane-local
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult
@@ -136,6 +125,7 @@ struct PrefilterLaunch {
   uint32_t* pids;
   unsigned long long* counter;  // [0] tuples, [1] candidates
   uint64_t cap;
+  uint32_t dyn;                 // 1: the warps of a CTA draw their tiles from a shared counter (see prefilter_kernel)
   uint32_t key_shift;           // stride 2: first-stage hash = window * (mult3 << key_shift).  8: the fourth window
                                 // byte drops out (3-byte keys); 5: its low 3 bits stay in the key (experiment).
                                 // Last member, so that the layout of the measured kernels' parameters is unchanged.

@@ -40,38 +40,17 @@ __device__ __forceinline__ void emit_state_matches(const DfaDev& d, uint32_t sid
 }
 
 constexpr int kWalkThreads = 256;
-constexpr int kWalkHotThreads = 512;  // hot variant: three CTAs of 512 lanes share an SM's shared memory
 
 // One lane per haystack shard.  A lane starts cold (start state) at most
 // max_pattern_len-1 bytes before its shard -- the Aho-Corasick state depends on
 // at most that many trailing bytes -- and only reports matches whose end lies
 // inside its shard, so every end offset is owned by exactly one lane.
-//
-// HOT (experiment, ACG_EXP_WALK_HOT): the rows of the start state and of the depth-1 states --
-// more than half of all transitions on the BASELINE workloads land there -- are staged in shared
-// memory.  The lanes walk a *flagged* copy of the table in which every entry that leads to a
-// staged row is kWalkHotFlag | (slot << stride2): the flag selects between the shared-memory copy
-// and the global table for the next lookup with no extra load.  Staged states are never match
-// states and never DEAD, so a flagged id (> max_match_id as an unsigned number) skips the match
-// branch as it should.
-template <bool HOT>
-__global__ void __launch_bounds__(HOT ? kWalkHotThreads : kWalkThreads)
+// (A variant that staged the start / depth-1 rows in shared memory behind a flagged table copy was
+// measured in r02 and lost: 4.68 ms against 2.75 ms per GiB on cfg 2, profiles/r02a_ab_walk.jsonl.)
+__global__ void __launch_bounds__(kWalkThreads)
 walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   __shared__ uint8_t s_cls[256];
-  ACB_DYNAMIC_SMEM(smem_raw);
-  uint32_t hot_a = 0, cls_a = 0;  // HOT: shared addresses of the staged rows and of the class map behind them
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = d.classes[i];
-  if (HOT) {
-    uint32_t* s_hot = reinterpret_cast<uint32_t*>(smem_raw);  // [n_hot << stride2] then [256] classes
-    const uint32_t stride = 1u << d.stride2, n = p.n_hot << d.stride2;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-      s_hot[i] = p.trans_hot[p.hot_ids[i >> d.stride2] + (i & (stride - 1))];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) smem_raw[n * 4 + i] = d.classes[i];
-    hot_a = ptx::smem_addr(smem_raw);
-    cls_a = hot_a + n * 4;
-    uint32_t unused = 0;
-    ptx::keep_in_registers(hot_a, cls_a, unused);  // not re-derived from the CTA's window base per byte
-  }
   __syncthreads();
 
   const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +61,7 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   const uint64_t back = d.max_pattern_len > 0 ? (uint64_t)d.max_pattern_len - 1 : 0;
   uint64_t pos = (g0 - p.span_start > back) ? g0 - back : p.span_start;
 
-  const uint32_t* __restrict__ trans = HOT ? p.trans_hot : d.trans;
+  const uint32_t* __restrict__ trans = d.trans;
   const uint32_t max_match = d.max_match_id;
   uint32_t sid = d.start_unanchored_id;
 
@@ -90,16 +69,8 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   // the span are reported before the first byte (src/automaton.rs:1456-1464)
   if (seg == 0 && sid != 0 && sid <= max_match)
     emit_state_matches(d, sid, 0, p.keys, p.pids, p.counter, p.cap);
-  if (HOT) sid = p.start_hot;  // the start state's id in the flagged table (itself if it is not staged)
 
-  auto next = [&](uint32_t from, uint32_t byte) -> uint32_t {
-    if (HOT) {
-      const uint32_t c = ptx::lds8(cls_a + byte);
-      if (from & kWalkHotFlag) return ptx::lds32(hot_a + ((from ^ kWalkHotFlag) + c) * 4);
-      return __ldg(trans + from + c);
-    }
-    return __ldg(trans + from + s_cls[byte]);
-  };
+  auto next = [&](uint32_t from, uint32_t byte) -> uint32_t { return __ldg(trans + from + s_cls[byte]); };
 
 #define ACB_STEP(byte_expr)                                                          \
   do {                                                                               \
@@ -133,18 +104,6 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   }
   while (pos < g1) ACB_STEP(hay[pos]);
 #undef ACB_STEP
-}
-
-// Flagged copy of the transition table for the HOT walk: out[i] = hot_of_row[target row] ?
-// kWalkHotFlag | (slot << stride2) : in[i], with hot_of_row[r] = slot + 1 of a staged row, else 0.
-__global__ void flag_table_kernel(const uint32_t* in, uint32_t* out, uint64_t n, const uint16_t* hot_of_row,
-                                  uint32_t stride2) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const uint32_t t = in[i];
-    const uint32_t h = hot_of_row[t >> stride2];
-    out[i] = h ? (kWalkHotFlag | ((h - 1) << stride2)) : t;
-  }
 }
 
 // ---- dense-table construction (one BFS level per launch) -------------------------
@@ -247,16 +206,33 @@ __global__ void seq_find_kernel(DfaDev d, SeqLaunch p) {
   *p.counter = n;
 }
 
-__global__ void expand_kernel(ExpandLaunch e) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e.first + i >= e.n) return;
-  const uint64_t key = e.keys[e.first + i];
-  const uint32_t pid = e.pids[e.first + i];
-  const uint64_t end = e.span_start + (key >> kTieBits) + e.offset_add;
-  // acg_match { u32 pid; u32 pad; u64 start; u64 end; }
-  e.out[i * 3 + 0] = (uint64_t)pid;
-  e.out[i * 3 + 1] = end - e.pattern_lens[pid];
-  e.out[i * 3 + 2] = end;
+// 256 records per CTA, built in shared memory and stored as 16-byte vectors: the target may be
+// another GPU's HBM (peer mapping of rank 0's receive buffer, acb_comm.hpp), where full 128-byte
+// lines per warp store matter more than at home.  Record = acg_match { u32 pid; u32 pad; u64 start; u64 end }.
+__global__ void __launch_bounds__(256) expand_kernel(ExpandLaunch e) {
+  __shared__ uint64_t s_rec[256 * 3];
+  const uint64_t m = e.n - e.first;
+  const uint64_t base = (uint64_t)blockIdx.x * 256;
+  const uint64_t i = base + threadIdx.x;
+  if (i < m) {
+    const uint64_t key = e.keys[e.first + i];
+    const uint32_t pid = e.pids[e.first + i];
+    const uint64_t end = e.span_start + (key >> kTieBits) + e.offset_add;
+    s_rec[threadIdx.x * 3 + 0] = (uint64_t)pid;
+    s_rec[threadIdx.x * 3 + 1] = end - e.pattern_lens[pid];
+    s_rec[threadIdx.x * 3 + 2] = end;
+  }
+  __syncthreads();
+  const uint64_t cnt = m - base < 256 ? m - base : 256;  // records of this CTA
+  uint64_t* dst = e.out + base * 3;
+  const uint32_t words = (uint32_t)cnt * 3;  // 8-byte words; base * 24 is a multiple of 16
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (uint32_t w = threadIdx.x * 2; w + 1 < words; w += 512)
+      *reinterpret_cast<ulonglong2*>(dst + w) = make_ulonglong2(s_rec[w], s_rec[w + 1]);
+    if ((words & 1) && threadIdx.x == 0) dst[words - 1] = s_rec[words - 1];
+  } else {
+    for (uint32_t w = threadIdx.x; w < words; w += 256) dst[w] = s_rec[w];
+  }
 }
 
 // keys are sorted: count the tuples with key < bound_key (single block, strided binary chunks)
@@ -286,20 +262,8 @@ cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_
 }
 
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s) {
-  if (p.n_hot) {
-    const size_t smem = (size_t(p.n_hot) << dfa.stride2) * 4 + 256;  // staged rows + byte classes
-    if (smem > kWalkHotSmemMax + 256 || p.trans_hot == nullptr) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(walk_overlapping_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const uint64_t blocks = (p.n_segs + kWalkHotThreads - 1) / kWalkHotThreads;
-#ifdef ACB_EMULATE
-    if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_walk hot rows %u smem %zu\n", p.n_hot, smem);
-#endif
-    ACB_LAUNCH(walk_overlapping_kernel<true>, (unsigned)blocks, kWalkHotThreads, smem, s, dfa, p);
-    return cudaGetLastError();
-  }
   const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;
-  ACB_LAUNCH(walk_overlapping_kernel<false>, (unsigned)blocks, kWalkThreads, 0, s, dfa, p);
+  ACB_LAUNCH(walk_overlapping_kernel, (unsigned)blocks, kWalkThreads, 0, s, dfa, p);
   return cudaGetLastError();
 }
 
@@ -313,12 +277,6 @@ cudaError_t launch_dfa_fill_level(const FillLaunch& f, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_flag_table(const uint32_t* in, uint32_t* out, uint64_t n, const uint16_t* hot_of_row,
-                              uint32_t stride2, cudaStream_t s) {
-  const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
-  ACB_LAUNCH(flag_table_kernel, blocks ? blocks : 1, 256, 0, s, in, out, n, hot_of_row, stride2);
-  return cudaGetLastError();
-}
 
 cudaError_t launch_seq_find(const DfaDev& dfa, const SeqLaunch& p, cudaStream_t s) {
   ACB_LAUNCH(seq_find_kernel, 1, 32, 0, s, dfa, p);

@@ -33,14 +33,11 @@ namespace {
 // probes), 16 KiB bitmap, two CTAs per SM -- the per-step bookkeeping is spread over twice as many
 // positions, which pays when first-stage hits are rare (few patterns); with frequent hits the 32
 // resident warps of the narrow geometry hide the latency of the second stage and the verifier
-// better.  TALL (2, stride 2 only; experiment, acg_debug_set_experiment): the wide tile with the
-// full 128 KiB bitmap -- 640 threads, one CTA per SM (the most warps whose rings fit beside the
-// bitmap): the wide geometry's amortisation for pattern sets that need the large bitmap.
-enum : int { kGeomNarrow = 0, kGeomWide = 1, kGeomTall = 2 };
-// NOSLOTS: the lane-local second stage keeps no per-warp slot queue, which lets the tall geometry
-// fit two more warps beside the bitmap (22 x 4 528 B + 128 KiB <= 227 KB).
-template <int GEOM, bool NOSLOTS = false> struct PfGeom {
-  static constexpr int kThreads = GEOM == kGeomNarrow ? 1024 : (GEOM == kGeomWide ? 512 : (NOSLOTS ? 704 : 640));
+// better.  (A third geometry -- the 2 KiB tile with the 128 KiB bitmap, 20 warps -- was measured in
+// r02 and lost to the narrow one on cfg 2 and cfg 3: profiles/r02a_ab_*.jsonl.)
+enum : int { kGeomNarrow = 0, kGeomWide = 1 };
+template <int GEOM> struct PfGeom {
+  static constexpr int kThreads = GEOM == kGeomNarrow ? 1024 : 512;
   static constexpr int kWarps = kThreads / 32;
   static constexpr int kGroups = GEOM == kGeomNarrow ? 2 : 4;  // 16-byte groups per lane and step
   static constexpr int kTile = kGroups * 512;           // haystack bytes per warp step
@@ -210,24 +207,27 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-// Second-stage organisation S2 (1 and 2 are experiments, stride 2 only):
+// Second-stage organisation S2 (stride 2 only):
 //   0  compacted (hit, start offset) items, one per lane: ballot prefix sum, per-warp slot queue
-//   1  PAIR: compacted hits, one per lane; the lane tests both start offsets the hit owns -- half
-//      the second-stage passes per step
 //   2  LOCAL: no compaction at all -- every lane walks its own hit mask, both start offsets per
-//      hit; the warp loops while any lane has a hit left (about twice per step on cfg 2).  Drops
-//      the ballot prefix sum, the slot queue and its decode; pays with idle lanes.
-enum : int { kS2Compact = 0, kS2Pair = 1, kS2Local = 2 };
-template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact>
-__global__ void __launch_bounds__(PfGeom<GEOM, S2 == 2>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
+//      hit; the warp loops while any lane has a hit left.  Drops the ballot prefix sum, the slot
+//      queue and its decode; pays with idle lanes.  r02 A/B: loses on cfg 2, wins on cfg 3 together
+//      with 27-bit keys (profiles/r02a_ab_cfg3.jsonl).
+// Tile distribution DYN: false -- warp w of a CTA takes the tiles w, w + W, w + 2W, ... of the CTA's
+// chunk; true -- the warps of a CTA draw tile numbers from a shared-memory counter.  With the static
+// split the warps of a CTA finish up to 25 % apart (ncu r02a: 27.8 of 32 warps active on average,
+// the least busy SM sub-partition active 74 % of the kernel), because the scheduler favours some
+// warps and nothing hands their neighbours' work over; the kernel ends with its slowest warp.
+enum : int { kS2Compact = 0, kS2Local = 2 };
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact, bool DYN = false>
+__global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
-  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the paired / lane-local second stages belong to the stride-2 first stage");
-  constexpr bool PAIR = S2 == kS2Pair;
+  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the lane-local second stage belongs to the stride-2 first stage");
   constexpr bool LOCAL = S2 == kS2Local;
-  constexpr int kPfThreads = PfGeom<GEOM, S2 == 2>::kThreads;
-  constexpr int kPfWarps = PfGeom<GEOM, S2 == 2>::kWarps;
+  constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
+  constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
   constexpr int kPfTile = PfGeom<GEOM>::kTile;
   constexpr int kPfStageBytes = PfGeom<GEOM>::kStageBytes;
   constexpr int kGroups = PfGeom<GEOM>::kGroups;
@@ -243,6 +243,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kSlotsAlloc]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kSlotsAlloc);
   __shared__ uint8_t s_cls[256];
+  __shared__ uint32_t s_next_tile;                  // DYN: next tile number of this CTA's chunk
+  __shared__ uint32_t s_tile_of[32 * kPfStages];   // DYN: tile number staged in [warp][stage]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -251,6 +253,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
   if (tid < kPfWarps * kPfStages) ptx::mbar_init(ptx::smem_addr(&s_bars[tid]), 1);
+  if (tid == 0) s_next_tile = 0;
   ptx::mbar_init_fence();
   ptx::fence_proxy_async();
   __syncthreads();
@@ -345,13 +348,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   // mbarrier): no load instructions or address arithmetic per lane, and the next tile is in
   // flight while the current one is probed.  Lane L owns the 16-byte groups at tile offsets
   // g*512 + 16L, so its 16-byte shared-memory reads are conflict free.
-  const uint64_t wstride = (uint64_t)kPfWarps * kPfTile;
-  const uint64_t wfirst = chunk_lo + (uint64_t)warp * kPfTile;
-  // step i of this warp covers [wfirst + i*wstride, +kPfTile) cut at chunk_hi; only the last
-  // step can be short
-  const uint64_t wspan = chunk_hi > wfirst ? chunk_hi - wfirst : 0;
-  const uint32_t n_steps = wspan ? (uint32_t)((wspan - 1) / wstride) + 1 : 0;
-  const uint32_t last_valid = n_steps ? (uint32_t)min((uint64_t)kPfTile, wspan - (uint64_t)(n_steps - 1) * wstride) : 0;
+  // Tile t of the chunk covers [chunk_lo + t * kPfTile, + kPfTile) cut at chunk_hi; only the last
+  // tile can be short.  Static split: step i of warp w handles tile w + i * kPfWarps.
+  const uint64_t chunk_bytes = chunk_hi - chunk_lo;
+  const uint32_t n_tiles = (uint32_t)((chunk_bytes + kPfTile - 1) / kPfTile);
+  const uint32_t last_valid = n_tiles ? (uint32_t)(chunk_bytes - (uint64_t)(n_tiles - 1) * kPfTile) : 0;
   // shared addresses of this warp's barriers and ring, and of the lane's first 16-byte group;
   // opaque to the compiler so that they stay in registers instead of being re-derived from the
   // thread index at every use
@@ -359,26 +360,41 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   ptx::keep_in_registers(bar0, ring0, lane0);
   // Refilling a stage needs no proxy fence: every lane has consumed its shared-memory reads of the
   // tile (their values fed the probes) before the __syncwarp that precedes the copy.
-  const uint8_t* next_src = p.hay + wfirst;  // source of the next tile to request
-  auto issue = [&](uint32_t step, uint32_t stage) {  // lane 0 only, steps in order
-    const uint32_t bytes = (step + 1 < n_steps ? (uint32_t)kPfTile : last_valid) + 16;
+  const uint8_t* chunk_src = p.hay + chunk_lo;
+  auto issue = [&](uint32_t t, uint32_t stage) {  // lane 0 only; t < n_tiles
+    const uint32_t bytes = (t + 1 < n_tiles ? (uint32_t)kPfTile : last_valid) + 16;
     const uint32_t bar = bar0 + stage * 8, dst = ring0 + stage * kPfStageBytes;
-    const uint8_t* src = next_src;
-    next_src += wstride;
     ptx::mbar_arrive_expect_tx(bar, bytes);
-    ptx::tma_load_1d(dst, src, bytes, bar);
+    ptx::tma_load_1d(dst, chunk_src + (uint64_t)t * kPfTile, bytes, bar);
+  };
+  // DYN: lane 0 draws the tile number for a stage from the CTA's counter, leaves it in
+  // s_tile_of[warp][stage] for the warp to read when it gets to that stage, and requests the tile
+  uint32_t* tile_of = s_tile_of + warp * kPfStages;
+  auto draw = [&](uint32_t stage) {  // lane 0 only
+    const uint32_t t = atomicAdd(&s_next_tile, 1u);
+    tile_of[stage] = t;
+    if (t < n_tiles) issue(t, stage);
   };
   if (lane == 0) {
-    if (n_steps > 0) issue(0, 0);
-    if (n_steps > 1) issue(1, 1);
+    if constexpr (DYN) {
+      draw(0);
+      draw(1);
+    } else {
+      if ((uint32_t)warp < n_tiles) issue((uint32_t)warp, 0);
+      if ((uint32_t)warp + kPfWarps < n_tiles) issue((uint32_t)warp + kPfWarps, 1);
+    }
   }
+  __syncwarp();
   constexpr int kBitsPerGroup = 16 / STRIDE;
   constexpr int kHitBits = kGroups * kBitsPerGroup;
-  const bool cta_warp_first = blockIdx.x == 0 && warp == 0;
-  uint64_t wbase = wfirst;
-  for (uint32_t it = 0; it < n_steps; ++it, wbase += wstride) {
+  for (uint32_t it = 0;; ++it) {
     const uint32_t stage = it & 1;
     const uint32_t parity = (it >> 1) & 1;
+    uint32_t t;
+    if constexpr (DYN) t = *reinterpret_cast<volatile uint32_t*>(tile_of + stage);
+    else t = (uint32_t)warp + it * (uint32_t)kPfWarps;
+    if (t >= n_tiles) break;  // tile numbers only grow: nothing is in flight for this warp any more
+    const uint64_t wbase = chunk_lo + (uint64_t)t * kPfTile;
     while (!ptx::mbar_try_wait(bar0 + stage * 8, parity)) {}
     const uint32_t stage_off = stage * (uint32_t)kPfStageBytes;
     const uint32_t tile_a = ring0 + stage_off;
@@ -427,7 +443,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 #undef ACB_WIN
     // the probes were funnelled in from the top: move the first one down to bit 0
     if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
-    if (it + 1 == n_steps) {
+    if (t + 1 == n_tiles) {
       // the last tile may be short: drop the hit bits of groups behind its end
       uint32_t ok_bits = 0;
 #pragma unroll
@@ -457,7 +473,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
       // the very first probe of the region has no start before it
-      const bool region_first = cta_warp_first && it == 0;
+      const bool region_first = blockIdx.x == 0 && t == 0;
       if (total > (uint32_t)kPfSlots) {
         // fingerprints not selective here: verify this step's hits in place
         uint32_t nver = 0;
@@ -471,7 +487,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         }
         cand_total += __reduce_add_sync(0xffffffffu, nver);
       } else {
-        // PAIR / LOCAL: both start offsets of the hit at tile offset e (even), tested by one lane
+        // LOCAL: both start offsets of the hit at tile offset e (even), tested by one lane
         auto survives = [&](uint32_t gram) -> bool {
           if (MASKED) gram = (gram | fold) & kmask;
           return bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
@@ -538,20 +554,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
         const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
         const uint32_t n_items = total * STRIDE;
-        if constexpr (PAIR) {
-          // one hit per lane; the lane tests the probed (even) offset e and the odd offset e-1
-          for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t w = base + lane;
-            bool pass0 = false, pass1 = false;
-            uint32_t e = 0;
-            if (w < total) {
-              const uint32_t raw = slots[w];
-              e = hit_offset(raw & 31u, raw >> 5);
-              test_hit(e, pass0, pass1);
-            }
-            queue_pair(wrel, e, pass0, pass1);
-          }
-        } else
         for (uint32_t base = 0; base < n_items; base += 32) {
           const uint32_t w = base + lane;
           const uint32_t j = STRIDE == 2 ? (w & 1u) : 0u;
@@ -591,7 +593,10 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       }
     }
     __syncwarp();  // every lane is done with this stage: refill it with the tile two steps ahead
-    if (lane == 0 && it + 2 < n_steps) issue(it + 2, stage);
+    if (lane == 0) {
+      if constexpr (DYN) draw(stage);
+      else if (t + 2 * kPfWarps < n_tiles) issue(t + 2 * kPfWarps, stage);
+    }
   }
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
@@ -647,16 +652,15 @@ struct MaxOp {
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
   const bool dense = p.dense != 0;
   const int geom = p.stride == 2 ? p.geom : kGeomNarrow;
-  if (geom < kGeomNarrow || geom > kGeomTall) return cudaErrorInvalidValue;
+  if (geom < kGeomNarrow || geom > kGeomWide) return cudaErrorInvalidValue;
   const int s2 = (p.stride == 2 && geom != kGeomWide) ? p.pair : kS2Compact;  // second-stage organisation
-  if (s2 < kS2Compact || s2 > kS2Local) return cudaErrorInvalidValue;
+  if (s2 != kS2Compact && s2 != kS2Local) return cudaErrorInvalidValue;
   const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
-  const int kThreadsOf[3] = {PfGeom<0>::kThreads, PfGeom<1>::kThreads,
-                             s2 == kS2Local ? PfGeom<2, true>::kThreads : PfGeom<2>::kThreads};
-  static const int kStageOf[3] = {PfGeom<0>::kStageBytes, PfGeom<1>::kStageBytes, PfGeom<2>::kStageBytes};
-  static const int kTileOf[3] = {PfGeom<0>::kTile, PfGeom<1>::kTile, PfGeom<2>::kTile};
+  static const int kThreadsOf[2] = {PfGeom<0>::kThreads, PfGeom<1>::kThreads};
+  static const int kStageOf[2] = {PfGeom<0>::kStageBytes, PfGeom<1>::kStageBytes};
+  static const int kTileOf[2] = {PfGeom<0>::kTile, PfGeom<1>::kTile};
   const int threads = kThreadsOf[geom];
   const int warps = threads / 32;
   const int stage_bytes = kStageOf[geom];
@@ -664,28 +668,26 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
   const int slot_bytes = s2 == kS2Local ? 0 : (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2;
   const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 + q2_bytes + slot_bytes) + bitmap_bytes;
-  if (smem > 227 * 1024 - 256) return cudaErrorInvalidValue;  // 256 B of static shared memory (byte classes)
+  if (smem > 227 * 1024 - 1024) return cudaErrorInvalidValue;  // static shared memory: byte classes, tile numbers
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
-  // [mode][masked][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
-  // 4 stride 2 tall, 5 / 6 narrow / tall + paired second stage, 7 / 8 narrow / tall + lane-local
-  // second stage (stride 2 is never combined with the dense variant; 4-8 are experiments, acb200_debug.h)
-#define ACB_PF_ROW(M, K)                                                                              \
-  {prefilter_kernel<M, K, false, 1, kGeomNarrow>, prefilter_kernel<M, K, true, 1, kGeomNarrow>,          \
-   prefilter_kernel<M, K, false, 2, kGeomNarrow>, prefilter_kernel<M, K, false, 2, kGeomWide>,           \
-   prefilter_kernel<M, K, false, 2, kGeomTall>, prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Pair>,  \
-   prefilter_kernel<M, K, false, 2, kGeomTall, kS2Pair>, prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Local>, \
-   prefilter_kernel<M, K, false, 2, kGeomTall, kS2Local>}
-  static const KernT table[2][2][9] = {{ACB_PF_ROW(0, false), ACB_PF_ROW(0, true)},
-                                       {ACB_PF_ROW(1, false), ACB_PF_ROW(1, true)}};
+  // [mode][masked][dyn][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
+  // 4 stride 2 narrow + lane-local second stage (stride 2 is never combined with the dense variant)
+#define ACB_PF_ROW(M, K, D)                                                                                 \
+  {prefilter_kernel<M, K, false, 1, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, true, 1, kGeomNarrow, kS2Compact, D>, \
+   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, false, 2, kGeomWide, kS2Compact, D>,  \
+   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Local, D>}
+  static const KernT table[2][2][2][5] = {{{ACB_PF_ROW(0, false, false), ACB_PF_ROW(0, false, true)},
+                                           {ACB_PF_ROW(0, true, false), ACB_PF_ROW(0, true, true)}},
+                                          {{ACB_PF_ROW(1, false, false), ACB_PF_ROW(1, false, true)},
+                                           {ACB_PF_ROW(1, true, false), ACB_PF_ROW(1, true, true)}}};
 #undef ACB_PF_ROW
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
   int variant = dense ? 1 : 0;
-  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (geom == kGeomTall ? (s2 == kS2Local ? 8 : s2 == kS2Pair ? 6 : 4)
-                                                                            : (s2 == kS2Local ? 7 : s2 == kS2Pair ? 5 : 2));
-  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][variant];
+  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (s2 == kS2Local ? 4 : 2);
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.dyn ? 1 : 0][variant];
 #ifdef ACB_EMULATE
-  if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d threads %d smem %zu\n", variant, threads, smem);
+  if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d dyn %d threads %d smem %zu\n", variant, (int)p.dyn, threads, smem);
 #endif
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

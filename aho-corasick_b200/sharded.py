@@ -3,28 +3,113 @@
 The path shards naturally: rank g owns the matches whose END lies in (a_g, b_g] (rank 0 also owns
 end == span start, i.e. empty-pattern matches of the start state, src/automaton.rs:1456-1464), reads
 max_pattern_len-1 bytes before a_g so that every pattern ending in its range is seen from a cold
-start, and never exchanges haystack data with another rank.  The only collective is the gather of
-the per-rank match buffers to rank 0 (torch.distributed: NCCL on GPUs, gloo in the CPU tests);
-because the slices are ordered and every end offset has exactly one owner, concatenating the
-per-rank buffers in rank order reproduces the single-GPU iteration order.
+start, and never exchanges haystack data with another rank.  The only exchange is the gather of
+the per-rank match buffers to rank 0; because the slices are ordered and every end offset has
+exactly one owner, concatenating the per-rank buffers in rank order reproduces the single-GPU
+iteration order.
+
+The product path is behind the C ABI (include/acb200.h: acg_comm_init, acg_shard_plan,
+acg_find_overlapping_sharded): `Comm` below is its ctypes mirror.  `gather_to_rank0` is the same
+gather written with torch.distributed for host-side arrays (gloo in the CPU tests).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
 MATCH_DTYPE = np.dtype([("pid", "<u4"), ("_pad", "<u4"), ("start", "<u8"), ("end", "<u8")])
+COMM_ID_BYTES = 128
+TRANSPORT = {0: "none", 1: "peer", 2: "nccl"}
 
 
-def slice_plan(span_start: int, span_end: int, world: int, max_pattern_len: int, align: int = 64):
-    """Per-rank (own_lo, own_hi, read_lo): rank g owns ends in (own_lo, own_hi] and scans the bytes
-    [read_lo, own_hi).  Boundaries are aligned so device loads stay vectorisable."""
-    n = span_end - span_start
-    back = max(max_pattern_len - 1, 0)
+def _ab():
+    import aho_corasick_b200 as ab
+    return ab
+
+
+class ShardStats(C.Structure):
+    _fields_ = [("local_matches", C.c_uint64), ("total_matches", C.c_uint64), ("candidates", C.c_uint64),
+                ("scan_ms", C.c_float), ("order_ms", C.c_float), ("gather_ms", C.c_float),
+                ("transport", C.c_int32), ("launches", C.c_int32)]
+
+
+def unique_id() -> bytes:
+    """Rendezvous token (ncclUniqueId) created by rank 0; hand it to the other ranks."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = _ab()._lib.acg_comm_unique_id(buf)
+    if rc:
+        raise _ab().DeviceError(rc)
+    return bytes(buf)
+
+
+class Comm:
+    """acg_comm: one per rank, bound to the current CUDA device (collective constructor)."""
+
+    def __init__(self, uid: bytes, rank: int, nranks: int):
+        assert len(uid) == COMM_ID_BYTES
+        self._lib = _ab()._lib
+        h = C.c_void_p()
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(uid)
+        rc = self._lib.acg_comm_init(buf, rank, nranks, C.byref(h))
+        if rc:
+            raise _ab().DeviceError(rc)
+        self._h, self.rank, self.nranks = h, rank, nranks
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.acg_comm_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def transport(self) -> str:
+        return TRANSPORT[self._lib.acg_comm_transport(self._h)]
+
+    def find_overlapping(self, ac, hay_ptr, hay_len, hay_global_offset, span, on_device=True, host_out=False):
+        """Collective.  Returns (n_total, device pointer of the records on rank 0 (0 elsewhere), stats,
+        host array on rank 0 if host_out)."""
+        ab = _ab()
+        dptr, n, st = C.c_void_p(), C.c_uint64(), ShardStats()
+        out, cap = None, 0
+        rc = self._lib.acg_find_overlapping_sharded(ac._h, self._h, hay_ptr, 1 if on_device else 0, hay_len,
+                                                    hay_global_offset, span[0], span[1], C.byref(dptr),
+                                                    C.byref(n), None, 0, C.byref(st))
+        if rc:
+            ab.AhoCorasick._raise(rc)
+        if host_out and self.rank == 0:
+            out = self.fetch()
+        stats = {k: getattr(st, k) for k, _ in ShardStats._fields_}
+        return n.value, (dptr.value or 0), stats, out
+
+    def fetch(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._lib.acg_comm_fetch(self._h, None, 0, C.byref(n))
+        out = np.empty(n.value, MATCH_DTYPE)
+        rc = self._lib.acg_comm_fetch(self._h, out.ctypes.data, n.value, C.byref(n))
+        if rc:
+            raise _ab().DeviceError(rc)
+        return out
+
+    def checksum(self):
+        n, f = C.c_uint64(), C.c_uint64()
+        rc = self._lib.acg_comm_checksum(self._h, C.byref(n), C.byref(f))
+        if rc:
+            raise _ab().DeviceError(rc)
+        return n.value, f.value
+
+
+def slice_plan(span_start: int, span_end: int, world: int, max_pattern_len: int):
+    """Per-rank (own_lo, own_hi, read_lo) from acg_shard_plan: rank g owns ends in (own_lo, own_hi]
+    and scans the bytes [read_lo, own_hi)."""
+    lib = _ab()._lib
     plan = []
     for g in range(world):
-        lo = span_start + (n * g // world) // align * align if g else span_start
-        hi = span_start + (n * (g + 1) // world) // align * align if g + 1 < world else span_end
-        plan.append((lo, hi, max(span_start, lo - back)))
+        lo, hi, rd = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        rc = lib.acg_shard_plan(span_start, span_end, world, g, max_pattern_len, C.byref(lo), C.byref(hi), C.byref(rd))
+        if rc:
+            raise ValueError("acg_shard_plan rejected the arguments")
+        plan.append((lo.value, hi.value, rd.value))
     return plan
 
 
@@ -61,40 +146,3 @@ def gather_to_rank0(local, dist, device=None):
         return None
     parts = [b[:c].cpu().numpy().view(MATCH_DTYPE) for b, c in zip(bufs, counts)]
     return np.concatenate(parts) if parts else np.zeros(0, MATCH_DTYPE)
-
-
-class MatchGatherer:
-    """Persistent-buffer version of gather_to_rank0 for the bench loop: match buffers stay on the
-    device (rank 0 ends up with every rank's acg_match records in rank order), one small
-    all_gather for the counts and one gather for the payload per call, no host round trips other
-    than reading the counts."""
-
-    def __init__(self, dist, device, cap_bytes):
-        import torch
-        self.dist, self.device = dist, device
-        self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.cap = int(cap_bytes)
-        self._torch = torch
-        self.count = torch.zeros(1, dtype=torch.int64, device=device)
-        self.counts = torch.zeros(self.world, dtype=torch.int64, device=device)
-        self.recv = ([torch.empty(self.cap, dtype=torch.uint8, device=device) for _ in range(self.world)]
-                     if self.rank == 0 else None)
-
-    def gather(self, local_buf, n_bytes):
-        """local_buf: uint8 CUDA tensor of capacity >= cap (only the first n_bytes are meaningful)."""
-        assert local_buf.numel() >= self.cap and n_bytes <= self.cap
-        self.count.fill_(n_bytes)
-        self.dist.all_gather_into_tensor(self.counts, self.count)
-        # ship only what the fullest rank needs (one small host read of the counts), not the capacity
-        width = int(self.counts.max().item())
-        width = min(self.cap, (width + 4095) // 4096 * 4096)
-        if width:
-            recv = [b[:width] for b in self.recv] if self.rank == 0 else None
-            self.dist.gather(local_buf[:width], recv, dst=0)
-        return self.counts
-
-    def result_numpy(self):
-        """(rank 0) concatenated matches as a host array -- outside any timed region."""
-        counts = self.counts.tolist()
-        parts = [b[:c].cpu().numpy().view(MATCH_DTYPE) for b, c in zip(self.recv, counts)]
-        return np.concatenate(parts)

@@ -191,6 +191,61 @@ int acg_count_overlapping_dev(const acg_dfa* dfa, const void* d_hay, uint64_t ha
                               uint64_t span_start, uint64_t span_end,
                               uint64_t* n_out, uint64_t* fnv, float* kernel_ms);
 
+/* ---- multi-GPU: haystack slices + gather of match buffers to rank 0 ----
+ * One process (or thread) per GPU.  The path shards naturally: rank g owns the matches whose END
+ * lies in (own_lo, own_hi] (rank 0 also owns end == span_start: empty-pattern matches of the start
+ * state, src/automaton.rs:1456-1464), scans [read_lo, own_hi) from a cold start with
+ * read_lo = own_lo - (max_pattern_len - 1), and never exchanges haystack bytes.  The only
+ * exchange is the gather of the per-rank match buffers to rank 0; concatenated in rank order they
+ * are the list AhoCorasick::find_overlapping_iter yields on the whole haystack
+ * (src/automaton.rs:954-970, 1423-1537).
+ * Transport: the records are stored by each rank's expand kernel directly into rank 0's receive
+ * buffer through a cudaIpc peer mapping (NVLink / NVSwitch); NCCL carries the 8-byte counts and the
+ * closing barrier, and the payload too (ncclSend / ncclRecv) if the peer mapping is unavailable. */
+enum { ACG_TRANSPORT_NONE = 0, ACG_TRANSPORT_PEER = 1, ACG_TRANSPORT_NCCL = 2 };
+#define ACG_COMM_ID_BYTES 128
+typedef struct acg_comm acg_comm;
+/* Rank 0 creates the rendezvous token (an ncclUniqueId) and hands it to the other ranks by whatever
+ * channel launched them (MPI, torch.distributed, a file). */
+int acg_comm_unique_id(uint8_t id[ACG_COMM_ID_BYTES]);
+/* Collective over all ranks; binds to the calling thread's current CUDA device. */
+int acg_comm_init(const uint8_t id[ACG_COMM_ID_BYTES], int rank, int nranks, acg_comm** out);
+void acg_comm_free(acg_comm* comm);
+int acg_comm_rank(const acg_comm* comm);
+int acg_comm_size(const acg_comm* comm);
+int acg_comm_transport(const acg_comm* comm); /* ACG_TRANSPORT_* */
+/* Slice of rank `rank` out of `nranks` for the span [span_start, span_end): the rank owns ends in
+ * (own_lo, own_hi] and must hold the haystack bytes [read_lo, own_hi).  Pure arithmetic. */
+int acg_shard_plan(uint64_t span_start, uint64_t span_end, int nranks, int rank, uint64_t max_pattern_len,
+                   uint64_t* own_lo, uint64_t* own_hi, uint64_t* read_lo);
+typedef struct {
+  uint64_t local_matches;  /* records this rank contributed */
+  uint64_t total_matches;  /* records in rank 0's buffer (known to every rank) */
+  uint64_t candidates;
+  float scan_ms, order_ms; /* this rank's scan kernel(s) / ordering */
+  float gather_ms;         /* count exchange + expand into rank 0's buffer + closing barrier */
+  int32_t transport;
+  int32_t launches;
+} acg_shard_stats;
+/* Collective.  `hay` holds this rank's slice of the global haystack: its byte 0 is global offset
+ * `hay_global_offset`, `hay_len` bytes are readable, and it must cover the rank's
+ * [read_lo, own_hi) of acg_shard_plan for the span (ACG_E_INVALID_SPAN otherwise).  hay_on_device
+ * != 0: `hay` is a device pointer on the communicator's device; 0: a host pointer (the copy is
+ * pipelined with the scan, as in acg_find_overlapping).  On rank 0, *d_matches receives a device
+ * pointer to *n_total acg_match records in GLOBAL offsets, in the reference's iteration order,
+ * valid until the next call on this communicator; if h_out != NULL they are also copied to the host
+ * (ACG_E_OVERFLOW with *n_total set if h_cap is too small; acg_comm_fetch then gets them without
+ * another scan).  Other ranks receive NULL / the total. */
+int acg_find_overlapping_sharded(const acg_dfa* dfa, acg_comm* comm, const void* hay, int hay_on_device,
+                                 uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
+                                 uint64_t span_end, const acg_match** d_matches, uint64_t* n_total,
+                                 acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats);
+/* Rank 0: copy the records of the most recent sharded search to the host; *n_out = their number. */
+int acg_comm_fetch(const acg_comm* comm, acg_match* out, uint64_t cap, uint64_t* n_out);
+/* Count + FNV-1a of the ordered (pid, start, end) stream of the most recent sharded search
+ * (rank 0), comparable with acg_count_overlapping_dev on one GPU over the same haystack. */
+int acg_comm_checksum(const acg_comm* comm, uint64_t* n_out, uint64_t* fnv);
+
 /* ---- packed searcher: packed::Config / Builder / Searcher, src/packed/api.rs ----------------
  * The reference's standalone "packed" API is Teddy (or Rabin-Karp) over a small pattern set with
  * leftmost semantics.  On the device its role is played by the same K3/K3b kernel pair that serves

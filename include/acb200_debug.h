@@ -40,15 +40,13 @@ int acg_debug_prefilter_plan(const acg_dfa* dfa, acg_prefilter_plan* out);
  * tests exercise the multi-chunk logic on small inputs. */
 int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 
-/* Kernel variants that are implemented and parity-tested but not yet measured against the default
- * on a B200; they never change results, only which instantiation of the prefilter kernel runs for
- * plans with the stride-2 first stage and the 128 KiB bitmap (e.g. BASELINE config 2), or whether
- * the walk engine stages its hot rows.  The default (0) is the measured kernel.  tools/ab_experiments.sh times every combination. */
-#define ACG_EXP_TALL 1u /* 2 KiB tiles, 640 threads, one CTA per SM: per-step bookkeeping over twice the positions */
-#define ACG_EXP_PAIR 2u /* second stage: one first-stage hit per lane, both of its start offsets tested by that lane */
-#define ACG_EXP_WALK_HOT 4u /* walk engine (K1): rows of the start and depth-1 states in shared memory, flagged table copy */
-#define ACG_EXP_KEY27 8u /* stride-2 first stage keyed by 27 bits (3 bytes + low 3 bits of the fourth): rebuilds the bitmap */
-#define ACG_EXP_LOCAL2 16u /* second stage without compaction: every lane walks its own hits (overrides ACG_EXP_PAIR) */
+/* Kernel / plan variants that never change results, only which instantiation of the prefilter kernel
+ * runs or how its first-stage keys are formed; kept switchable so that tools/ab_inproc.py can time
+ * them against each other in one process.  (The r01 variants TALL = 1, PAIR = 2 and WALK_HOT = 4 were
+ * measured in r02 -- profiles/r02a_ab_*.jsonl -- lost, and are gone.) */
+#define ACG_EXP_KEY27 8u   /* stride-2 first stage keyed by 27 bits (3 bytes + low 3 bits of the fourth): rebuilds the bitmap */
+#define ACG_EXP_LOCAL2 16u /* second stage without compaction: every lane walks its own hits */
+#define ACG_EXP_DYN 32u    /* the warps of a CTA draw their tiles from a shared-memory counter instead of a static split */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

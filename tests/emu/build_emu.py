@@ -9,7 +9,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / "aho-corasick_b200" / "csrc"
 OUT = HERE / "libacb200_emu.so"
-SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_prefilter.cu", "acb_api.cu"]
+SOURCES = ["acb_build.cpp", "acb_kernels.cu", "acb_prefilter.cu", "acb_comm.cu", "acb_api.cu"]
 
 
 def build(force=False, asan=False):

@@ -34,6 +34,8 @@
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct ulonglong2 { unsigned long long x, y; };
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct dim3 {
   unsigned x = 1, y = 1, z = 1;
   dim3() = default;
@@ -86,6 +88,7 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new CUevent_st{}; retu
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
   *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
   return cudaSuccess;
@@ -319,6 +322,7 @@ inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned shift) {
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const unsigned char*)p - emu::g_dyn_smem); }
 template <class T>
 inline T min(T a, T b) { return a < b ? a : b; }

@@ -71,6 +71,12 @@ def test_malformed_descriptors_are_rejected():
     t = _valid(); t["match_offsets"][1] = t["match_offsets"][-1] + 7; _rejects(t)  # non-monotone CSR
     t = _valid(); t["match_kind"] = 3; _rejects(t)
     t = _valid(); t["max_pattern_len"] = 2; _rejects(t)                          # a pattern longer than the maximum
+    # the FAIL row (row 1, id == stride) is never a transition target or a start state: its id looks
+    # like a match state to the kernels (non-zero, <= max_match_id) and would index match_offsets[-1]
+    stride = 1 << int(_valid()["stride2"])
+    t = _valid(); t["trans"][2 * stride + 1] = stride; _rejects(t)
+    t = _valid(); t["start_unanchored_id"] = stride; _rejects(t)
+    t = _valid(); t["start_anchored_id"] = stride; _rejects(t)
 
 
 def test_builder_row_depth_equals_the_walked_depth_of_the_same_table():

@@ -251,19 +251,19 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- kernel variants awaiting a measurement (include/acb200_debug.h: ACG_EXP_TALL = 1, ACG_EXP_PAIR = 2,
-# ACG_EXP_WALK_HOT = 4, ACG_EXP_KEY27 = 8, ACG_EXP_LOCAL2 = 16)
+# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY27 = 8, ACG_EXP_LOCAL2 = 16,
+# ACG_EXP_DYN = 32)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
     return ac
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 8, 10, 11, 16, 17, 25])
+@pytest.mark.parametrize("flags", [8, 16, 24, 32, 40, 48, 56])
 @pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
 def test_experimental_variants_match_the_oracle(name, flags):
-    """The tall geometry and the paired second stage on the cfg 2 / cfg 3 pattern sets: overlapping,
-    find_iter, sub-span, host path, count + FNV."""
+    """27-bit first-stage keys, the lane-local second stage and the dynamic tile distribution on the
+    cfg 2 / cfg 3 pattern sets: overlapping, find_iter, sub-span, host path, count + FNV."""
     n, seed, nbytes, kind, ci = VARIANTS[name]
     pats, hay = workload(n, seed, nbytes, ci)
     W.plant(hay[: 64 << 10], pats, 9, period=96, window=40)   # a stretch with dense matches
@@ -286,10 +286,10 @@ def test_experimental_variants_match_the_oracle(name, flags):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 8, 11, 16, 17, 24])
+@pytest.mark.parametrize("flags", [8, 16, 24, 32, 56])
 def test_experimental_variants_at_every_alignment(flags):
     """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
-    paired second stage, the 2 KiB tiles of the tall geometry) at 18 pointer phases x 8 span ends."""
+    lane-local second stage, tiles drawn dynamically) at 18 pointer phases x 8 span ends."""
     n, seed, _, kind, ci = VARIANTS["stride2_narrow"]
     pats, hay = workload(n, seed, 72 << 10, ci)
     W.plant(hay, pats, 8, period=64, window=32)
@@ -322,7 +322,7 @@ def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
 
 
-@pytest.mark.parametrize("flags", [1, 2, 3, 16, 17])
+@pytest.mark.parametrize("flags", [16, 32, 48])
 def test_experimental_variants_unselective_steps(flags):
     pats = [b"abab", b"baba", b"ababab"] + W.make_patterns(5000, 0xAC5000)
     ac = set_experiment(build(pats, 0), flags)
@@ -333,36 +333,20 @@ def test_experimental_variants_unselective_steps(flags):
     eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), flags)
 
 
-@pytest.mark.parametrize("name", ["stride2_narrow", "stride2_wide", "stride1_short_patterns", "dense"])
-def test_walk_engine_with_hot_rows(name):
-    """ACG_EXP_WALK_HOT = 4: K1 over the flagged table copy with the start / depth-1 rows staged in
-    shared memory -- same stream as the oracle and as the plain walk, incl. sub-spans and 1-byte
-    patterns (depth-1 match states are not staged)."""
+@pytest.mark.parametrize("name", ["stride2_wide", "stride1_short_patterns", "dense"])
+def test_dynamic_tiles_on_the_other_variants(name):
+    """ACG_EXP_DYN = 32 with the wide, stride-1 and dense instantiations."""
     n, seed, nbytes, kind, ci = VARIANTS[name]
     pats, hay = workload(n, seed, min(nbytes, 256 << 10), ci)
     if name == "stride1_short_patterns":
-        pats = [p[:3] for p in pats[:150]] + pats[150:] + [b"q", b"Z"]
-    W.plant(hay[: 32 << 10], pats, 9, period=96, window=40)
-    ac = set_experiment(build(pats, 0, ci, engine=ab.Engine.Walk), 4)
-    o = O.Oracle(pats, ascii_case_insensitive=ci, kind=O.KIND_DFA)
-    want = o.find_overlapping_iter_np(hay)
-    got, _ = ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)
-    eq(got, want, name)
-    assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
-    s, e = 4099, hay.size - 777
-    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size, span=(s, e))[0], o.find_overlapping_iter_np(hay, span=(s, e)), name)
-    eq(ac.try_find_overlapping_iter_np(hay), want, name + " host")
-    set_experiment(ac, 0)
-    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], want, name + " plain")
-
-
-def test_walk_hot_rows_with_empty_pattern_and_tiny_automata():
-    """The start state is a match state (empty pattern): it is not staged; single-pattern automata."""
-    for pats in ([b"", b"ab", b"b"], [b"abc"], [b"a"], [b"ab", b"ba", b"abab"]):
-        hay = np.frombuffer(b"xxabcabab" * 300 + b"ab", dtype=np.uint8).copy()
-        ac = set_experiment(build(pats, 0, engine=ab.Engine.Walk), 4)
-        o = O.Oracle(pats, kind=O.KIND_DFA)
-        eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), pats)
+        pats = [p[:3] for p in pats[:150]] + pats[150:]
+    ac = set_experiment(build(pats, kind, ci), 32)
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), name)
+    if kind == 0:
+        eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), name)
+        s, e = 4099, hay.size - 777
+        eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size, span=(s, e))[0], o.find_overlapping_iter_np(hay, span=(s, e)), name)
 
 
 # ---- dense table produced on the "device" (acg_build_on_device, SURVEY section 8f.2) -------------

@@ -32,7 +32,7 @@ def _worker(rank, world, port, case, q):
         pats, hay, span = case
         o = O.Oracle(pats, kind=O.KIND_DFA)
         s0, s1 = span
-        lo, hi, read_lo = S.slice_plan(s0, s1, world, o.max_pattern_len, align=16)[rank]
+        lo, hi, read_lo = S.slice_plan(s0, s1, world, o.max_pattern_len)[rank]
         local = o.find_overlapping_iter_np(hay, span=(read_lo, hi))
         local = S.owned(local, rank, lo)
         full = S.gather_to_rank0(local, dist)
