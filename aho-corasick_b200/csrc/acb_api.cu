@@ -65,7 +65,7 @@ struct PrefilterPlan {
   uint32_t k = 0, kmask = 0, fold = 0, mult = 1, mult3 = 1, shift = 0, log_bits = 0;
   uint32_t stride = 1;
   uint32_t key_shift = 8;  // stride 2: first-stage hash = window * (mult3 << key_shift); 5: the key also
-                           // holds the low 3 bits of the window's fourth byte (ACG_EXP_KEY27)
+                           // holds the low 3 bits of the window's fourth byte (default; 8 with ACG_EXP_KEY24)
   bool wide = false;
   bool brute = false;
   uint32_t dup_shift = 0;
@@ -332,13 +332,13 @@ void derive_metadata(acg_dfa* a) {
       // the byte from the fingerprint's own low bits.  A multiplicative hash of such short keys is
       // sensitive to the constant, so pick the candidate that lets through the fewest fingerprints
       // drawn from the bytes the patterns use at each position.
-      // First-stage keys.  Default: the 3-byte fingerprints.  ACG_EXP_KEY27 (experiment): 27-bit keys
+      // First-stage keys.  ACG_EXP_KEY24: the 3-byte fingerprints.  Default (r02 A/B: -2 % cfg 2, -18 % cfg 3): 27-bit keys
       // -- the 3 bytes plus the low 3 bits of the window's fourth byte, which a shift of 5 instead
       // of 8 in the multiplier keeps at no cost in the kernel.  For a pattern that starts at the
       // probed (even) offset the fourth byte is its own fourth byte; for one that starts one byte
       // earlier it is the pattern's fifth byte -- any of the 8 values if the pattern ends after four
       // bytes.  Genuine 3-byte prefix hits (the bulk of the first-stage hits of cfg 2) drop 8-fold.
-      const bool key27 = (a->experiment & ACG_EXP_KEY27) != 0;
+      const bool key27 = (a->experiment & ACG_EXP_KEY24) == 0;
       pf.key_shift = key27 ? 5 : 8;
       std::vector<uint32_t> keys1;
       if (!key27) {
@@ -716,7 +716,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   // kernel geometry as planned; second-stage organisation and tile distribution: see prefilter_kernel
   p.geom = pf.wide ? 1 : 0;
   p.pair = (pf.stride == 2 && !pf.wide && (a->experiment & ACG_EXP_LOCAL2)) ? 2 : 0;
-  p.dyn = (a->experiment & ACG_EXP_DYN) ? 1 : 0;
+  p.dyn = (a->experiment & ACG_EXP_STATIC_TILES) ? 0 : 1;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
@@ -1527,11 +1527,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_KEY27 | ACG_EXP_LOCAL2 | ACG_EXP_DYN))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_LOCAL2 | ACG_EXP_STATIC_TILES))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;
-  if (changed & ACG_EXP_KEY27) {
+  if (changed & ACG_EXP_KEY24) {
     // the first-stage keys are part of the plan: rebuild it and refresh the device copy of the bitmap
     const size_t old_words = a->pf.bitmap.size();
     derive_metadata(a);

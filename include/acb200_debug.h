@@ -44,9 +44,12 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
  * runs or how its first-stage keys are formed; kept switchable so that tools/ab_inproc.py can time
  * them against each other in one process.  (The r01 variants TALL = 1, PAIR = 2 and WALK_HOT = 4 were
  * measured in r02 -- profiles/r02a_ab_*.jsonl -- lost, and are gone.) */
-#define ACG_EXP_KEY27 8u   /* stride-2 first stage keyed by 27 bits (3 bytes + low 3 bits of the fourth): rebuilds the bitmap */
-#define ACG_EXP_LOCAL2 16u /* second stage without compaction: every lane walks its own hits */
-#define ACG_EXP_DYN 32u    /* the warps of a CTA draw their tiles from a shared-memory counter instead of a static split */
+#define ACG_EXP_KEY24 8u         /* stride-2 first stage keyed by the 3 fingerprint bytes only; default: 27 bits (3 bytes +
+                                  * low 3 bits of the fourth).  Rebuilds the bitmap. */
+#define ACG_EXP_LOCAL2 16u       /* second stage without compaction: every lane walks its own hits */
+#define ACG_EXP_STATIC_TILES 32u /* warp w of a CTA takes tiles w, w + W, ...; default: the warps of a CTA draw their tiles
+                                  * from a shared-memory counter.  r02 A/B (profiles/r02b_*.jsonl): dynamic tiles + 27-bit
+                                  * keys -7 % on cfg 2, -22 % on cfg 3, -15 % on cfg 5. */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

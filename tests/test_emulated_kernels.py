@@ -251,8 +251,8 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY27 = 8, ACG_EXP_LOCAL2 = 16,
-# ACG_EXP_DYN = 32)
+# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_LOCAL2 = 16,
+# ACG_EXP_STATIC_TILES = 32)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
@@ -305,18 +305,18 @@ def test_experimental_variants_at_every_alignment(flags):
 
 
 def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
-    """ACG_EXP_KEY27 with the 16 KiB bitmap (cfg 4's plan), and 4-byte patterns at odd offsets followed
-    by every possible byte."""
+    """27-bit first-stage keys (the default) with the 16 KiB bitmap (cfg 4's plan), and 4-byte patterns
+    at odd offsets followed by every possible byte."""
     n, seed, nbytes, kind, ci = VARIANTS["stride2_wide"]
     pats, hay = workload(n, seed, 256 << 10, ci)
-    ac = set_experiment(build(pats, kind, ci), 8)
+    ac = build(pats, kind, ci)
     assert plan_of(ac).wide and plan_of(ac).key_shift == 5
     o = O.Oracle(pats, match_kind=kind, kind=O.KIND_DFA)
     eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), "wide key27")
     pats = [b"abcd", b"bcde", b"wxyz", b"abcdq"] + W.make_patterns(5000, 0xAC5000)
     body = b"".join(b" " * (i % 2) + p + bytes([x]) for i, p in enumerate(pats[:4] * 64) for x in (i * 37 % 256,))
     hay = np.frombuffer(body + bytes(range(256)) * 4, dtype=np.uint8).copy()
-    ac = set_experiment(build(pats, 0), 8)
+    ac = build(pats, 0)
     assert plan_of(ac).stride == 2 and plan_of(ac).key_shift == 5
     o = O.Oracle(pats, kind=O.KIND_DFA)
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
@@ -335,7 +335,7 @@ def test_experimental_variants_unselective_steps(flags):
 
 @pytest.mark.parametrize("name", ["stride2_wide", "stride1_short_patterns", "dense"])
 def test_dynamic_tiles_on_the_other_variants(name):
-    """ACG_EXP_DYN = 32 with the wide, stride-1 and dense instantiations."""
+    """ACG_EXP_STATIC_TILES = 32 with the wide, stride-1 and dense instantiations."""
     n, seed, nbytes, kind, ci = VARIANTS[name]
     pats, hay = workload(n, seed, min(nbytes, 256 << 10), ci)
     if name == "stride1_short_patterns":
@@ -425,17 +425,18 @@ def test_device_fill_on_the_baseline_pattern_sets():
 
 
 def test_device_fill_with_a_rebuilt_plan():
-    """ACG_EXP_KEY27 re-derives the prefilter plan after the build: on a device-filled handle that runs
+    """ACG_EXP_KEY24 re-derives the prefilter plan after the build: on a device-filled handle that runs
     off the builder's shallow trie edges (the fill plan's per-row arrays are gone by then)."""
     pats, hay = workload(5000, 0xAC5000, 192 << 10)
     host = set_experiment(_builder(0, False).build(pats), 8)
     dev = set_experiment(_builder(0, False, device_fill=True).build(pats), 8)
-    assert plan_of(dev).key_shift == 5
-    _same_plan(host, dev, "key27")
+    assert plan_of(dev).key_shift == 8
+    _same_plan(host, dev, "key24")
     o = O.Oracle(pats, kind=O.KIND_DFA)
-    eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "key27 dev fill")
+    eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "key24 dev fill")
     set_experiment(dev, 0)
-    _same_plan(set_experiment(host, 0), dev, "back to 24-bit keys")
+    assert plan_of(dev).key_shift == 5
+    _same_plan(set_experiment(host, 0), dev, "back to 27-bit keys")
     eq(dev.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "default dev fill")
 
 

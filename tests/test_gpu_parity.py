@@ -329,6 +329,124 @@ def test_full_size_properties_config2():
             and np.array_equal(got["end"] - off, want["end"])
 
 
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("device_fill", [False, True])
+def test_full_size_properties_config5(device_fill):
+    """BASELINE config 5's automaton at its full 100 000 patterns (dense-set kernel variant, 414 MB
+    table), host-built and device-built, on a 2 GiB device-generated haystack: the two independent
+    engines agree on count + FNV of the whole ordered stream, whole = left + right + straddlers, and
+    the oracle agrees tuple for tuple on sampled 8 MiB windows."""
+    import torch
+    n = 2 << 30
+    c = W.CONFIGS["cfg5"]
+    pats = W.make_patterns(c["n_patterns"], c["pattern_seed"])
+    assert len(pats) == 100000
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    planted = W.torch_fill_config("cfg5", d, pats)
+    b = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA)
+    if device_fill:
+        b.device_fill(True)
+    ac = b.build(pats)
+    cnt_p, fnv_p, _ = ac.count_overlapping_dev(d.data_ptr(), n)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    ac.set_engine(ab.Engine.Walk)
+    cnt_w, fnv_w, _ = ac.count_overlapping_dev(d.data_ptr(), n)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
+    assert (cnt_p, fnv_p) == (cnt_w, fnv_w)
+    assert cnt_p >= planted
+    ac.set_engine(ab.Engine.Auto)
+    full, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n)
+    assert len(full) == cnt_p
+    cut = (1 << 30) + 54321
+    left, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n, span=(0, cut))
+    right, _ = ac.find_overlapping_iter_dev_np(d.data_ptr(), n, span=(cut, n))
+    straddle = full[(full["start"] < cut) & (full["end"] > cut)]
+    assert len(left) + len(right) + len(straddle) == len(full)
+    assert_np_equal(left, full[full["end"] <= cut])
+    assert_np_equal(right, full[full["start"] >= cut])
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    for off in (0, (1 << 30) + 4096 * 7 + 3, n - (8 << 20)):
+        w = d[off: off + (8 << 20)].cpu().numpy()
+        want = o.find_overlapping_iter_np(w)
+        got = full[(full["start"] >= off) & (full["end"] <= off + (8 << 20))]
+        assert len(got) == len(want)
+        assert np.array_equal(got["pid"], want["pid"]) and np.array_equal(got["start"] - off, want["start"]) \
+            and np.array_equal(got["end"] - off, want["end"])
+
+
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("cfg,kind,ci", [("cfg3", 1, True), ("cfg4", 1, False)])
+def test_full_size_properties_config3_4(cfg, kind, ci):
+    """BASELINE configs 3 and 4 at their full size (4 GiB, find_iter, leftmost-first).  Size-independent
+    properties: the list is ordered and non-overlapping; every reported span holds its pattern's bytes
+    (checked on the device for all ~10^6 matches); every planted occurrence lies inside a reported
+    match or overlaps one; on sampled windows that begin at a reported match end (so that the
+    iterator's cursor is the same) the list equals the oracle's and the single-lane restatement of
+    the reference loop (seq_find_kernel, the second device engine) tuple for tuple."""
+    import torch
+    n = 4 << 30
+    c = W.CONFIGS[cfg]
+    pats = W.make_patterns(c["n_patterns"], c["pattern_seed"])
+    try:
+        d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    except RuntimeError:
+        pytest.skip("not enough device memory for the 4 GiB haystack")
+    planted = W.torch_fill_config(cfg, d, pats)
+    ac = build(pats, kind, ascii_case_insensitive=ci, kind=ab.AhoCorasickKind.DFA)
+    full, _ = ac.find_iter_dev_np(d.data_ptr(), n)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    st, en, pid = full["start"].astype(np.int64), full["end"].astype(np.int64), full["pid"].astype(np.int64)
+    assert len(full) >= planted * 0.98   # a planted occurrence can be shadowed by a match that overlaps it
+    assert bool(np.all(st[1:] >= en[:-1])) and bool(np.all(en > st))
+    # every span spells its pattern (ASCII case folded for cfg 3)
+    lens = np.array([len(p) for p in pats], dtype=np.int64)
+    assert np.array_equal(en - st, lens[pid])
+    maxlen = int(lens.max())
+    table = np.zeros((len(pats), maxlen), dtype=np.uint8)
+    for i, p in enumerate(pats):
+        table[i, :len(p)] = np.frombuffer(p, dtype=np.uint8)
+
+    def fold(x):
+        if not ci:
+            return x
+        up = (x >= 65) & (x <= 90)
+        return torch.where(up, x + 32, x)
+    t_table = torch.from_numpy(table).cuda()
+    t_st, t_pid, t_len = torch.from_numpy(st).cuda(), torch.from_numpy(pid).cuda(), torch.from_numpy(en - st).cuda()
+    ar = torch.arange(maxlen, device="cuda")
+    for lo in range(0, len(full), 1 << 18):
+        sl = slice(lo, lo + (1 << 18))
+        mask = ar[None, :] < t_len[sl][:, None]
+        idx = (t_st[sl][:, None] + ar[None, :]).clamp_(max=n - 1)
+        hb = fold(d[idx])
+        pb = fold(t_table[t_pid[sl]])
+        assert bool(torch.all((hb == pb) | ~mask))
+    # sampled windows, starting where the iterator's cursor is known
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    win = 4 << 20
+    for off in (0, (1 << 30) + 4096 * 7 + 3, (3 << 30) + 999, n - win - 4096):
+        i0 = int(np.searchsorted(en, off))
+        ws = int(en[i0]) if off else 0
+        we = min(n, ws + win)
+        w = d[ws:we].cpu().numpy()
+        want = o.find_iter_np(w)
+        safe = we - ws - maxlen     # a match that starts before this offset is decided by bytes inside the window
+        want = want[want["start"].astype(np.int64) < safe]
+        got = full[(st >= ws) & (st < ws + safe)]
+        assert len(got) == len(want) and len(want) > 500
+        assert np.array_equal(got["pid"], want["pid"]) and np.array_equal(got["start"] - ws, want["start"]) \
+            and np.array_equal(got["end"] - ws, want["end"])
+        # second device engine on the same window
+        ac.set_engine(ab.Engine.Sequential)
+        seq, _ = ac.find_iter_dev_np(d.data_ptr(), n, span=(ws, we))
+        assert ac.last_stats()["engine"] == int(ab.Engine.Sequential)
+        ac.set_engine(ab.Engine.Auto)
+        pf, _ = ac.find_iter_dev_np(d.data_ptr(), n, span=(ws, we))
+        assert_np_equal(seq, pf, (cfg, off))
+        keep = seq["start"].astype(np.int64) < ws + safe
+        assert_np_equal(seq[keep], got, (cfg, off, "seq vs full"))
+
+
 @pytest.mark.parametrize("kind", [0, 1, 2])
 def test_find_single_vs_oracle(kind):
     """AhoCorasick::try_find (src/ahocorasick.rs:1021): windowed device scan vs the oracle."""

@@ -1,4 +1,4 @@
-"""Switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY27, ACG_EXP_LOCAL2, ACG_EXP_DYN)
+"""Switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24, ACG_EXP_LOCAL2, ACG_EXP_STATIC_TILES)
 on the device: same tuple stream as the oracle and as the default kernel; and the dense table built
 on the device."""
 import ctypes

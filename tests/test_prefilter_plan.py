@@ -135,7 +135,7 @@ def check(pats, experiment=0, **knobs):
         getattr(b, k)(v)
     ac = set_experiment(b.build(pats), experiment)
     p = plan_of(ac)
-    assert p.key_shift == (5 if (experiment & 8 and p.stride == 2) else 8)
+    assert p.key_shift == (5 if (not experiment & 8 and p.stride == 2) else 8)
     t = ac.tables()
     ci = bool(knobs.get("ascii_case_insensitive"))
     if not p.supported:
@@ -245,13 +245,16 @@ def test_first_stage_pass_rate_is_low_on_random_text():
 @pytest.mark.parametrize("knobs", [dict(), dict(match_kind=ab.MatchKind.LeftmostFirst, ascii_case_insensitive=True),
                                    dict(match_kind=ab.MatchKind.LeftmostLongest)])
 def test_plan_with_27_bit_first_stage_keys(knobs):
-    """ACG_EXP_KEY27 = 8: the first-stage key also holds the low 3 bits of the window's fourth byte.
-    No false negatives at either alignment, whatever follows a 4-byte pattern; fewer random hits."""
+    """Default plan: the first-stage key also holds the low 3 bits of the window's fourth byte.
+    No false negatives at either alignment, whatever follows a 4-byte pattern; fewer random hits.
+    ACG_EXP_KEY24 = 8 goes back to 3-byte keys."""
     for pats in (W.make_patterns(5000, 0xAC5000), W.make_patterns(50, 0xAC0050),
                  [b"abcd", b"bcde", b"cdef", b"abcdefgh", b"xyzw", b"abcdX", b"abcdY"],
                  W.make_patterns(700, 11, lo=4, hi=5)):
-        p = check(pats, experiment=8, **knobs)
+        p = check(pats, experiment=0, **knobs)
         assert p.stride == 2 and p.key_shift == 5
+        p = check(pats, experiment=8, **knobs)
+        assert p.stride == 2 and p.key_shift == 8
 
 
 def test_27_bit_keys_cut_the_first_stage_pass_rate():
@@ -260,12 +263,12 @@ def test_27_bit_keys_cut_the_first_stage_pass_rate():
     rng = np.random.default_rng(3)
     txt = rng.integers(0x20, 0x7F, size=(40000, 4), dtype=np.uint32)
     wins = txt[:, 0] | (txt[:, 1] << 8) | (txt[:, 2] << 16) | (txt[:, 3] << 24)
-    base = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
-    set_experiment(ac, 8)
     k27 = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
+    set_experiment(ac, 8)
+    base = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
     set_experiment(ac, 0)
     again = sum(first_stage_hit(plan_of(ac), int(w)) for w in wins)
     print("first-stage pass rate on random printable text: 24-bit keys %.4f, 27-bit keys %.4f" % (base / len(wins), k27 / len(wins)))
     # the genuine 3-byte prefix hits (10 000 fingerprints in 95^3) all but disappear; what remains are the
     # Bloom false positives of a bitmap that also carries the second stage's two bits per 4-gram
-    assert again == base and k27 < base * 0.97
+    assert again == k27 and k27 < base * 0.97
