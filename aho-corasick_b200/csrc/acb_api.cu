@@ -281,6 +281,42 @@ void derive_metadata(acg_dfa* a) {
     }
   }
   if (pf.k == 0) return;
+  // Dense sets (more fingerprints than a two-probe Bloom filter of 2^20 bits can keep apart; cfg 5:
+  // 10^5): a blocked filter instead -- every fingerprint owns one 32-bit word (top 15 bits of
+  // gram * mult) and two bits inside it (bits 0-4 and 5-9 of the product's high half), so that the
+  // per-position probe settles both with a single shared-memory load; the second stage is then the
+  // exact anchor-map lookup.  Must match the DENSE branch of ACB_PROBE in acb_prefilter.cu.
+  const bool dense = best_set.size() > 8192;
+  if (dense) {
+    std::fill(pf.bitmap.begin(), pf.bitmap.end(), 0u);
+    const uint32_t word_shift = 32 - (pf.log_bits - 5);
+    for (uint32_t g : best_set) {
+      const uint64_t prod = uint64_t(g) * pf.mult;
+      const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
+      pf.bitmap[lo >> word_shift] |= (1u << (hi & 31)) | (1u << ((hi >> 5) & 31));
+    }
+    // pass rate on text drawn from the bytes the patterns use at each fingerprint position
+    std::vector<uint8_t> alpha[4];
+    for (uint32_t j = 0; j < pf.k; ++j) {
+      bool seen[256] = {false};
+      for (uint32_t g : best_set) seen[(g >> (8 * j)) & 0xFF] = true;
+      for (uint32_t b = 0; b < 256; ++b) if (seen[b]) alpha[j].push_back(uint8_t(b));
+    }
+    uint64_t pass = 0, x = 0x9E3779B97F4A7C15ull;
+    const int kTrials = 65536;
+    for (int i = 0; i < kTrials; ++i) {
+      uint32_t g = 0;
+      for (uint32_t j = 0; j < pf.k; ++j) {
+        x = x * 6364136223846793005ull + 1442695040888963407ull;
+        g |= uint32_t(alpha[j][(x >> 33) % alpha[j].size()]) << (8 * j);
+      }
+      const uint64_t prod = uint64_t(g) * pf.mult;
+      const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
+      const uint32_t w = pf.bitmap[lo >> word_shift];
+      pass += (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1u;
+    }
+    pf.fill = double(pass) / kTrials;
+  }
   pf.brute = pf.fill > 0.25;
   pf.supported = true;
   // Stride-2 first stage: with 4-byte fingerprints and patterns of at least 4 bytes, probing only
@@ -409,7 +445,7 @@ void derive_metadata(acg_dfa* a) {
       }
     }
   }
-  pf.dense = !pf.brute && best_set.size() > 8192;
+  pf.dense = !pf.brute && dense;
   // Anchor map: the verifier looks the first k bytes at a candidate offset up here and starts at
   // depth k.  Keys are raw (unfolded) byte strings: one entry per trie path of length k.
   const std::vector<Item>& paths = level[pf.k];

@@ -123,6 +123,17 @@ __device__ __forceinline__ uint32_t anchor_lookup(const DfaDev& d, const Prefilt
   }
 }
 
+// The same lookup for a key already in a register (the dense variant's second stage reads the
+// candidate's bytes out of the staged tile): `key` = the raw first k bytes at the offset.
+__device__ __forceinline__ uint32_t anchor_lookup_key(const DfaDev& d, uint32_t key) {
+  uint32_t slot = bloom_hash3(key) >> d.amap_shift;
+  for (;;) {
+    const uint2 e = __ldg(d.amap + slot);
+    if (e.y == 0 || e.x == key) return e.y;
+    slot = (slot + 1) & d.amap_mask;
+  }
+}
+
 // Verify one candidate start offset `s` (K3b): walk the shipped DFA while the state stays on the
 // trie path anchored at s (depth == bytes consumed), starting from state `sid` at depth `j`
 // (the start state, or the state the anchor map gave for the first j bytes).
@@ -235,7 +246,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   constexpr int kSlotsAlloc = LOCAL ? 0 : kPfSlots;  // the lane-local second stage keeps no slot queue
   constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
   constexpr uint32_t kBloomShift = PfBloom<GEOM>::kShift;
-  using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, gram])
+  using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, trie state of its first k bytes])
   ACB_DYNAMIC_SMEM(smem_raw);
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
   uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
@@ -304,40 +315,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   Q2Entry* q2 = s_queue2 + warp * kPfQ2;
   uint32_t q2len = 0;  // warp-uniform
 
-  auto q2_off = [](const Q2Entry& e) -> uint32_t {
-    if constexpr (DENSE) return e.x; else return e;
-  };
-  auto drain2 = [&]() {  // verify the survivors of both probes (K3b), one per lane
+  auto drain2 = [&]() {  // verify the queued survivors (K3b), one per lane
     __syncwarp();
-    if constexpr (DENSE) {
-      // dense pattern sets: the Bloom probes still let through far more offsets than there are
-      // pattern beginnings, so look each survivor up in the anchor map first (one L2 access) and
-      // compact in place: the DFA walks then run with full warps, from depth k
-      if (d.amap != nullptr) {
-        uint32_t w = 0;
-        for (uint32_t base = 0; base < q2len; base += 32) {
-          const uint32_t i = base + lane;
-          uint2 e = make_uint2(0, 0);
-          if (i < q2len) {
-            e = q2[i];
-            e.y = anchor_lookup(d, p, chunk_base + e.x);
-          }
-          const uint32_t bal = __ballot_sync(0xffffffffu, e.y != 0);
-          if (e.y != 0) q2[w + __popc(bal & ((1u << lane) - 1))] = e;
-          w += __popc(bal);
-          __syncwarp();
-        }
-        cand_total += w;
-        for (uint32_t i = lane; i < w; i += 32) {
-          const uint2 e = q2[i];
-          verify_from<MODE>(d, p, s_cls, chunk_base + e.x, e.y, d.amap_k, em);
-        }
-        q2len = 0;
-        __syncwarp();
-        return;
+    for (uint32_t i = lane; i < q2len; i += 32) {
+      if constexpr (DENSE) {
+        // (offset, trie state of its first k bytes): the anchor map was consulted when the entry was queued
+        const uint2 e = q2[i];
+        if (e.y != 0) verify_from<MODE>(d, p, s_cls, chunk_base + e.x, e.y, d.amap_k, em);
+        else verify_at<MODE>(d, p, s_cls, chunk_base + e.x, em);
+      } else {
+        verify_at<MODE>(d, p, s_cls, chunk_base + q2[i], em);
       }
     }
-    for (uint32_t i = lane; i < q2len; i += 32) verify_at<MODE>(d, p, s_cls, chunk_base + q2_off(q2[i]), em);
     cand_total += q2len;
     q2len = 0;
     __syncwarp();
@@ -424,8 +413,16 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       h = gm * mult;                                                                          \
       sel = h;                                                                                \
     }                                                                                         \
-    const uint32_t rep = (uint32_t)s_bytes[h >> kBloomShift] * 0x01010101u;                   \
-    mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, sel), 1);                          \
+    if constexpr (DENSE) {                                                                    \
+      /* blocked filter: one word per key (top bits of the product), two bits inside it (low    \
+         bits of the product's high half) -- both tested with this one load */                  \
+      const uint32_t ph = __umulhi(gm, mult);                                                  \
+      const uint32_t bw = s_bitmap[h >> (kBloomShift + 2)];                                    \
+      mask = __funnelshift_r(mask, __funnelshift_r(bw, bw, ph) & __funnelshift_r(bw, bw, ph >> 5), 1); \
+    } else {                                                                                  \
+      const uint32_t rep = (uint32_t)s_bytes[h >> kBloomShift] * 0x01010101u;                 \
+      mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, sel), 1);                        \
+    }                                                                                         \
   } while (0)
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
@@ -460,7 +457,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     // ballots; a lane with more hits than the planes cover sends the step down the unselective path
     const uint32_t cnt = __popc(mask);
     const uint32_t lt = (1u << lane) - 1;
-    constexpr int kPlanes = DENSE ? 6 : 3;  // dense sets: up to 32 hits per lane are normal
+    constexpr int kPlanes = DENSE ? 4 : 3;  // per-lane hit counts the ballot prefix sum covers (dense: 32 probes per lane)
     uint32_t slot = 0, total = 0;
     constexpr int kSumPlanes = LOCAL ? 0 : kPlanes;  // the lane-local second stage needs no slots
 #pragma unroll
@@ -570,12 +567,22 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
               const uint32_t off = e - j;
               const uint32_t sa = tile_a + (off & ~3u);
               uint32_t gram = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8);
+              if constexpr (DENSE) {
+                // dense sets: the exact answer is one L2 access away -- the anchor map says whether
+                // the k bytes at the offset begin a pattern, and at which trie state
+                const uint64_t s0 = chunk_base + (wrel + e - j);
+                if (d.amap == nullptr) pass = true;
+                else if (s0 + d.amap_k <= p.span_end) {
+                  gram_keep = anchor_lookup_key(d, gram & d.amap_kmask);
+                  pass = gram_keep != 0;
+                }
+              } else {
               if (MASKED) gram = (gram | fold) & kmask;
-              gram_keep = gram;
               // stride 2: the first stage saw only three of the four bytes, so the cheap
               // multiplicative hash of the whole fingerprint rejects most items before the mix
               if (STRIDE == 2) pass = bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
               else pass = bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
+              }
             }
           }
           const uint32_t bal = __ballot_sync(0xffffffffu, pass);

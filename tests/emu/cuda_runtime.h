@@ -311,6 +311,7 @@ inline unsigned long long __shfl_sync(unsigned mask, unsigned long long v, int s
 // has no notion of convergence, so the caller alone it is.
 inline unsigned __activemask() { return 1u << (emu::g_cur->tid.x & 31); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
   return (unsigned)((((unsigned long long)hi << 32) | lo) >> (shift & 31));

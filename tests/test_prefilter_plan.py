@@ -77,11 +77,19 @@ def first_stage_hit(p, window):
         h = (gm * ((p.mult3 << p.key_shift) & M32)) & M32   # key_shift 8: 3-byte key; 5: + 3 bits of the 4th byte
         return bit_set(p, h >> p.shift, gm & 7)
     gm = (window | p.fold) & p.kmask
+    if p.dense:
+        # blocked filter: the word from the top bits of the product, two bits from its high half
+        prod = gm * p.mult
+        lo, hi = prod & M32, (prod >> 32) & M32
+        w = p.bitmap[lo >> (32 - (p.log_bits - 5))]
+        return (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1
     h = (gm * p.mult) & M32
     return bit_set(p, h >> p.shift, h & 7)
 
 
 def second_stage_hit(p, window):
+    if p.dense:
+        return True   # the dense variant's second stage is the (exact) anchor-map lookup
     gram = (window | p.fold) & p.kmask
     ok = probe_full(p, hash2(gram))
     if p.stride == 2:
