@@ -664,7 +664,7 @@ struct TupleResult {
 
 // K1 + K4 on a device-resident haystack; leaves `n` ordered tuples in
 // ws.d_keys[sorted_buf] / ws.d_pids[sorted_buf].
-int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start,
+int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uint64_t span_start,
                          uint64_t span_end, TupleResult* res) {
   Workspace& w = a->ws;
   const uint64_t n_bytes = span_end - span_start;
@@ -672,13 +672,14 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
-  const uint64_t target_lanes = uint64_t(dev_sms) * 2048;
-  uint64_t seg_len = (n_bytes + target_lanes - 1) / std::max<uint64_t>(target_lanes, 1);
+  // shards: four per lane (kWalkChains in acb_kernels.cu), enough lanes to fill every SM's thread slots
+  const uint64_t target_shards = uint64_t(dev_sms) * 1536 * 4;
+  uint64_t seg_len = (n_bytes + target_shards - 1) / std::max<uint64_t>(target_shards, 1);
   seg_len = std::max<uint64_t>(seg_len, 256);
   seg_len = (seg_len + 15) & ~15ull;
-  // shard starts are placed so that (d_hay + span_start + k*seg_len) keeps the 16-byte
-  // phase of the first shard; the kernel handles the unaligned head per lane.
-  const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
+  // the shard grid starts at the 16-byte boundary at or before d_hay + span_start (see the kernel)
+  const uint64_t phase = reinterpret_cast<uintptr_t>(d_hay + span_start) & 15;
+  const uint64_t n_segs = std::max<uint64_t>((n_bytes + phase + seg_len - 1) / seg_len, 1);
   uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 256));
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
@@ -686,6 +687,7 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_s
     CK(cudaMemsetAsync(w.d_counter, 0, 8, w.stream));
     acb::WalkLaunch p;
     p.hay = d_hay;
+    p.hay_len = readable;
     p.span_start = span_start;
     p.span_end = span_end;
     p.seg_len = seg_len;
@@ -1097,7 +1099,7 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   TupleResult r;
   if (engine == ACG_ENGINE_PREFILTER)
     rc = run_prefilter(a, d_base, readable, span_start, span_end, 0, &r, pipelined ? hay : nullptr);
-  else rc = run_walk_overlapping(a, d_base, span_start, span_end, &r);
+  else rc = run_walk_overlapping(a, d_base, readable, span_start, span_end, &r);
   if (rc) return rc;
   if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
   if (devout) {
@@ -1195,7 +1197,7 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
       if (!rc) {
         if (engine == ACG_ENGINE_PREFILTER)
           rc = run_prefilter(a, d_base, readable, lspan_s, lspan_e, 0, &r, pipelined ? hay : nullptr);
-        else rc = run_walk_overlapping(a, d_base, lspan_s, lspan_e, &r);
+        else rc = run_walk_overlapping(a, d_base, readable, lspan_s, lspan_e, &r);
       }
       if (!rc && r.n && own_lo > read_lo) {
         // ends <= own_lo belong to the previous rank: first key with end > own_lo

@@ -46,9 +46,11 @@ struct DfaDev {
 
 struct WalkLaunch {
   const uint8_t* hay;   // device pointer to haystack byte 0
+  uint64_t hay_len;     // bytes readable behind `hay`
   uint64_t span_start, span_end;
-  uint64_t seg_len;     // bytes owned per lane
-  uint64_t n_segs;
+  uint64_t seg_len;     // bytes owned per shard (a multiple of 16; a lane walks kWalkChains = 4 shards)
+  uint64_t n_segs;      // shards: shard k owns [origin + k * seg_len, + seg_len) cut to the span, origin = the
+                        // 16-byte boundary at or before hay + span_start
   uint64_t* keys;       // [cap]
   uint32_t* pids;       // [cap]
   unsigned long long* counter;  // total tuples wanted (may exceed cap => overflow)

@@ -27,6 +27,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n)
@@ -311,6 +312,12 @@ inline unsigned long long __shfl_sync(unsigned mask, unsigned long long v, int s
 // has no notion of convergence, so the caller alone it is.
 inline unsigned __activemask() { return 1u << (emu::g_cur->tid.x & 31); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return r;
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {

@@ -507,3 +507,22 @@ def test_verify_equality_vectors_of_packed_pattern_rs():
             assert [m.as_tuple() for m in searcher.find_iter(y + x + y + x)] == [(0, n, 2 * n), (0, 3 * n, 4 * n)]
     foo = packed.Searcher.new([b"foo"])
     assert foo.find(b"foobar").as_tuple() == (0, 0, 3) and foo.find(b"fobfo") is None
+
+
+def test_walk_engine_at_every_alignment():
+    """K1 walks four shards per lane on a 16-byte grid anchored below the span start: every pointer
+    phase x span start / end inside a block, spans shorter than one shard, 1-byte and empty patterns."""
+    pats = W.make_patterns(300, 21) + [b"a", b"ab", b""]
+    hay = np.empty(20 << 10, dtype=np.uint8)
+    W.fill_haystack(hay, 12, alphabet=(0x61, 0x66))
+    W.plant(hay, pats[:300], 13, period=128, window=64)
+    ac = build(pats, 0, engine=ab.Engine.Walk)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    backing = np.zeros(hay.size + 64, dtype=np.uint8)
+    for phase in (0, 1, 3, 7, 8, 15, 16, 17):
+        view = backing[phase:phase + hay.size]
+        view[:] = hay
+        for s, e in ((0, hay.size), (1, hay.size - 1), (5, 6), (17, 40), (33, 33), (4097, 9001), (hay.size - 3, hay.size)):
+            got, _ = ac.find_overlapping_iter_dev_np(view.ctypes.data, view.size, span=(s, e))
+            eq(got, o.find_overlapping_iter_np(view, span=(s, e)), (phase, s, e))
+            assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
