@@ -387,13 +387,17 @@ class AhoCorasickBuilder:
     def build(self, patterns):
         pats = [p.encode() if isinstance(p, str) else bytes(p) for p in patterns]
         n = len(pats)
-        arr = (C.c_char_p * max(n, 1))()
-        keep = []
-        for i, p in enumerate(pats):
-            b = C.create_string_buffer(p, max(len(p), 1))
-            keep.append(b)
-            arr[i] = C.cast(b, C.c_char_p)
-        lens = (_u64 * max(n, 1))(*[len(p) for p in pats])
+        # one contiguous buffer + a pointer per pattern (a ctypes object per pattern costs ~3 us each:
+        # a third of a second for the 100 000 patterns of BASELINE config 5)
+        lens_np = np.fromiter((len(p) for p in pats), dtype=np.uint64, count=n) if n else np.zeros(1, np.uint64)
+        blob = np.frombuffer(b"".join(pats) + b"\0", dtype=np.uint8)
+        offs = np.zeros(max(n, 1), dtype=np.uint64)
+        if n > 1:
+            np.cumsum(lens_np[:-1], out=offs[1:n])
+        ptrs = (offs + np.uint64(blob.ctypes.data)).astype(np.uint64)
+        arr = ptrs.ctypes.data_as(C.POINTER(C.c_char_p))
+        lens = lens_np.ctypes.data_as(C.POINTER(_u64))
+        keep = (blob, ptrs, lens_np)
         o = self._o
         opts = _BuildOpts(int(o["match_kind"]), int(o["start_kind"]), int(o["ascii_case_insensitive"]),
                           int(o["byte_classes"]), int(o["prefilter"]), int(o["kind"] or 0), o["dense_depth"])

@@ -3,8 +3,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -54,6 +57,7 @@ struct Workspace {
   uint64_t seq_cap = 0;
   uint64_t* h_seq = nullptr;
   uint64_t h_seq_cap = 0;
+  acg_stats stats{};  // of the search that holds (or last held) this workspace
 };
 
 }  // namespace
@@ -67,6 +71,7 @@ struct PrefilterPlan {
   uint32_t key_shift = 8;  // stride 2: first-stage hash = window * (mult3 << key_shift); 5: the key also
                            // holds the low 3 bits of the window's fourth byte (default; 8 with ACG_EXP_KEY24)
   bool wide = false;
+  bool anchor2 = false;  // stride 2, narrow: the second stage is the anchor-map lookup; the bitmap holds first-stage keys only
   bool brute = false;
   uint32_t dup_shift = 0;
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
@@ -76,6 +81,11 @@ struct PrefilterPlan {
   // anchor map: (k-byte haystack prefix -> trie state at depth k), open addressing, see DfaDev::amap
   std::vector<uint64_t> amap;  // low word = key, high word = premultiplied state id (0 = empty)
   uint32_t amap_log = 0;
+  // byte-set scan (bytescan_kernel): the needles of the reference's start-bytes / rare-bytes prefilter
+  // when it would have picked one (bs_n == 0: fingerprint filter)
+  uint32_t bs_n = 0;
+  uint8_t bs_byte[3] = {0, 0, 0};
+  uint8_t bs_back[3] = {0, 0, 0};
 };
 
 struct acg_dfa {
@@ -98,13 +108,93 @@ struct acg_dfa {
   DfaDev dev{};
   int engine_override = ACG_ENGINE_AUTO;
   uint64_t pipeline_chunk = 64ull << 20;  // H2D chunk of the pipelined host path (acg_debug_set_pipeline_chunk)
+  mutable bool bytescan_inert = false;    // the needles turned out to be frequent in a haystack: fingerprint filter from then on
   uint32_t experiment = 0;                // ACG_EXP_* kernel variants awaiting measurement (acg_debug_set_experiment)
-  mutable std::mutex mu;
-  mutable Workspace ws;
-  mutable acg_stats stats{};
+  mutable std::mutex mu;  // configuration (engine / experiment knobs, lazy table fetch) and the workspace pool
+  // Searches run through `&self` from many threads (the reference's automata are Send + Sync,
+  // src/lib.rs:274-326): every search leases a workspace -- its own stream pair, events, tuple
+  // buffers and haystack staging -- from this pool, so concurrent callers overlap on the device
+  // instead of queueing behind one mutex.  Workspaces are created on demand, at most kMaxWorkspaces.
+  static constexpr size_t kMaxWorkspaces = 4;
+  mutable std::vector<Workspace*> ws_all, ws_free;
+  mutable std::condition_variable ws_cv;
+  mutable acg_stats last_stats{};  // of the search that finished last (acg_last_stats from another thread)
 };
 
 namespace {
+
+// The workspace leased by the search running on this thread (WsLease below).
+thread_local Workspace* tls_ws = nullptr;
+thread_local const acg_dfa* tls_stats_owner = nullptr;
+thread_local acg_stats tls_stats{};
+Workspace& cur_ws() { return *tls_ws; }
+
+int init_workspace(Workspace& w) {
+  CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&w.ev0));
+  CK(cudaEventCreate(&w.ev1));
+  CK(cudaEventCreate(&w.ev2));
+  CK(cudaEventCreate(&w.ev3));
+  CK(cudaMalloc(&w.d_counter, 64));
+  CK(cudaMallocHost(&w.h_counter, 64));
+  return ACG_OK;
+}
+
+void destroy_workspace(Workspace& w) {
+  if (w.stream) cudaStreamSynchronize(w.stream);
+  for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
+  cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
+  cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);
+  if (w.h_counter) cudaFreeHost(w.h_counter);
+  if (w.h_keys) cudaFreeHost(w.h_keys);
+  if (w.h_pids) cudaFreeHost(w.h_pids);
+  if (w.h_seq) cudaFreeHost(w.h_seq);
+  if (w.ev0) cudaEventDestroy(w.ev0);
+  if (w.ev1) cudaEventDestroy(w.ev1);
+  if (w.ev2) cudaEventDestroy(w.ev2);
+  if (w.ev3) cudaEventDestroy(w.ev3);
+  if (w.stream) cudaStreamDestroy(w.stream);
+  if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+}
+
+// RAII lease of one workspace of the handle for the duration of a search.
+struct WsLease {
+  const acg_dfa* a;
+  Workspace* w = nullptr;
+  Workspace* prev;
+  int rc = ACG_OK;
+  explicit WsLease(const acg_dfa* a_) : a(a_), prev(tls_ws) {
+    std::unique_lock<std::mutex> lk(a->mu);
+    for (;;) {
+      if (!a->ws_free.empty()) { w = a->ws_free.back(); a->ws_free.pop_back(); break; }
+      if (a->ws_all.size() < acg_dfa::kMaxWorkspaces) {
+        w = new (std::nothrow) Workspace();
+        if (!w) { rc = ACG_E_NOMEM; return; }
+        a->ws_all.push_back(w);
+        lk.unlock();
+        int prev_dev = -1;
+        cudaGetDevice(&prev_dev);
+        if (prev_dev != a->device) cudaSetDevice(a->device);
+        rc = init_workspace(*w);
+        if (prev_dev != a->device && prev_dev >= 0) cudaSetDevice(prev_dev);
+        break;  // a half-initialised workspace stays in ws_all and is destroyed with the handle
+      }
+      a->ws_cv.wait(lk);
+    }
+    if (rc == ACG_OK) { w->stats = acg_stats{}; tls_ws = w; }
+  }
+  ~WsLease() {
+    if (!w) return;
+    tls_stats = w->stats;
+    tls_stats_owner = a;
+    tls_ws = prev;
+    std::lock_guard<std::mutex> lk(a->mu);
+    a->last_stats = w->stats;
+    if (rc == ACG_OK) a->ws_free.push_back(w);
+    a->ws_cv.notify_one();
+  }
+};
 
 int bits_for(uint64_t v) {
   int b = 0;
@@ -363,6 +453,10 @@ void derive_metadata(acg_dfa* a) {
           set_hash(bloom_hash2(g));
         }
       }
+      // ACG_EXP_ANCHOR2: leave the second stage to the anchor map -- the bitmap then carries the
+      // first-stage keys alone (cfg 2: ~13 000 bits of 2^20 instead of ~23 000)
+      pf.anchor2 = !pf.wide && (a->experiment & ACG_EXP_ANCHOR2) != 0 && paths4.size() <= (4u << 20);
+      if (pf.anchor2) std::fill(pf.bitmap.begin(), pf.bitmap.end(), 0u);
       // First-stage probe of the stride-2 kernel: byte index from the 3-byte fingerprint times
       // (mult3 << 8) -- the shifted multiplier discards the fourth window byte -- and the bit inside
       // the byte from the fingerprint's own low bits.  A multiplicative hash of such short keys is
@@ -460,6 +554,22 @@ void derive_metadata(acg_dfa* a) {
       pf.amap[slot] = uint64_t(key) | (uint64_t(it.row << s2) << 32);
     }
   }
+  // Byte-set scan for the automata the reference gives a start-bytes / rare-bytes prefilter
+  // (src/util/prefilter.rs:163-305).  Tables built here carry the set; for an adopted table that
+  // reports start bytes the set is read off the start row (the first bytes of all patterns).
+  if (h.prefilter_kind == ACG_PRE_START_BYTES || h.prefilter_kind == ACG_PRE_RARE_BYTES) {
+    if (h.pre_n) {
+      bool ok = true;
+      for (uint32_t i = 0; i < h.pre_n; ++i) ok = ok && h.pre_back[i] <= 15;
+      if (ok) {
+        pf.bs_n = h.pre_n;
+        for (uint32_t i = 0; i < h.pre_n; ++i) { pf.bs_byte[i] = h.pre_byte[i]; pf.bs_back[i] = h.pre_back[i]; }
+      }
+    } else if (h.prefilter_kind == ACG_PRE_START_BYTES && !level[1].empty() && grams[1].size() <= 3) {
+      pf.bs_n = uint32_t(grams[1].size());
+      for (uint32_t i = 0; i < pf.bs_n; ++i) { pf.bs_byte[i] = uint8_t(grams[1][i]); pf.bs_back[i] = 0; }
+    }
+  }
 }
 
 // Dense table produced on the device from the builder's DenseFillPlan (acb_build.hpp): one
@@ -502,7 +612,6 @@ int fill_table_on_device(acg_dfa* a) {
     p.edge_to = d_eto;
     p.n = hi - lo;
     e = acb::launch_dfa_fill_level(p, nullptr);  // default stream: levels run in order
-    a->stats.launches += 1;
   }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   release();
@@ -565,15 +674,6 @@ int upload(acg_dfa* a) {
   d.amap_mask = a->pf.amap_log ? (1u << a->pf.amap_log) - 1 : 0;
   d.amap_k = a->pf.k;
   d.amap_kmask = a->pf.kmask;
-  Workspace& w = a->ws;
-  CK(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&w.ev0));
-  CK(cudaEventCreate(&w.ev1));
-  CK(cudaEventCreate(&w.ev2));
-  CK(cudaEventCreate(&w.ev3));
-  CK(cudaMalloc(&w.d_counter, 64));
-  CK(cudaMallocHost(&w.h_counter, 64));
   a->on_device = true;
   return ACG_OK;
 }
@@ -666,7 +766,7 @@ struct TupleResult {
 // ws.d_keys[sorted_buf] / ws.d_pids[sorted_buf].
 int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uint64_t span_start,
                          uint64_t span_end, TupleResult* res) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   const uint64_t n_bytes = span_end - span_start;
   if (a->max_list_len >= (1u << acb::kTieBits)) return ACG_E_INVALID_ARG;
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
@@ -701,14 +801,14 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readab
     CK(cudaEventRecord(w.ev1, w.stream));
     CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
-    a->stats.launches += 1;
+    cur_ws().stats.launches += 1;
     const uint64_t want = *w.h_counter;
     if (want > w.cap) { cap = want + want / 8 + 1024; continue; }  // overflow: grow and rescan
     res->n = want;
-    a->stats.raw_matches = want;
+    cur_ws().stats.raw_matches = want;
     float ms = 0;
     cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-    a->stats.scan_ms = ms;
+    cur_ws().stats.scan_ms = ms;
     if (want > 1) {
       size_t tb = w.temp_bytes;
       const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
@@ -718,8 +818,8 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readab
       CK(cudaEventRecord(w.ev3, w.stream));
       CK(cudaStreamSynchronize(w.stream));
       cudaEventElapsedTime(&ms, w.ev2, w.ev3);
-      a->stats.order_ms = ms;
-      a->stats.launches += 8;  // radix passes (upper bound, library code)
+      cur_ws().stats.order_ms = ms;
+      cur_ws().stats.launches += 8;  // radix passes (upper bound, library code)
       res->sorted_buf = 1;
     } else {
       res->sorted_buf = 0;
@@ -733,7 +833,7 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readab
 int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable,
                             uint64_t span_start, uint64_t span_end, uint64_t scan_lo,
                             uint64_t scan_hi, int mode, int dev_sms) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   const PrefilterPlan& pf = a->pf;
   // 16-byte aligned filter region whose 4-byte look-ahead stays inside the readable bytes
   const uintptr_t base = reinterpret_cast<uintptr_t>(d_hay);
@@ -753,7 +853,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.stride = pf.stride;
   // kernel geometry as planned; second-stage organisation and tile distribution: see prefilter_kernel
   p.geom = pf.wide ? 1 : 0;
-  p.pair = (pf.stride == 2 && !pf.wide && (a->experiment & ACG_EXP_LOCAL2)) ? 2 : 0;
+  p.pair = (pf.stride == 2 && !pf.wide && pf.anchor2) ? 1 : 0;
   p.dyn = (a->experiment & ACG_EXP_STATIC_TILES) ? 0 : 1;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
@@ -774,16 +874,24 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.pids = w.d_pids[0];
   p.counter = w.d_counter;
   p.cap = w.cap;
-  CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
-  a->stats.launches += 1;
+  p.bs_n = 0;
+  for (int i = 0; i < 3; ++i) { p.bs_needle[i] = 0; p.bs_back[i] = 0; }
+  if (pf.bs_n && !a->bytescan_inert && !(a->experiment & ACG_EXP_NO_BYTESCAN)) {
+    p.bs_n = pf.bs_n;
+    for (uint32_t i = 0; i < pf.bs_n; ++i) { p.bs_needle[i] = uint32_t(pf.bs_byte[i]) * 0x01010101u; p.bs_back[i] = pf.bs_back[i]; }
+    CK(acb::launch_bytescan(a->dev, p, dev_sms, w.stream));
+  } else {
+    CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
+  }
+  cur_ws().stats.launches += 1;
   return ACG_OK;
 }
 
 // K4: order the appended tuples; `want` tuples sit in buffer 0.
 int order_tuples(const acg_dfa* a, uint64_t want, uint64_t n_bytes, TupleResult* res) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   res->n = want;
-  a->stats.raw_matches = want;
+  cur_ws().stats.raw_matches = want;
   if (want > 1) {
     size_t tb = w.temp_bytes;
     const int end_bit = std::min(64, acb::kTieBits + bits_for(n_bytes + 1));
@@ -794,8 +902,8 @@ int order_tuples(const acg_dfa* a, uint64_t want, uint64_t n_bytes, TupleResult*
     CK(cudaEventRecord(w.ev3, w.stream));
     CK(cudaStreamSynchronize(w.stream));
     cudaEventElapsedTime(&ms, w.ev2, w.ev3);
-    a->stats.order_ms = ms;
-    a->stats.launches += 8;  // radix passes (library code, upper bound)
+    cur_ws().stats.order_ms = ms;
+    cur_ws().stats.launches += 8;  // radix passes (library code, upper bound)
     res->sorted_buf = 1;
   } else {
     res->sorted_buf = 0;
@@ -812,7 +920,7 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
                   uint64_t span_end, int mode, TupleResult* res, const uint8_t* h_hay = nullptr,
                   uint64_t scan_lo = UINT64_MAX, uint64_t scan_hi = UINT64_MAX) {
   if (scan_lo == UINT64_MAX) { scan_lo = span_start; scan_hi = span_end; }
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   const uint64_t n_bytes = span_end - span_start;
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
@@ -857,10 +965,14 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
     CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 16, cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
     const uint64_t want = w.h_counter[0];
-    a->stats.candidates = w.h_counter[1];
+    cur_ws().stats.candidates = w.h_counter[1];
+    // the reference retires a prefilter that keeps reporting candidates (PrefilterState,
+    // src/util/prefilter.rs): needles in more than one offset out of eight => fingerprint filter next time
+    if (a->pf.bs_n && !a->bytescan_inert && scan_hi - scan_lo >= (1u << 16) && w.h_counter[1] > (scan_hi - scan_lo) / 8)
+      a->bytescan_inert = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-    a->stats.scan_ms = ms;  // with a host haystack this is the overlapped copy+scan time
+    cur_ws().stats.scan_ms = ms;  // with a host haystack this is the overlapped copy+scan time
     if (want > w.cap) { cap = want + want / 8 + 1024; continue; }
     return order_tuples(a, want, n_bytes, res);
   }
@@ -889,7 +1001,7 @@ int ensure_chain(Workspace& w, uint64_t n) {
 // FindIter over ordered candidate tuples, on the device: marks the tuples the reference's
 // iterator yields and compacts them into the other tuple buffer.
 int run_chain(const acg_dfa* a, int mode, TupleResult* r) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   if (r->n == 0) return ACG_OK;
   int rc = ensure_chain(w, r->n);
   if (rc) return rc;
@@ -916,8 +1028,8 @@ int run_chain(const acg_dfa* a, int mode, TupleResult* r) {
   CK(cudaStreamSynchronize(w.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, w.ev2, w.ev3);
-  a->stats.order_ms += ms;
-  a->stats.launches += 8;
+  cur_ws().stats.order_ms += ms;
+  cur_ws().stats.launches += 8;
   r->n = *w.h_counter;
   r->sorted_buf = dst;
   return ACG_OK;
@@ -926,7 +1038,7 @@ int run_chain(const acg_dfa* a, int mode, TupleResult* r) {
 // D2H + expansion of ordered (key,pid) tuples into acg_match / count / fnv.
 int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, acg_match* out,
                  uint64_t cap, uint64_t* n_out, uint64_t* fnv, int key_mode = 0) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   *n_out = r.n;
   if (fnv) *fnv = 0xcbf29ce484222325ull;
   if (r.n == 0) return ACG_OK;
@@ -940,7 +1052,7 @@ int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, ac
   CK(cudaStreamSynchronize(w.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-  a->stats.d2h_ms += ms;
+  cur_ws().stats.d2h_ms += ms;
   const uint32_t* plens = a->h.pattern_lens.data();
   uint64_t hsh = 0xcbf29ce484222325ull;
   auto mix = [&](uint64_t v) {
@@ -971,7 +1083,7 @@ int drain_tuples(const acg_dfa* a, const TupleResult& r, uint64_t span_start, ac
 
 int run_seq(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start, uint64_t span_end,
             int anchored, int earliest, int single, acg_match* out, uint64_t cap, uint64_t* n_out) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   uint64_t scap = std::max<uint64_t>(std::max<uint64_t>(cap, 1024), w.seq_cap);
   for (int attempt = 0; attempt < 4; ++attempt) {
     int rc = ensure_seq(w, scap);
@@ -992,13 +1104,13 @@ int run_seq(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start, uint64_
     CK(cudaEventRecord(w.ev1, w.stream));
     CK(cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream));
     CK(cudaStreamSynchronize(w.stream));
-    a->stats.launches += 1;
+    cur_ws().stats.launches += 1;
     float ms = 0;
     cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-    a->stats.scan_ms = ms;
+    cur_ws().stats.scan_ms = ms;
     const uint64_t n = *w.h_counter;
     *n_out = n;
-    a->stats.raw_matches = n;
+    cur_ws().stats.raw_matches = n;
     if (n > cap) return ACG_E_OVERFLOW;  // caller retries with a bigger buffer (two-call protocol)
     if (n > w.seq_cap) { scap = n; continue; }
     if (n) {
@@ -1020,7 +1132,7 @@ int run_seq(const acg_dfa* a, const uint8_t* d_hay, uint64_t span_start, uint64_
 // pointer that can be indexed with ABSOLUTE haystack offsets in that range.
 int stage_host_span(const acg_dfa* a, const uint8_t* hay, uint64_t span_start, uint64_t span_end,
                     const uint8_t** d_base, bool alloc_only = false) {
-  Workspace& w = a->ws;
+  Workspace& w = cur_ws();
   // keep the 16-byte phase of the host offsets so vector loads stay aligned
   const uint64_t lead = span_start & 15;
   const uint64_t bytes = span_end - span_start;
@@ -1035,7 +1147,7 @@ int stage_host_span(const acg_dfa* a, const uint8_t* hay, uint64_t span_start, u
   CK(cudaStreamSynchronize(w.stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, w.ev0, w.ev1);
-  a->stats.h2d_ms = ms;
+  cur_ws().stats.h2d_ms = ms;
   *d_base = w.d_hay + lead - span_start;  // never dereferenced outside [span_start, span_end)
   return ACG_OK;
 }
@@ -1081,14 +1193,14 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
   if (!a->on_device) return ACG_E_NO_DEVICE;
   if (fnv) *fnv = 0xcbf29ce484222325ull;
   if (span_start > span_end) return ACG_OK;  // Input::is_done
-  std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
-  a->stats = acg_stats{};
+  WsLease lease(a);
+  if (lease.rc) return lease.rc;
   int engine = a->engine_override;
   if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) return ACG_E_INVALID_ARG;
   if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
     engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
-  a->stats.engine = engine;
+  cur_ws().stats.engine = engine;
   const uint8_t* d_base = hay;
   uint64_t readable = hay_len;
   const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
@@ -1101,10 +1213,10 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
     rc = run_prefilter(a, d_base, readable, span_start, span_end, 0, &r, pipelined ? hay : nullptr);
   else rc = run_walk_overlapping(a, d_base, readable, span_start, span_end, &r);
   if (rc) return rc;
-  if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
+  if (kernel_ms) *kernel_ms = cur_ws().stats.scan_ms + cur_ws().stats.order_ms;
   if (devout) {
     // keep the matches on the device: drop ends <= min_end (owned by the previous shard), expand
-    Workspace& w = a->ws;
+    Workspace& w = cur_ws();
     uint64_t first = 0;
     if (r.n && devout->min_end > span_start) {
       const uint64_t bound_key = (devout->min_end - span_start + 1) << acb::kTieBits;  // first key with end > min_end
@@ -1127,7 +1239,7 @@ int overlapping_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, u
     e.out = static_cast<uint64_t*>(devout->d_out);
     CK(acb::launch_expand(e, w.stream));
     CK(cudaStreamSynchronize(w.stream));
-    a->stats.launches += 2;
+    cur_ws().stats.launches += 2;
     return ACG_OK;
   }
   return drain_tuples(a, r, span_start, out, cap, n_out, fnv);
@@ -1176,9 +1288,9 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
   uint64_t first = 0;
   uint64_t lspan_s = 0;
   {
-    std::lock_guard<std::mutex> lock(a->mu);
     DeviceGuard guard(a->device);
-    a->stats = acg_stats{};
+    WsLease lease(a);
+    if (lease.rc) return lease.rc;  // (a rank that cannot even get a stream cannot join the exchange either)
     if (covered && own_hi > own_lo) {
       lspan_s = read_lo - hay_off;
       const uint64_t lspan_e = own_hi - hay_off;
@@ -1186,7 +1298,7 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
       if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) engine = ACG_ENGINE_AUTO;
       if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
         engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
-      a->stats.engine = engine;
+      cur_ws().stats.engine = engine;
       const uint8_t* d_base = hay;
       uint64_t readable = hay_len;
       const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
@@ -1201,7 +1313,7 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
       }
       if (!rc && r.n && own_lo > read_lo) {
         // ends <= own_lo belong to the previous rank: first key with end > own_lo
-        Workspace& w = a->ws;
+        Workspace& w = cur_ws();
         const uint64_t bound_key = (own_lo - read_lo + 1) << acb::kTieBits;
         cudaError_t e = acb::launch_lower_bound(w.d_keys[r.sorted_buf], r.n, bound_key, w.d_counter, w.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream);
@@ -1231,7 +1343,7 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
     uint8_t* target = nullptr;
     if ((rc = acb::comm_record_target(c, my_off, mine, &target))) return rc;
     if (mine) {
-      Workspace& w = a->ws;
+      Workspace& w = cur_ws();
       acb::ExpandLaunch e;
       e.keys = w.d_keys[r.sorted_buf];
       e.pids = w.d_pids[r.sorted_buf];
@@ -1249,17 +1361,17 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
     float gms = 0;
     cudaEventElapsedTime(&gms, c->ev0, c->ev1);
     c->last_gather_ms = gms;
-    a->stats.launches += 3;
+    cur_ws().stats.launches += 3;
     *n_total = total;
     if (st) {
       st->local_matches = mine;
       st->total_matches = total;
-      st->candidates = a->stats.candidates;
-      st->scan_ms = a->stats.scan_ms;
-      st->order_ms = a->stats.order_ms;
+      st->candidates = cur_ws().stats.candidates;
+      st->scan_ms = cur_ws().stats.scan_ms;
+      st->order_ms = cur_ws().stats.order_ms;
       st->gather_ms = gms;
       st->transport = c->transport;
-      st->launches = a->stats.launches;
+      st->launches = cur_ws().stats.launches;
     }
     if (c->rank == 0) {
       if (d_matches) *d_matches = reinterpret_cast<const acg_match*>(c->recv_own);
@@ -1282,14 +1394,14 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   if ((rc = check_start(a->h, anchored))) return rc;  // FindIter::new, src/automaton.rs:861-870
   if (!a->on_device) return ACG_E_NO_DEVICE;
   if (span_start > span_end) return ACG_OK;
-  std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
-  a->stats = acg_stats{};
+  WsLease lease(a);
+  if (lease.rc) return lease.rc;
   int engine = a->engine_override;
   if (engine == ACG_ENGINE_PREFILTER && (!a->pf.supported || anchored)) return ACG_E_INVALID_ARG;
   if (engine != ACG_ENGINE_SEQUENTIAL && engine != ACG_ENGINE_PREFILTER)
     engine = (a->pf.supported && !anchored) ? ACG_ENGINE_PREFILTER : ACG_ENGINE_SEQUENTIAL;
-  a->stats.engine = engine;
+  cur_ws().stats.engine = engine;
   const uint8_t* d_base = hay;
   uint64_t readable = hay_len;
   const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
@@ -1299,7 +1411,7 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   }
   if (engine == ACG_ENGINE_SEQUENTIAL) {
     rc = run_seq(a, d_base, span_start, span_end, anchored, 0, 0, out, cap, n_out);
-    if (kernel_ms) *kernel_ms = a->stats.scan_ms;
+    if (kernel_ms) *kernel_ms = cur_ws().stats.scan_ms;
     return rc;
   }
   // Standard: all occurrences in (end, len desc, list) order, then the iterator's greedy choice;
@@ -1309,7 +1421,7 @@ int find_iter_impl(const acg_dfa* a, const uint8_t* hay, bool hay_on_device, uin
   if ((rc = run_prefilter(a, d_base, readable, span_start, span_end, mode == 0 ? 2 : 1, &r, pipelined ? hay : nullptr)))
     return rc;
   if ((rc = run_chain(a, mode, &r))) return rc;
-  if (kernel_ms) *kernel_ms = a->stats.scan_ms + a->stats.order_ms;
+  if (kernel_ms) *kernel_ms = cur_ws().stats.scan_ms + cur_ws().stats.order_ms;
   return drain_tuples(a, r, span_start, out, cap, n_out, nullptr, mode);
 }
 
@@ -1348,13 +1460,24 @@ static int build_common(const uint8_t* const* patterns, const uint64_t* lens, ui
   acg_dfa* a = new (std::nothrow) acg_dfa();
   if (!a) return ACG_E_NOMEM;
   int rc = ACG_OK;
+  static const bool trace = std::getenv("ACB_BUILD_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "acb200 build: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+    t0 = now;
+  };
   try {
     rc = acb::build_dfa(pats, bo, &a->h);
+    lap("build_dfa total");
     if (rc == ACG_OK) derive_metadata(a);
+    lap("derive_metadata (device plan)");
   } catch (const std::bad_alloc&) {
     rc = ACG_E_NOMEM;
   }
   if (rc == ACG_OK && to_device) rc = upload(a);
+  lap("upload / device fill");
   if (rc != ACG_OK) { acg_dfa_free(a); return rc; }
   *out = a;
   return ACG_OK;
@@ -1453,23 +1576,9 @@ void acg_dfa_free(acg_dfa* a) {
   if (!a) return;
   if (a->on_device || a->dev_touched) {
     DeviceGuard guard(a->device);
-    Workspace& w = a->ws;
-    if (w.stream) cudaStreamSynchronize(w.stream);
+    for (Workspace* w : a->ws_all) { destroy_workspace(*w); delete w; }
     cudaFree(a->d_trans); cudaFree(a->d_classes); cudaFree(a->d_moff); cudaFree(a->d_mpids);
     cudaFree(a->d_plens); cudaFree(a->d_depth16); cudaFree(a->d_bitmap); cudaFree(a->d_amap);
-    for (int i = 0; i < 2; ++i) { cudaFree(w.d_keys[i]); cudaFree(w.d_pids[i]); }
-    cudaFree(w.d_counter); cudaFree(w.d_temp); cudaFree(w.d_hay); cudaFree(w.d_seq);
-    cudaFree(w.d_scratch); cudaFree(w.d_flags); cudaFree(w.d_temp2);
-    if (w.h_counter) cudaFreeHost(w.h_counter);
-    if (w.h_keys) cudaFreeHost(w.h_keys);
-    if (w.h_pids) cudaFreeHost(w.h_pids);
-    if (w.h_seq) cudaFreeHost(w.h_seq);
-    if (w.ev0) cudaEventDestroy(w.ev0);
-    if (w.ev1) cudaEventDestroy(w.ev1);
-    if (w.ev2) cudaEventDestroy(w.ev2);
-    if (w.ev3) cudaEventDestroy(w.ev3);
-    if (w.stream) cudaStreamDestroy(w.stream);
-    if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
   }
   delete a;
 }
@@ -1555,6 +1664,9 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
   out->amap = pf.amap.data(); out->amap_log = pf.amap_log;
   out->depth16 = a->depth16.data(); out->n_rows = a->depth16.size();
   out->dup_shift = pf.dup_shift;
+  out->bs_n = (pf.bs_n && !a->bytescan_inert) ? pf.bs_n : 0;
+  for (int i = 0; i < 3; ++i) { out->bs_byte[i] = pf.bs_byte[i]; out->bs_back[i] = pf.bs_back[i]; }
+  out->anchor2 = pf.anchor2 ? 1 : 0;
   return ACG_OK;
 }
 
@@ -1565,11 +1677,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_LOCAL2 | ACG_EXP_STATIC_TILES))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_ANCHOR2 | ACG_EXP_STATIC_TILES | ACG_EXP_NO_BYTESCAN))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;
-  if (changed & ACG_EXP_KEY24) {
+  if (changed & (ACG_EXP_KEY24 | ACG_EXP_ANCHOR2)) {
     // the first-stage keys are part of the plan: rebuild it and refresh the device copy of the bitmap
     const size_t old_words = a->pf.bitmap.size();
     derive_metadata(a);
@@ -1590,10 +1702,17 @@ int acg_set_engine(acg_dfa* a, int engine) {
   a->engine_override = engine;
   return ACG_OK;
 }
-int acg_last_engine(const acg_dfa* a) { return a ? a->stats.engine : 0; }
+// Statistics of the most recent search on this handle: the calling thread's own last search if it
+// made one (concurrent callers do not see each other's numbers), else the search that finished last.
+static acg_stats stats_for(const acg_dfa* a) {
+  if (tls_stats_owner == a) return tls_stats;
+  std::lock_guard<std::mutex> lk(a->mu);
+  return a->last_stats;
+}
+int acg_last_engine(const acg_dfa* a) { return a ? stats_for(a).engine : 0; }
 int acg_last_stats(const acg_dfa* a, acg_stats* out) {
   if (!a || !out) return ACG_E_INVALID_ARG;
-  *out = a->stats;
+  *out = stats_for(a);
   return ACG_OK;
 }
 
@@ -1654,17 +1773,17 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
   // unanchored try_find returns what the prefilter reports, a confirmed leftmost match
   // (Candidate::Match, src/automaton.rs:1304-1309), whether or not `earliest` was asked for.
   if (earliest && !anchored && a->h.match_kind != ACG_STANDARD && a->h.prefilter_kind == ACG_PRE_PACKED) earliest = 0;
-  std::lock_guard<std::mutex> lock(a->mu);
   DeviceGuard guard(a->device);
-  a->stats = acg_stats{};
-  Workspace& w = a->ws;
+  WsLease lease(a);
+  if (lease.rc) return lease.rc;
+  Workspace& w = cur_ws();
   // `earliest` on a leftmost automaton reports the first match STATE entered (src/automaton.rs
   // :1381-1383), which the per-start formulation does not model: sequential engine.
   const bool use_pf = a->pf.supported && !anchored && a->engine_override != ACG_ENGINE_SEQUENTIAL &&
                       !(earliest && a->h.match_kind != ACG_STANDARD);
   const uint8_t* d_base = nullptr;
   if (!use_pf) {
-    a->stats.engine = ACG_ENGINE_SEQUENTIAL;
+    cur_ws().stats.engine = ACG_ENGINE_SEQUENTIAL;
     if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base))) return rc;
     uint64_t n = 0;
     rc = run_seq(a, d_base, span_start, span_end, anchored, earliest, 1, out, 1, &n);
@@ -1674,7 +1793,7 @@ int acg_find(const acg_dfa* a, const uint8_t* hay, uint64_t hay_len, uint64_t sp
   // The reference's try_find is lazy (it stops reading at the first match, SURVEY.md section
   // 7h); the eager device scan therefore works through geometrically growing windows of start
   // offsets (1 MiB, 16 MiB, 256 MiB, ...), copying only what a window needs.
-  a->stats.engine = ACG_ENGINE_PREFILTER;
+  cur_ws().stats.engine = ACG_ENGINE_PREFILTER;
   if ((rc = stage_host_span(a, hay, span_start, span_end, &d_base, true))) return rc;
   const int mode = a->h.match_kind == ACG_STANDARD ? 0 : 1;
   const uint64_t look = a->h.max_pattern_len + 64;

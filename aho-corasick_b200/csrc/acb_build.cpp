@@ -6,6 +6,9 @@
 #include "acb_build.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 
@@ -103,6 +106,15 @@ class PrefilterChooser {
     }
   }
 
+  // The bytes (ascending) and offsets of the prefilter `kind` that choose() returned.
+  void byte_set(int kind, uint32_t* n, uint8_t bytes[3], uint8_t back[3]) const {
+    *n = 0;
+    const bool* set = kind == kPreStartBytes ? start_set_ : (kind == kPreRareBytes ? rare_set_ : nullptr);
+    if (!set) return;
+    for (int b = 0; b < 256 && *n < 3; ++b)
+      if (set[b]) { bytes[*n] = uint8_t(b); back[*n] = kind == kPreRareBytes ? max_off_[b] : 0; ++*n; }
+  }
+
   int choose(PackedPlan* plan) const {  // Builder::build :163-305
     *plan = PackedPlan{};
     if (!enabled_) return kPreNone;
@@ -163,14 +175,20 @@ class PrefilterChooser {
     if (!rare_ok_) return;
     if (rare_count_ > 3 || n >= 256) { rare_ok_ = false; return; }
     uint8_t best = p[0], best_rank = rank_of(p[0]);
+    bool found = false;
     for (uint64_t i = 0; i < n; ++i) {
-      if (rare_set_[p[i]]) return;  // an already chosen rare byte occurs in this pattern
+      set_offset(i, p[i]);  // RareByteOffsets::set keeps the maximum, for every byte of every pattern (:634-641)
+      if (ci_) set_offset(i, flip_ascii_case(p[i]));
+      if (found) continue;
+      if (rare_set_[p[i]]) { found = true; continue; }  // an already chosen rare byte occurs in this pattern
       uint8_t r = rank_of(p[i]);
       if (r < best_rank) { best = p[i]; best_rank = r; }
     }
+    if (found) return;
     mark_rare(best);
     if (ci_) mark_rare(flip_ascii_case(best));
   }
+  void set_offset(uint64_t pos, uint8_t b) { if (pos > max_off_[b]) max_off_[b] = uint8_t(pos); }
   bool rare_available() const {  // RareBytesBuilder::build :535-575
     return rare_ok_ && rare_count_ <= 3 && rare_count_ != 0;
   }
@@ -182,6 +200,7 @@ class PrefilterChooser {
   unsigned start_count_ = 0;
   uint16_t start_rank_sum_ = 0;
   bool rare_set_[256] = {false};
+  uint8_t max_off_[256] = {0};
   bool rare_ok_ = true;
   unsigned rare_count_ = 0;
   uint16_t rare_rank_sum_ = 0;
@@ -192,6 +211,15 @@ class PrefilterChooser {
 }  // namespace
 
 int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts, HostDfa* out) {
+  // ACB_BUILD_TRACE=1: phase times on stderr (where a 100 000-pattern build spends its second)
+  static const bool trace = std::getenv("ACB_BUILD_TRACE") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "acb200 build: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   const bool leftmost = opts.match_kind != kStandard;
   const bool ci = opts.ascii_case_insensitive;
   HostDfa& d = *out;
@@ -245,6 +273,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     if (!shadowed) t.hits[cur].push_back(uint32_t(pid));
   }
   const size_t ns = t.edges.size();
+  lap("trie");
 
   // byte classes (src/util/alphabet.rs:235-250); `byte_classes(false)` => singletons (src/dfa.rs:436-440)
   uint8_t nfa_classes[256];
@@ -293,6 +322,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     }
   }
   t.root_loop_closed = leftmost && !t.hits[kRoot].empty();
+  lap("failure links + match lists");
 
   // ---- state permutation: DEAD, FAIL, MATCH.., START_U, START_A, NON-MATCH.. (:1399-1481) ----
   // `slot[pos]` = trie node sitting at state index pos after the reference's swap sequence.
@@ -311,7 +341,9 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   if (!t.hits[kAnchoredRoot].empty()) n_max_match = n_start_a;
   for (size_t i = 0; i < ns; ++i) newid[slot[i]] = uint32_t(i);
 
+  lap("state permutation");
   d.prefilter_kind = chooser.choose(&d.packed);
+  chooser.byte_set(d.prefilter_kind, &d.pre_n, d.pre_byte, d.pre_back);
   const uint32_t n_max_special = d.prefilter_kind != kPreNone ? n_start_a : n_max_match;  // :1036-1045
 
   // auto-selection as reported by AhoCorasick::kind() (src/ahocorasick.rs:2213-2261)
@@ -460,6 +492,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     d.start_anchored_id = map_a[n_start_a];
   }
 
+  lap("dense table / fill plan");
   // CSR of `matches: Vec<Vec<PatternID>>` (src/dfa.rs:96-99)
   d.match_offsets.assign(n_match_states + 1, 0);
   size_t total = 0;
@@ -467,6 +500,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   d.match_offsets[n_match_states] = uint32_t(total);
   d.match_pids.reserve(total);
   for (auto& l : mlists) d.match_pids.insert(d.match_pids.end(), l.begin(), l.end());
+  lap("match CSR");
   return 0;
 }
 

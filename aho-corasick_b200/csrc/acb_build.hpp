@@ -74,6 +74,13 @@ struct HostDfa {
   uint64_t state_len = 0;
   int prefilter_kind = kPreNone;
   PackedPlan packed;
+  // The byte set of the reference's start-bytes / rare-bytes prefilter when it picks one of them
+  // (src/util/prefilter.rs:535-575, 784-824): up to three bytes; pre_back[i] = the largest offset at
+  // which pre_byte[i] occurs in any pattern (RareByteOffsets, :460-520; 0 for start bytes), i.e. a
+  // pattern that shows the byte at haystack offset q starts in [q - pre_back[i], q].
+  uint32_t pre_n = 0;
+  uint8_t pre_byte[3] = {0, 0, 0};
+  uint8_t pre_back[3] = {0, 0, 0};
   // Trie depth of every table row that is reachable from the unanchored start state (0xFFFF for
   // the others), when the builder knows it (unanchored start kind); empty otherwise.  Equals the
   // BFS distance from the start row that acb_api.cu derives for adopted tables.

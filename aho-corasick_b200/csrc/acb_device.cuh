@@ -128,11 +128,18 @@ struct PrefilterLaunch {
   unsigned long long* counter;  // [0] tuples, [1] candidates
   uint64_t cap;
   uint32_t dyn;                 // 1: the warps of a CTA draw their tiles from a shared counter (see prefilter_kernel)
+  // byte-set scan (bytescan_kernel, the memchr-class start-bytes / rare-bytes prefilter): bs_n needles,
+  // each replicated into the four bytes of a word; a pattern that shows needle i at offset q starts in
+  // [q - bs_back[i], q] (0 for start bytes, <= 15)
+  uint32_t bs_n;
+  uint32_t bs_needle[3];
+  uint32_t bs_back[3];
   uint32_t key_shift;           // stride 2: first-stage hash = window * (mult3 << key_shift).  8: the fourth window
                                 // byte drops out (3-byte keys); 5: its low 3 bits stay in the key (experiment).
                                 // Last member, so that the layout of the measured kernels' parameters is unchanged.
 };
 cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s);
+cudaError_t launch_bytescan(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s);
 
 // Non-overlapping iteration (FindIter, src/automaton.rs:857-936) over ordered candidate tuples.
 // mode 1 (leftmost): keys = (start_rel << 24 | len), sorted by start;

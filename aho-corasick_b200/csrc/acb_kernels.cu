@@ -95,16 +95,14 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   for (int64_t j = 0; j < n_blocks; ++j) {
     const int64_t blk0 = g00 - back16 + (j << 4);  // this block of chain 0
     const bool warm = (j << 4) < back16;           // cold-start run-in: nothing is reported
-    bool checked = true;
     // every chain has a whole block inside the span (then also inside its shard): 16 x 4 transitions
-    // with no per-byte checks, tracking only the smallest state id seen -- match states are the
-    // smallest ids (src/dfa.rs:229-247), so one comparison per block tells whether anything is to
-    // be reported, and the rare block that has something is walked again by the careful loop below
+    // with no per-byte checks, tracking only the smallest state id each chain saw -- match states are
+    // the smallest ids (src/dfa.rs:229-247), so one comparison per chain and block tells whether
+    // anything is to be reported; the rare chain that has something walks its 16 bytes again, carefully
     if (blk0 >= span_start && blk0 + (kWalkChains - 1) * seg_len + 16 <= span_end) {
-      uint32_t at[kWalkChains];
+      uint32_t at[kWalkChains], lowest[kWalkChains];
 #pragma unroll
-      for (int c = 0; c < kWalkChains; ++c) at[c] = sid[c];
-      uint32_t lowest = 0xFFFFFFFFu;
+      for (int c = 0; c < kWalkChains; ++c) { at[c] = sid[c]; lowest[c] = 0xFFFFFFFFu; }
       const uint8_t* src = hay + blk0;
 #pragma unroll 1
       for (int wi = 0; wi < 4; ++wi, src += 4) {  // rolled: keeps the live set to one word per chain
@@ -117,19 +115,26 @@ walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
           for (int c = 0; c < kWalkChains; ++c) {
             const uint32_t b = __byte_perm(w[c], 0, 0x4440 + k);
             sid[c] = __ldg(trans + sid[c] + s_cls[b]);
-            lowest = min(lowest, sid[c]);
+            lowest[c] = min(lowest[c], sid[c]);
           }
         }
       }
-      checked = lowest <= max_match && !warm;
-      if (checked) {
+      if (!warm) {
 #pragma unroll
-        for (int c = 0; c < kWalkChains; ++c) sid[c] = at[c];
+        for (int c = 0; c < kWalkChains; ++c) {
+          if (lowest[c] > max_match) continue;
+          uint32_t s = at[c];
+          const int64_t pos0 = blk0 + c * seg_len;
+#pragma unroll 1
+          for (int k = 0; k < 16; ++k) {
+            s = __ldg(trans + s + s_cls[hay[pos0 + k]]);
+            if (s <= max_match && s != 0) report(s, pos0 + k);
+          }
+        }
       }
-    }
-    if (checked) {
-      // a block with a match state in it, one that crosses the span's edges, or shards that do not
-      // exist: byte by byte, nothing outside [cold start, shard end) is read
+    } else {
+      // a block that crosses the span's edges, or shards that do not exist: byte by byte, nothing
+      // outside [cold start, shard end) is read
 #pragma unroll 1
       for (int k = 0; k < 16; ++k) {
 #pragma unroll

@@ -218,44 +218,46 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-// Second-stage organisation S2 (stride 2 only):
-//   0  compacted (hit, start offset) items, one per lane: ballot prefix sum, per-warp slot queue
-//   2  LOCAL: no compaction at all -- every lane walks its own hit mask, both start offsets per
-//      hit; the warp loops while any lane has a hit left.  Drops the ballot prefix sum, the slot
-//      queue and its decode; pays with idle lanes.  r02 A/B: loses on cfg 2, wins on cfg 3 together
-//      with 27-bit keys (profiles/r02a_ab_cfg3.jsonl).
+// Second-stage organisation S2 (stride 2, narrow geometry):
+//   0  compacted (hit, start offset) items, one per lane, tested with two more Bloom hashes of the
+//      4-byte fingerprint in the shared-memory bitmap
+//   1  ANCHOR: the same items looked up in the anchor map instead (exact: one L2 access tells whether
+//      the 4 bytes begin a pattern and at which trie state) -- the bitmap then holds first-stage keys
+//      only, which lowers its density and with it the first-stage hits per step
+// (A lane-local second stage without compaction was measured in r02 and lost on cfg 2 and, once the
+// 27-bit keys were in, on cfg 3: profiles/r02a_ab_*.jsonl, r02b_cfg3.jsonl.)
 // Tile distribution DYN: false -- warp w of a CTA takes the tiles w, w + W, w + 2W, ... of the CTA's
 // chunk; true -- the warps of a CTA draw tile numbers from a shared-memory counter.  With the static
 // split the warps of a CTA finish up to 25 % apart (ncu r02a: 27.8 of 32 warps active on average,
 // the least busy SM sub-partition active 74 % of the kernel), because the scheduler favours some
 // warps and nothing hands their neighbours' work over; the kernel ends with its slowest warp.
-enum : int { kS2Compact = 0, kS2Local = 2 };
+enum : int { kS2Compact = 0, kS2Anchor = 1 };
 template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact, bool DYN = false>
 __global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
-  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the lane-local second stage belongs to the stride-2 first stage");
-  constexpr bool LOCAL = S2 == kS2Local;
+  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the anchor second stage is an option of the stride-2 first stage (dense sets always use it)");
+  constexpr bool ANCH = DENSE || S2 == kS2Anchor;  // second stage = anchor-map lookup, queue entries carry the trie state
   constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
   constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
   constexpr int kPfTile = PfGeom<GEOM>::kTile;
   constexpr int kPfStageBytes = PfGeom<GEOM>::kStageBytes;
   constexpr int kGroups = PfGeom<GEOM>::kGroups;
   constexpr int kPfSlots = PfCfg<DENSE>::kSlots;
-  constexpr int kSlotsAlloc = LOCAL ? 0 : kPfSlots;  // the lane-local second stage keeps no slot queue
-  constexpr int kPfQ2 = PfCfg<DENSE>::kQ2;
+  constexpr int kSlotsAlloc = kPfSlots;
+  constexpr int kPfQ2 = PfCfg<ANCH>::kQ2;
   constexpr uint32_t kBloomShift = PfBloom<GEOM>::kShift;
-  using Q2Entry = typename std::conditional<DENSE, uint2, uint32_t>::type;  // (offset[, trie state of its first k bytes])
+  using Q2Entry = typename std::conditional<ANCH, uint2, uint32_t>::type;  // (offset[, trie state of its first k bytes])
   ACB_DYNAMIC_SMEM(smem_raw);
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
   uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
-  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_bars + kPfWarps * kPfStages);  // [kPfWarps][kPfQ2]
+  uint32_t* s_tile_of = reinterpret_cast<uint32_t*>(s_bars + kPfWarps * kPfStages);  // DYN: tile number staged in [warp][stage]
+  uint32_t* s_next_tile = s_tile_of + kPfWarps * kPfStages;                        // DYN: next tile number of this CTA's chunk (+ pad)
+  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_next_tile + 2);  // [kPfWarps][kPfQ2]
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kSlotsAlloc]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kSlotsAlloc);
   __shared__ uint8_t s_cls[256];
-  __shared__ uint32_t s_next_tile;                  // DYN: next tile number of this CTA's chunk
-  __shared__ uint32_t s_tile_of[32 * kPfStages];   // DYN: tile number staged in [warp][stage]
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -264,7 +266,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
   if (tid < kPfWarps * kPfStages) ptx::mbar_init(ptx::smem_addr(&s_bars[tid]), 1);
-  if (tid == 0) s_next_tile = 0;
+  if (tid == 0) *s_next_tile = 0;
   ptx::mbar_init_fence();
   ptx::fence_proxy_async();
   __syncthreads();
@@ -318,7 +320,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   auto drain2 = [&]() {  // verify the queued survivors (K3b), one per lane
     __syncwarp();
     for (uint32_t i = lane; i < q2len; i += 32) {
-      if constexpr (DENSE) {
+      if constexpr (ANCH) {
         // (offset, trie state of its first k bytes): the anchor map was consulted when the entry was queued
         const uint2 e = q2[i];
         if (e.y != 0) verify_from<MODE>(d, p, s_cls, chunk_base + e.x, e.y, d.amap_k, em);
@@ -356,11 +358,20 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     ptx::mbar_arrive_expect_tx(bar, bytes);
     ptx::tma_load_1d(dst, chunk_src + (uint64_t)t * kPfTile, bytes, bar);
   };
-  // DYN: lane 0 draws the tile number for a stage from the CTA's counter, leaves it in
-  // s_tile_of[warp][stage] for the warp to read when it gets to that stage, and requests the tile
+  // DYN: lane 0 draws tile numbers from the CTA's counter -- kDrawBatch consecutive tiles per atomic
+  // -- leaves the number for a stage in s_tile_of[warp][stage] for the warp to read when it gets to
+  // that stage, and requests the tile
+  constexpr uint32_t kDrawBatch = 4;
   uint32_t* tile_of = s_tile_of + warp * kPfStages;
+  const uint32_t next_tile_a = ptx::smem_addr(s_next_tile);
+  uint32_t batch_next = 0, batch_left = 0;  // lane 0's current batch
   auto draw = [&](uint32_t stage) {  // lane 0 only
-    const uint32_t t = atomicAdd(&s_next_tile, 1u);
+    if (batch_left == 0) {
+      batch_next = ptx::atoms_add(next_tile_a, kDrawBatch);
+      batch_left = kDrawBatch;
+    }
+    const uint32_t t = batch_next++;
+    --batch_left;
     tile_of[stage] = t;
     if (t < n_tiles) issue(t, stage);
   };
@@ -459,14 +470,13 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     const uint32_t lt = (1u << lane) - 1;
     constexpr int kPlanes = DENSE ? 4 : 3;  // per-lane hit counts the ballot prefix sum covers (dense: 32 probes per lane)
     uint32_t slot = 0, total = 0;
-    constexpr int kSumPlanes = LOCAL ? 0 : kPlanes;  // the lane-local second stage needs no slots
+    constexpr int kSumPlanes = kPlanes;
 #pragma unroll
     for (int b = 0; b < kSumPlanes; ++b) {
       const uint32_t bl = __ballot_sync(0xffffffffu, (cnt >> b) & 1u);
       slot += __popc(bl & lt) << b;
       total += __popc(bl) << b;
     }
-    if constexpr (LOCAL) total = __any_sync(0xffffffffu, mask != 0) ? 1u : 0u;  // only "is there anything to do"
     if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
       // the very first probe of the region has no start before it
@@ -484,57 +494,6 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         }
         cand_total += __reduce_add_sync(0xffffffffu, nver);
       } else {
-        // LOCAL: both start offsets of the hit at tile offset e (even), tested by one lane
-        auto survives = [&](uint32_t gram) -> bool {
-          if (MASKED) gram = (gram | fold) & kmask;
-          return bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
-        };
-        auto test_hit = [&](uint32_t e, bool& pass0, bool& pass1) {
-          if (e == 0) {
-            // the odd start lies one byte before the tile (at most one hit per step): no second
-            // probe, the verifier decides -- unless it would fall before the filter region
-            pass0 = survives(ptx::lds32(tile_a));
-            pass1 = !region_first;
-          } else {
-            // e is even: the bytes e-1 .. e+3 lie in the two words around (e-1) & ~3
-            const uint32_t o1 = e - 1;
-            const uint32_t sa = tile_a + (o1 & ~3u);
-            const uint32_t lo = ptx::lds32(sa), hi = ptx::lds32(sa + 4);
-            const uint32_t sh = (o1 & 3u) * 8;  // 8 or 24
-            pass1 = survives(__funnelshift_r(lo, hi, sh));
-            pass0 = survives(__funnelshift_rc(lo, hi, sh + 8));  // shift 32 (e word aligned) -> hi
-          }
-        };
-        auto queue_pair = [&](uint32_t wrel, uint32_t e, bool pass0, bool pass1) {  // warp-uniform call
-          if constexpr (!DENSE) {
-            const uint32_t bal0 = __ballot_sync(0xffffffffu, pass0);
-            const uint32_t bal1 = __ballot_sync(0xffffffffu, pass1);
-            if (bal0) {
-              if (pass0) q2[q2len + __popc(bal0 & lt)] = wrel + e;
-              q2len += __popc(bal0);
-              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
-            }
-            if (bal1) {
-              if (pass1) q2[q2len + __popc(bal1 & lt)] = wrel + e - 1;
-              q2len += __popc(bal1);
-              if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
-            }
-          }
-        };
-        if constexpr (LOCAL) {
-          // every lane walks its own hits; the warp iterates while any lane has one left
-          while (__any_sync(0xffffffffu, mask != 0)) {
-            bool pass0 = false, pass1 = false;
-            uint32_t e = 0;
-            if (mask) {
-              const uint32_t b = (uint32_t)__ffs(mask) - 1;
-              mask &= mask - 1;
-              e = hit_offset(b, (uint32_t)lane);
-              test_hit(e, pass0, pass1);
-            }
-            queue_pair((uint32_t)(wbase - chunk_lo) + rel_bias, e, pass0, pass1);
-          }
-        } else {
         // hit t of the step is recorded as (lane << 5 | bit); the consumer decodes the offset
         {
           uint16_t* sp = slots + slot;
@@ -567,8 +526,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
               const uint32_t off = e - j;
               const uint32_t sa = tile_a + (off & ~3u);
               uint32_t gram = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8);
-              if constexpr (DENSE) {
-                // dense sets: the exact answer is one L2 access away -- the anchor map says whether
+              if constexpr (ANCH) {
+                // the exact answer is one L2 access away -- the anchor map says whether
                 // the k bytes at the offset begin a pattern, and at which trie state
                 const uint64_t s0 = chunk_base + (wrel + e - j);
                 if (d.amap == nullptr) pass = true;
@@ -589,14 +548,13 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
           if (bal) {
             if (pass) {
               const uint32_t rel = wrel + e - j;
-              if constexpr (DENSE) q2[q2len + __popc(bal & lt)] = make_uint2(rel, gram_keep);
+              if constexpr (ANCH) q2[q2len + __popc(bal & lt)] = make_uint2(rel, gram_keep);
               else q2[q2len + __popc(bal & lt)] = rel;
             }
             q2len += __popc(bal);
             if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
           }
         }
-        }  // !LOCAL
       }
     }
     __syncwarp();  // every lane is done with this stage: refill it with the tile two steps ahead
@@ -607,6 +565,141 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   }
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
+}
+
+// ---- byte-set scan: the memchr-class prefilters ------------------------------------------------
+// The reference skips ahead with memchr / memchr2 / memchr3 over the patterns' start bytes or over
+// up to three "rare" bytes with their largest offsets (src/util/prefilter.rs:665-731, 855-904, chosen
+// by :163-305 for automata with at most three such bytes), and runs the automaton from each
+// candidate.  The same first stage here is a streaming compare: every lane takes 16 bytes per step
+// (one coalesced 512-byte load per warp), flags the bytes that equal a needle with three integer
+// instructions per word and needle, and the flagged offsets -- widened to the start offsets
+// [q - back, q] they can belong to -- go through the same per-warp queue and anchored DFA verifier
+// (K3b) as the fingerprint prefilter's survivors.  No shared-memory table, no staging: the kernel is
+// bound by the haystack read as long as the needles are as rare as the reference's heuristics assume.
+constexpr int kBsThreads = 512;
+constexpr int kBsWarps = kBsThreads / 32;
+constexpr int kBsQueue = 128;  // queued start offsets per warp (8 bytes each)
+
+template <int MODE>
+__global__ void __launch_bounds__(kBsThreads, 2) bytescan_kernel(DfaDev d, PrefilterLaunch p) {
+  __shared__ uint8_t s_cls[256];
+  __shared__ uint64_t s_q[kBsWarps * kBsQueue];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 256) s_cls[tid] = d.classes[tid];
+  __syncthreads();
+  Emitter em{p.keys, p.pids, p.counter, p.cap};
+  unsigned long long cand_total = 0;
+  // head / tail positions outside the aligned region are unconditional candidates
+  if (blockIdx.x == 0) {
+    const uint64_t head_n = p.region_lo - p.scan_lo;
+    const uint64_t tail_n = p.scan_hi > p.region_hi ? p.scan_hi - p.region_hi : 0;
+    for (uint64_t i = tid; i < head_n + tail_n; i += kBsThreads)
+      verify_at<MODE>(d, p, s_cls, i < head_n ? p.scan_lo + i : p.region_hi + (i - head_n), em);
+  }
+  uint64_t* q = s_q + warp * kBsQueue;
+  uint32_t qlen = 0;  // warp-uniform
+  auto drain = [&]() {
+    __syncwarp();
+    for (uint32_t i = lane; i < qlen; i += 32) verify_at<MODE>(d, p, s_cls, q[i], em);
+    cand_total += qlen;
+    qlen = 0;
+    __syncwarp();
+  };
+  const uint32_t n_needles = p.bs_n;
+  const uint32_t max_back = max(p.bs_back[0], max(p.bs_back[1], p.bs_back[2]));
+  // A warp step covers `owned` lanes x 16 bytes of start offsets.  With offsets (rare bytes) the last
+  // lane only supplies the look-ahead of lane 30, and the next step begins at its 16 bytes.
+  const uint32_t owned_lanes = max_back ? 31u : 32u;
+  const uint64_t step_bytes = (uint64_t)owned_lanes * 16;
+  const uint64_t region_bytes = p.region_hi - p.region_lo;
+  const uint64_t n_steps = (region_bytes + step_bytes - 1) / step_bytes;
+  const uint32_t lt = (1u << lane) - 1;
+  // bytes past the region's end belong to the tail (verified above); a look-ahead lane may read up
+  // to 16 bytes behind region_hi, which enqueue_prefilter_range keeps readable
+  const uint64_t load_end = p.region_hi + (max_back ? 16 : 0);
+  auto load = [&](uint64_t base) -> uint4 {
+    return base < load_end ? ptx::ld_nc_u4(p.hay + base) : make_uint4(0, 0, 0, 0);
+  };
+  auto process = [&](uint64_t base, const uint4& v) {
+    const bool in_range = base < load_end;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    // flagged bytes, one 16-bit mask per needle (bit i = byte i of the lane's 16).  The zero-byte
+    // test (x - 0x01..) & ~x & 0x80.. may also flag the byte above a true hit: a spurious candidate
+    // the verifier rejects, never a missed one.
+    uint32_t cand = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= (int)n_needles) break;
+      const uint32_t needle = p.bs_needle[j];
+      uint32_t m = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = w[k] ^ needle;
+        const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;  // bit 7 of every byte that is zero
+        m |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * k);  // gather the four flags
+      }
+      if (!in_range) m = 0;
+      const uint32_t back = p.bs_back[j];
+      if (back == 0) {
+        cand |= m;
+      } else {
+        // start offsets [q - back, q] of a flag at q: the flags of the next 16 bytes count for the
+        // last `back` offsets of this lane
+        const uint32_t both = m | (__shfl_down_sync(0xffffffffu, m, 1) << 16);
+        uint32_t smear = both;
+        for (uint32_t sft = 1; sft <= back; ++sft) smear |= both >> sft;
+        cand |= smear & 0xFFFFu;
+      }
+    }
+    if (lane >= (int)owned_lanes || base >= p.region_hi) cand = 0;  // look-ahead only / the tail's offsets
+    const uint32_t cnt = __popc(cand);
+    if (__any_sync(0xffffffffu, cnt != 0)) {
+      // warp-wide slot allocation by ballot bit planes (counts <= 16)
+      uint32_t slot = 0, total = 0;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        const uint32_t bl = __ballot_sync(0xffffffffu, (cnt >> b) & 1u);
+        slot += __popc(bl & lt) << b;
+        total += __popc(bl) << b;
+      }
+      if (qlen + total > (uint32_t)kBsQueue) drain();
+      if (total > (uint32_t)kBsQueue) {
+        // needles everywhere (the reference would have retired such a prefilter): verify in place
+        uint32_t c = cand, nver = 0;
+        while (c) {
+          const int bit = __ffs(c) - 1;
+          c &= c - 1;
+          verify_at<MODE>(d, p, s_cls, base + bit, em);
+          ++nver;
+        }
+        cand_total += __reduce_add_sync(0xffffffffu, nver);
+      } else {
+        uint64_t* dst = q + qlen + slot;
+        uint32_t c = cand;
+        while (c) {
+          const int bit = __ffs(c) - 1;
+          c &= c - 1;
+          *dst++ = base + bit;
+        }
+        qlen += total;
+        if (qlen >= 64) drain();
+      }
+    }
+  };
+  // two steps per iteration: two 512-byte loads of the warp in flight
+  const uint64_t stride = (uint64_t)gridDim.x * kBsWarps;
+  for (uint64_t st = (uint64_t)blockIdx.x * kBsWarps + warp; st < n_steps; st += 2 * stride) {
+    const uint64_t base0 = p.region_lo + st * step_bytes + (uint64_t)lane * 16;  // this lane's 16 bytes
+    const uint64_t base1 = base0 + stride * step_bytes;
+    const bool second = st + stride < n_steps;
+    const uint4 v0 = load(base0);
+    const uint4 v1 = second ? load(base1) : make_uint4(0, 0, 0, 0);
+    process(base0, v0);
+    if (second) process(base1, v1);
+  }
+  if (qlen) drain();
+  if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);
 }
 
 // ---- chain resolution ---------------------------------------------------------
@@ -661,7 +754,7 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int geom = p.stride == 2 ? p.geom : kGeomNarrow;
   if (geom < kGeomNarrow || geom > kGeomWide) return cudaErrorInvalidValue;
   const int s2 = (p.stride == 2 && geom != kGeomWide) ? p.pair : kS2Compact;  // second-stage organisation
-  if (s2 != kS2Compact && s2 != kS2Local) return cudaErrorInvalidValue;
+  if (s2 != kS2Compact && s2 != kS2Anchor) return cudaErrorInvalidValue;
   const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
@@ -672,18 +765,18 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int warps = threads / 32;
   const int stage_bytes = kStageOf[geom];
   const int tile = kTileOf[geom];
-  const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
-  const int slot_bytes = s2 == kS2Local ? 0 : (dense ? PfCfg<true>::kSlots : PfCfg<false>::kSlots) * 2;
-  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 8 + q2_bytes + slot_bytes) + bitmap_bytes;
+  const int q2_bytes = (dense || s2 == kS2Anchor) ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
+  const int slot_bytes = PfCfg<false>::kSlots * 2;
+  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 12 + q2_bytes + slot_bytes) + 8 + bitmap_bytes;
   if (smem > 227 * 1024 - 1024) return cudaErrorInvalidValue;  // static shared memory: byte classes, tile numbers
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
   // [mode][masked][dyn][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
-  // 4 stride 2 narrow + lane-local second stage (stride 2 is never combined with the dense variant)
+  // 4 stride 2 narrow + anchor-map second stage (stride 2 is never combined with the dense variant)
 #define ACB_PF_ROW(M, K, D)                                                                                 \
   {prefilter_kernel<M, K, false, 1, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, true, 1, kGeomNarrow, kS2Compact, D>, \
    prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, false, 2, kGeomWide, kS2Compact, D>,  \
-   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Local, D>}
+   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Anchor, D>}
   static const KernT table[2][2][2][5] = {{{ACB_PF_ROW(0, false, false), ACB_PF_ROW(0, false, true)},
                                            {ACB_PF_ROW(0, true, false), ACB_PF_ROW(0, true, true)}},
                                           {{ACB_PF_ROW(1, false, false), ACB_PF_ROW(1, false, true)},
@@ -691,7 +784,7 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
 #undef ACB_PF_ROW
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
   int variant = dense ? 1 : 0;
-  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (s2 == kS2Local ? 4 : 2);
+  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (s2 == kS2Anchor ? 4 : 2);
   KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.dyn ? 1 : 0][variant];
 #ifdef ACB_EMULATE
   if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d dyn %d threads %d smem %zu\n", variant, (int)p.dyn, threads, smem);
@@ -707,6 +800,19 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const uint64_t warp_steps = ((p.region_hi - p.region_lo) + cta_step - 1) / cta_step;
   if (grid > warp_steps) grid = warp_steps ? warp_steps : 1;
   ACB_LAUNCH(kern, (unsigned)grid, threads, smem, s, dfa, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bytescan(const DfaDev& dfa, const PrefilterLaunch& p, int sm_count, cudaStream_t s) {
+  if (p.bs_n < 1 || p.bs_n > 3) return cudaErrorInvalidValue;
+  for (uint32_t j = 0; j < 3; ++j)
+    if (p.bs_back[j] > 15) return cudaErrorInvalidValue;
+  uint64_t grid = (uint64_t)sm_count * 2;
+  const uint64_t steps = ((p.region_hi - p.region_lo) + 16 * 31 - 1) / (16 * 31);
+  const uint64_t ctas = (steps + kBsWarps - 1) / kBsWarps;
+  if (grid > ctas) grid = ctas ? ctas : 1;
+  if (p.mode) ACB_LAUNCH(bytescan_kernel<1>, (unsigned)grid, kBsThreads, 0, s, dfa, p);
+  else ACB_LAUNCH(bytescan_kernel<0>, (unsigned)grid, kBsThreads, 0, s, dfa, p);
   return cudaGetLastError();
 }
 

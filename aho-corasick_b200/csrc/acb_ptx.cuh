@@ -65,6 +65,13 @@ __device__ __forceinline__ uint32_t lds8(uint32_t a) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+// shared-memory fetch-and-add by one thread (the plain atomicAdd is compiled into a warp-aggregated
+// sequence that costs a dozen instructions even when a single lane calls it)
+__device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 // make three values opaque to the compiler so that they stay in registers instead of being
 // re-derived (from the thread index) at every use
 __device__ __forceinline__ void keep_in_registers(uint32_t& a, uint32_t& b, uint32_t& c) {

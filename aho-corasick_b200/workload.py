@@ -106,6 +106,10 @@ def flip_case(out: np.ndarray, seed: int, global_offset: int = 0, chunk: int = 1
 
 
 CONFIGS = {
+    # BASELINE config 1's automaton (README example; the reference gives it a start-bytes prefilter: a, m, S)
+    # over a synthetic haystack: the byte-set scan's workload
+    "cfg1": dict(patterns=[b"apple", b"maple", b"Snapple"], n_patterns=3, pattern_seed=0, hay_seed=0xAC4611,
+                 alphabet=(0x20, 0x7E)),
     # name: (n_patterns, pattern_seed, haystack_seed, alphabet)
     "cfg2": dict(n_patterns=5000, pattern_seed=0xAC5000, hay_seed=0xAC4611, alphabet=(0x20, 0x7E)),
     "cfg2b": dict(n_patterns=5000, pattern_seed=0xAC5000, hay_seed=0xAC4611, alphabet=(0x61, 0x7A)),
@@ -116,9 +120,17 @@ CONFIGS = {
 }
 
 
+def config_patterns(name: str):
+    """The pattern set of a named configuration."""
+    c = CONFIGS[name]
+    if "patterns" in c:
+        return list(c["patterns"])
+    return make_patterns(c["n_patterns"], c["pattern_seed"], alphabet=c["alphabet"])
+
+
 def make_config(name: str, hay_bytes: int, out: np.ndarray | None = None, global_offset: int = 0):
     c = CONFIGS[name]
-    pats = make_patterns(c["n_patterns"], c["pattern_seed"], alphabet=c["alphabet"])
+    pats = config_patterns(name)
     if out is None:
         out = np.empty(hay_bytes, dtype=np.uint8)
     fill_haystack(out, c["hay_seed"], global_offset, alphabet=c["alphabet"])

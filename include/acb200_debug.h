@@ -30,7 +30,12 @@ typedef struct {
   const uint16_t* depth16; /* trie depth per table row */
   uint64_t n_rows;
   uint32_t dup_shift;      /* tie-break layout: (max_len - len) << dup_shift | index among equal patterns */
-  uint32_t key_shift;      /* stride 2: first-stage hash = window * (mult3 << key_shift); 8, or 5 with ACG_EXP_KEY27 */
+  uint32_t key_shift;      /* stride 2: first-stage hash = window * (mult3 << key_shift); 5, or 8 with ACG_EXP_KEY24 */
+  uint32_t bs_n;           /* byte-set scan (start-bytes / rare-bytes role): number of needles, 0 = fingerprint filter */
+  uint8_t bs_byte[3];
+  uint8_t bs_back[3];      /* largest offset of the needle in any pattern (0 for start bytes) */
+  uint8_t pad_[2];
+  uint32_t anchor2;        /* stride 2: the second stage is the anchor-map lookup (no second-stage bits in the bitmap) */
 } acg_prefilter_plan;
 
 /* Fills *out with views of the handle's derived tables.  Works on host-only handles. */
@@ -46,10 +51,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
  * measured in r02 -- profiles/r02a_ab_*.jsonl -- lost, and are gone.) */
 #define ACG_EXP_KEY24 8u         /* stride-2 first stage keyed by the 3 fingerprint bytes only; default: 27 bits (3 bytes +
                                   * low 3 bits of the fourth).  Rebuilds the bitmap. */
-#define ACG_EXP_LOCAL2 16u       /* second stage without compaction: every lane walks its own hits */
+#define ACG_EXP_ANCHOR2 16u      /* stride 2, narrow geometry: second stage = anchor-map lookup, bitmap without second-stage bits */
 #define ACG_EXP_STATIC_TILES 32u /* warp w of a CTA takes tiles w, w + W, ...; default: the warps of a CTA draw their tiles
                                   * from a shared-memory counter.  r02 A/B (profiles/r02b_*.jsonl): dynamic tiles + 27-bit
                                   * keys -7 % on cfg 2, -22 % on cfg 3, -15 % on cfg 5. */
+#define ACG_EXP_NO_BYTESCAN 64u  /* automata with a start-bytes / rare-bytes set: use the fingerprint filter anyway */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 
 #ifdef __cplusplus

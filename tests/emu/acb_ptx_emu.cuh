@@ -51,6 +51,12 @@ inline uint32_t lds32(uint32_t a) {
   return v;
 }
 inline uint32_t lds8(uint32_t a) { return *smem_ptr(a, 1); }
+inline uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t* p = reinterpret_cast<uint32_t*>(smem_ptr(a, 4));
+  const uint32_t old = *p;
+  *p = old + v;
+  return old;
+}
 inline void keep_in_registers(uint32_t&, uint32_t&, uint32_t&) {}
 inline uint4 ld_nc_u4(const void* p) {
   if ((uintptr_t)p & 15) emu::die("misaligned 16-byte global load");

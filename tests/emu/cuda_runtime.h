@@ -35,6 +35,7 @@
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 struct ulonglong2 { unsigned long long x, y; };
 inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct dim3 {
@@ -307,6 +308,10 @@ inline unsigned long long __shfl_sync(unsigned mask, unsigned long long v, int s
   const uint32_t lo = emu::warp_collective(emu::kOpShfl, mask, (uint32_t)v, (uint32_t)src);
   const uint32_t hi = emu::warp_collective(emu::kOpShfl, mask, (uint32_t)(v >> 32), (uint32_t)src);
   return ((unsigned long long)hi << 32) | lo;
+}
+inline unsigned __shfl_down_sync(unsigned mask, unsigned v, unsigned delta) {
+  const unsigned lane = emu::g_cur->tid.x & 31;
+  return emu::warp_collective(emu::kOpShfl, mask, v, lane + delta < 32 ? lane + delta : lane);
 }
 // Any subset of the converged lanes that contains the caller is a legal answer; the fiber model
 // has no notion of convergence, so the caller alone it is.

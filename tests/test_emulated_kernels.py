@@ -251,7 +251,7 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_LOCAL2 = 16,
+# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_ANCHOR2 = 16,
 # ACG_EXP_STATIC_TILES = 32)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
@@ -526,3 +526,90 @@ def test_walk_engine_at_every_alignment():
             got, _ = ac.find_overlapping_iter_dev_np(view.ctypes.data, view.size, span=(s, e))
             eq(got, o.find_overlapping_iter_np(view, span=(s, e)), (phase, s, e))
             assert ac.last_stats()["engine"] == int(ab.Engine.Walk)
+
+
+def test_concurrent_searches_lease_separate_workspaces():
+    """Searches through one handle from several threads (Send + Sync, src/lib.rs:274-326) each lease
+    a workspace of the handle's pool; results are the oracle's and acg_last_stats is per caller."""
+    from concurrent.futures import ThreadPoolExecutor
+    import random
+    rng = random.Random(5)
+    pats = [bytes(rng.choice(b"abcd") for _ in range(rng.randint(2, 6))) for _ in range(40)]
+    hays = [np.frombuffer(bytes(rng.choice(b"abcd") for _ in range(rng.choice([10, 500, 20000]))), dtype=np.uint8).copy()
+            for _ in range(12)]
+    ac = build(pats, 0)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    want = [(o.find_overlapping_iter_np(h), o.find_iter_np(h)) for h in hays]
+
+    def work(i):
+        h = hays[i % len(hays)]
+        a = ac.try_find_overlapping_iter_np(h)
+        raw = ac.last_stats()["raw_matches"]       # this thread's own search, whatever the others are doing
+        b = ac.try_find_iter_np(h)
+        return i % len(hays), a, raw, b
+
+    with ThreadPoolExecutor(6) as ex:
+        for i, a, raw, b in ex.map(work, range(72)):
+            eq(a, want[i][0], i)
+            eq(b, want[i][1], i)
+            assert raw == len(want[i][0]), (i, raw)
+
+
+# ---- byte-set scan: the start-bytes / rare-bytes prefilter role (bytescan_kernel) -----------------
+BYTESCAN_SETS = [
+    ("start3", [b"apple", b"maple", b"Snapple"], dict()),                       # README example: start bytes a, m, S
+    ("start1", [b"xylophone", b"xyz", b"xx"], dict()),
+    ("start_ci", [b"Sam", b"samwise"], dict(ci=True)),                          # S, s
+    ("rare", [b"zebra", b"crazy", b"jazz", b"quiz"], dict()),                   # rare bytes z (and q?) with offsets
+    ("rare_long", [b"abcdefghijklmnoz", b"zabcdefghijklmno", b"hello world q"], dict()),
+    ("leftmost", [b"apple", b"app", b"maple syrup", b"ma"], dict(kind=1)),
+    ("leftmost_longest", [b"apple", b"app", b"maple syrup", b"ma"], dict(kind=2)),
+]
+
+
+@pytest.mark.parametrize("name,pats,kw", BYTESCAN_SETS)
+def test_bytescan_engine(name, pats, kw):
+    kind, ci = kw.get("kind", 0), kw.get("ci", False)
+    rng = np.random.default_rng(len(name))
+    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz SM .,", dtype=np.uint8)
+    hay = alpha[rng.integers(0, len(alpha), size=96 << 10)].copy()
+    for i in range(0, hay.size - 64, 977):      # plant occurrences at many alignments
+        p = pats[(i // 977) % len(pats)]
+        hay[i:i + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    ac = (ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci).build(pats))
+    plan = plan_of(ac)
+    assert plan.bs_n >= 1, (name, ac.prefilter_kind())
+    o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci)
+    ptr = hay.ctypes.data
+    eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), name)
+    assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
+    cand = ac.last_stats()["candidates"]
+    assert 0 < cand <= hay.size   # (rare bytes with large offsets in a 32-letter text: nearly every offset)
+    if kind == 0:
+        eq(ac.find_overlapping_iter_dev_np(ptr, hay.size)[0], o.find_overlapping_iter_np(hay), name)
+        eq(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay), (name, "host"))
+    # every pointer phase x span ends inside a block
+    backing = np.zeros(hay.size + 64, dtype=np.uint8)
+    small = hay[: 20 << 10]
+    for phase in (0, 1, 5, 15, 16, 17, 31):
+        view = backing[phase:phase + small.size]
+        view[:] = small
+        for s, e in ((0, small.size), (3, small.size - 5), (977, 977 + 40), (4097, 9001), (small.size - 20, small.size)):
+            eq(ac.find_iter_dev_np(view.ctypes.data, view.size, span=(s, e))[0], o.find_iter_np(view, span=(s, e)), (name, phase, s, e))
+    # the fingerprint filter on the same handle agrees
+    set_experiment(ac, 64)
+    eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "fingerprints"))
+    set_experiment(ac, 0)
+
+
+def test_bytescan_retires_when_needles_are_everywhere():
+    """Needles in more than one offset out of eight: the scan still answers correctly and the handle
+    goes back to the fingerprint filter for later searches (the reference's PrefilterState)."""
+    pats = [b"aaab", b"aab"]
+    ac = ab.AhoCorasick.builder().build(pats)
+    assert plan_of(ac).bs_n == 1
+    hay = np.frombuffer(b"aaaaab" * 30000, dtype=np.uint8).copy()
+    o = O.Oracle(pats)
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "dense needles")
+    assert plan_of(ac).bs_n == 0
+    eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "after retiring")

@@ -30,7 +30,8 @@ class Plan(C.Structure):
                 ("bitmap", C.POINTER(C.c_uint32)), ("bitmap_words", C.c_uint64),
                 ("amap", C.POINTER(C.c_uint64)), ("amap_log", C.c_uint32),
                 ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64), ("dup_shift", C.c_uint32),
-                ("key_shift", C.c_uint32)]
+                ("key_shift", C.c_uint32), ("bs_n", C.c_uint32), ("bs_byte", C.c_uint8 * 3), ("bs_back", C.c_uint8 * 3),
+                ("pad_", C.c_uint8 * 2), ("anchor2", C.c_uint32)]
 
 
 def plan_of(ac):
@@ -88,8 +89,8 @@ def first_stage_hit(p, window):
 
 
 def second_stage_hit(p, window):
-    if p.dense:
-        return True   # the dense variant's second stage is the (exact) anchor-map lookup
+    if p.dense or p.anchor2:
+        return True   # the second stage is the (exact) anchor-map lookup
     gram = (window | p.fold) & p.kmask
     ok = probe_full(p, hash2(gram))
     if p.stride == 2:

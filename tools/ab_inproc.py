@@ -31,7 +31,7 @@ def main():
     from aho_corasick_b200 import workload as W
 
     cfg = W.CONFIGS[args.workload]
-    pats = W.make_patterns(cfg["n_patterns"], cfg["pattern_seed"], alphabet=cfg["alphabet"])
+    pats = W.config_patterns(args.workload)
     b = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA)
     if args.workload == "cfg3":
         b.ascii_case_insensitive(True).match_kind(ab.MatchKind.LeftmostFirst)
