@@ -162,6 +162,7 @@ def _declare(lib):
     lib.acg_find_overlapping_sharded.argtypes = [_vp, _vp, _vp, _i, _u64, _u64, _u64, _u64, C.POINTER(_vp),
                                                   C.POINTER(_u64), _vp, _u64, _vp]
     lib.acg_comm_fetch.argtypes = [_vp, _vp, _u64, C.POINTER(_u64)]
+    lib.acg_comm_fetch_view.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_u64)]
     lib.acg_comm_checksum.argtypes = [_vp, C.POINTER(_u64), C.POINTER(_u64)]
 
 
@@ -551,7 +552,9 @@ class AhoCorasick:
             hay, span, anchored = hay.haystack(), hay.get_span(), hay.get_anchored()
         keep, ptr, n = _hay_ptr(hay)
         s, e = _span(span, n)
-        cap = self._cap_hint
+        # room for one match per 256 haystack bytes from the start (the device sizes its own tuple buffer the
+        # same way): an overflow retry repeats the whole copy + scan, so it should be the exception
+        cap = max(self._cap_hint, max(e - s, 0) // 256 + 64)
         while True:
             out = np.empty(cap, MATCH_DTYPE)
             cnt = _u64()

@@ -71,7 +71,6 @@ struct PrefilterPlan {
   uint32_t key_shift = 8;  // stride 2: first-stage hash = window * (mult3 << key_shift); 5: the key also
                            // holds the low 3 bits of the window's fourth byte (default; 8 with ACG_EXP_KEY24)
   bool wide = false;
-  bool anchor2 = false;  // stride 2, narrow: the second stage is the anchor-map lookup; the bitmap holds first-stage keys only
   bool brute = false;
   uint32_t dup_shift = 0;
   double fill = 0;          // fraction of bitmap bits set (~ candidate rate on random input)
@@ -201,6 +200,9 @@ int bits_for(uint64_t v) {
   while (v) { ++b; v >>= 1; }
   return b;
 }
+
+// second bit selector of the dense variant's blocked filter; must match acb_prefilter.cu
+constexpr uint32_t kDenseMult2 = 0x85EBCA6Bu;
 
 // second Bloom hash; must match bloom_hash2() in acb_prefilter.cu
 uint32_t bloom_hash2(uint32_t x) {
@@ -373,7 +375,7 @@ void derive_metadata(acg_dfa* a) {
   if (pf.k == 0) return;
   // Dense sets (more fingerprints than a two-probe Bloom filter of 2^20 bits can keep apart; cfg 5:
   // 10^5): a blocked filter instead -- every fingerprint owns one 32-bit word (top 15 bits of
-  // gram * mult) and two bits inside it (bits 0-4 and 5-9 of the product's high half), so that the
+  // gram * mult) and two bits inside it (bits 0-4 of the high halves of gram * mult and gram * kDenseMult2), so that the
   // per-position probe settles both with a single shared-memory load; the second stage is then the
   // exact anchor-map lookup.  Must match the DENSE branch of ACB_PROBE in acb_prefilter.cu.
   const bool dense = best_set.size() > 8192;
@@ -383,7 +385,8 @@ void derive_metadata(acg_dfa* a) {
     for (uint32_t g : best_set) {
       const uint64_t prod = uint64_t(g) * pf.mult;
       const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
-      pf.bitmap[lo >> word_shift] |= (1u << (hi & 31)) | (1u << ((hi >> 5) & 31));
+      const uint32_t hi2 = uint32_t((uint64_t(g) * kDenseMult2) >> 32);
+      pf.bitmap[lo >> word_shift] |= (1u << (hi & 31)) | (1u << (hi2 & 31));
     }
     // pass rate on text drawn from the bytes the patterns use at each fingerprint position
     std::vector<uint8_t> alpha[4];
@@ -402,8 +405,9 @@ void derive_metadata(acg_dfa* a) {
       }
       const uint64_t prod = uint64_t(g) * pf.mult;
       const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
+      const uint32_t hi2 = uint32_t((uint64_t(g) * kDenseMult2) >> 32);
       const uint32_t w = pf.bitmap[lo >> word_shift];
-      pass += (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1u;
+      pass += (w >> (hi & 31)) & (w >> (hi2 & 31)) & 1u;
     }
     pf.fill = double(pass) / kTrials;
   }
@@ -453,10 +457,6 @@ void derive_metadata(acg_dfa* a) {
           set_hash(bloom_hash2(g));
         }
       }
-      // ACG_EXP_ANCHOR2: leave the second stage to the anchor map -- the bitmap then carries the
-      // first-stage keys alone (cfg 2: ~13 000 bits of 2^20 instead of ~23 000)
-      pf.anchor2 = !pf.wide && (a->experiment & ACG_EXP_ANCHOR2) != 0 && paths4.size() <= (4u << 20);
-      if (pf.anchor2) std::fill(pf.bitmap.begin(), pf.bitmap.end(), 0u);
       // First-stage probe of the stride-2 kernel: byte index from the 3-byte fingerprint times
       // (mult3 << 8) -- the shifted multiplier discards the fourth window byte -- and the bit inside
       // the byte from the fingerprint's own low bits.  A multiplicative hash of such short keys is
@@ -544,7 +544,9 @@ void derive_metadata(acg_dfa* a) {
   // depth k.  Keys are raw (unfolded) byte strings: one entry per trie path of length k.
   const std::vector<Item>& paths = level[pf.k];
   if (!paths.empty() && paths.size() <= (4u << 20)) {
-    pf.amap_log = uint32_t(std::max(4, bits_for(uint64_t(paths.size()) * 2 - 1)));
+    // load factor <= 1/4: a lookup of a key that is not there (the common case) ends at the first slot
+    // three times out of four, and every further slot is another dependent L2 access
+    pf.amap_log = uint32_t(std::max(4, bits_for(uint64_t(paths.size()) * 4 - 1)));
     pf.amap.assign(size_t(1) << pf.amap_log, 0ull);
     const uint32_t cap_mask = (1u << pf.amap_log) - 1;
     for (const Item& it : paths) {
@@ -559,8 +561,12 @@ void derive_metadata(acg_dfa* a) {
   // reports start bytes the set is read off the start row (the first bytes of all patterns).
   if (h.prefilter_kind == ACG_PRE_START_BYTES || h.prefilter_kind == ACG_PRE_RARE_BYTES) {
     if (h.pre_n) {
+      // Needles with offsets (rare bytes in the middle of patterns) turn every occurrence into
+      // back + 1 start offsets to verify; measured on BASELINE config 1's automaton over uniform
+      // printable text (r02f: 4.7 ms against 2.1 ms per 4 GiB for the fingerprint filter), so the scan
+      // is reserved for needles that mark a pattern's first byte.
       bool ok = true;
-      for (uint32_t i = 0; i < h.pre_n; ++i) ok = ok && h.pre_back[i] <= 15;
+      for (uint32_t i = 0; i < h.pre_n; ++i) ok = ok && h.pre_back[i] == 0;
       if (ok) {
         pf.bs_n = h.pre_n;
         for (uint32_t i = 0; i < h.pre_n; ++i) { pf.bs_byte[i] = h.pre_byte[i]; pf.bs_back[i] = h.pre_back[i]; }
@@ -772,14 +778,13 @@ int run_walk_overlapping(const acg_dfa* a, const uint8_t* d_hay, uint64_t readab
   if (n_bytes >= (1ull << (64 - acb::kTieBits))) return ACG_E_INVALID_ARG;
   int dev_sms = 148;
   cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, a->device);
-  // shards: four per lane (kWalkChains in acb_kernels.cu), enough lanes to fill every SM's thread slots
-  const uint64_t target_shards = uint64_t(dev_sms) * 1536 * 4;
-  uint64_t seg_len = (n_bytes + target_shards - 1) / std::max<uint64_t>(target_shards, 1);
+  const uint64_t target_lanes = uint64_t(dev_sms) * 2048;
+  uint64_t seg_len = (n_bytes + target_lanes - 1) / std::max<uint64_t>(target_lanes, 1);
   seg_len = std::max<uint64_t>(seg_len, 256);
   seg_len = (seg_len + 15) & ~15ull;
-  // the shard grid starts at the 16-byte boundary at or before d_hay + span_start (see the kernel)
-  const uint64_t phase = reinterpret_cast<uintptr_t>(d_hay + span_start) & 15;
-  const uint64_t n_segs = std::max<uint64_t>((n_bytes + phase + seg_len - 1) / seg_len, 1);
+  // shard starts are placed so that (d_hay + span_start + k*seg_len) keeps the 16-byte
+  // phase of the first shard; the kernel handles the unaligned head per lane.
+  const uint64_t n_segs = std::max<uint64_t>((n_bytes + seg_len - 1) / seg_len, 1);
   uint64_t cap = std::max<uint64_t>(w.cap, std::max<uint64_t>(1 << 20, n_bytes / 256));
   for (int attempt = 0; attempt < 8; ++attempt) {
     int rc = ensure_tuple_cap(w, cap);
@@ -853,7 +858,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   p.stride = pf.stride;
   // kernel geometry as planned; second-stage organisation and tile distribution: see prefilter_kernel
   p.geom = pf.wide ? 1 : 0;
-  p.pair = (pf.stride == 2 && !pf.wide && pf.anchor2) ? 1 : 0;
+  p.pair = 0;
   p.dyn = (a->experiment & ACG_EXP_STATIC_TILES) ? 0 : 1;
   p.kmask = pf.kmask;
   p.fold = pf.fold;
@@ -967,8 +972,9 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
     const uint64_t want = w.h_counter[0];
     cur_ws().stats.candidates = w.h_counter[1];
     // the reference retires a prefilter that keeps reporting candidates (PrefilterState,
-    // src/util/prefilter.rs): needles in more than one offset out of eight => fingerprint filter next time
-    if (a->pf.bs_n && !a->bytescan_inert && scan_hi - scan_lo >= (1u << 16) && w.h_counter[1] > (scan_hi - scan_lo) / 8)
+    // src/util/prefilter.rs): needles in more than one offset out of 64 => fingerprint filter next time
+    // (beyond that the verifications cost more than the fingerprint probes they replace)
+    if (a->pf.bs_n && !a->bytescan_inert && scan_hi - scan_lo >= (1u << 16) && w.h_counter[1] > (scan_hi - scan_lo) / 64)
       a->bytescan_inert = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, w.ev0, w.ev1);
@@ -1666,7 +1672,6 @@ int acg_debug_prefilter_plan(const acg_dfa* a, acg_prefilter_plan* out) {
   out->dup_shift = pf.dup_shift;
   out->bs_n = (pf.bs_n && !a->bytescan_inert) ? pf.bs_n : 0;
   for (int i = 0; i < 3; ++i) { out->bs_byte[i] = pf.bs_byte[i]; out->bs_back[i] = pf.bs_back[i]; }
-  out->anchor2 = pf.anchor2 ? 1 : 0;
   return ACG_OK;
 }
 
@@ -1677,11 +1682,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_ANCHOR2 | ACG_EXP_STATIC_TILES | ACG_EXP_NO_BYTESCAN))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_STATIC_TILES | ACG_EXP_NO_BYTESCAN))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;
-  if (changed & (ACG_EXP_KEY24 | ACG_EXP_ANCHOR2)) {
+  if (changed & ACG_EXP_KEY24) {
     // the first-stage keys are part of the plan: rebuild it and refresh the device copy of the bitmap
     const size_t old_words = a->pf.bitmap.size();
     derive_metadata(a);
@@ -2007,6 +2012,27 @@ int acg_comm_fetch(const acg_comm* c, acg_match* out, uint64_t cap, uint64_t* n_
   if (total > cap || (total && !out)) return ACG_E_OVERFLOW;
   DeviceGuard guard(c->device);
   if (total) CK(cudaMemcpy(out, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+  return ACG_OK;
+}
+
+int acg_comm_fetch_view(acg_comm* c, const acg_match** view, uint64_t* n_out) {
+  if (!c || !view || !n_out || c->rank != 0) return ACG_E_INVALID_ARG;
+  uint64_t total = 0;
+  for (uint64_t v : c->counts) total += v;
+  *n_out = total;
+  *view = nullptr;
+  DeviceGuard guard(c->device);
+  if (total > c->h_view_cap) {
+    if (c->h_view) { cudaFreeHost(c->h_view); c->h_view = nullptr; c->h_view_cap = 0; }
+    const uint64_t cap = total + total / 8 + 1024;
+    CK(cudaMallocHost(&c->h_view, size_t(cap) * sizeof(acg_match)));
+    c->h_view_cap = cap;
+  }
+  if (total) {
+    CK(cudaMemcpyAsync(c->h_view, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  *view = reinterpret_cast<const acg_match*>(c->h_view);
   return ACG_OK;
 }
 

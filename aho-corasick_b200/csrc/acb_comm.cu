@@ -210,6 +210,7 @@ void comm_destroy(acg_comm* c) {
   cudaFree(c->d_counts);
   cudaFree(c->d_handle);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->h_view) cudaFreeHost(c->h_view);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);

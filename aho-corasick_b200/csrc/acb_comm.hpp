@@ -34,6 +34,8 @@ struct acg_comm {
   unsigned long long* h_counts = nullptr;  // pinned mirror
   uint8_t* d_handle = nullptr;             // 64-byte cudaIpcMemHandle_t in transit
   std::vector<uint64_t> counts;            // last call: records per rank
+  uint8_t* h_view = nullptr;               // pinned host copy of the gathered records (acg_comm_fetch_view)
+  uint64_t h_view_cap = 0;                 // records
   float last_gather_ms = 0;
 };
 

@@ -48,9 +48,8 @@ struct WalkLaunch {
   const uint8_t* hay;   // device pointer to haystack byte 0
   uint64_t hay_len;     // bytes readable behind `hay`
   uint64_t span_start, span_end;
-  uint64_t seg_len;     // bytes owned per shard (a multiple of 16; a lane walks kWalkChains = 4 shards)
-  uint64_t n_segs;      // shards: shard k owns [origin + k * seg_len, + seg_len) cut to the span, origin = the
-                        // 16-byte boundary at or before hay + span_start
+  uint64_t seg_len;     // bytes owned per lane
+  uint64_t n_segs;
   uint64_t* keys;       // [cap]
   uint32_t* pids;       // [cap]
   unsigned long long* counter;  // total tuples wanted (may exceed cap => overflow)
@@ -108,7 +107,7 @@ struct PrefilterLaunch {
                                 // 3-byte fingerprints of pattern bytes [0,3) and [1,4) (k == 4 only)
   uint16_t geom;                // stride 2 only: 0 narrow, 1 wide (2 KiB tiles / 512 threads / 16 KiB bitmap: rare
                                 // first-stage hits)
-  uint16_t pair;                // stride 2, narrow: second-stage organisation -- 0 compacted items, 2 lane-local
+  uint16_t pair;                // (unused)
   uint32_t kmask;               // mask of the low k bytes
   uint32_t fold;                // 0 or 0x20202020 (ASCII case folding of the fingerprint)
   uint32_t mult;                // first Bloom hash: gram * mult

@@ -47,108 +47,75 @@ __device__ __noinline__ void emit_state_matches(const uint32_t* match_offsets, c
 }
 
 constexpr int kWalkThreads = 256;
-constexpr int kWalkChains = 4;  // independent shards walked by one lane (must match acb_api.cu)
 
-// K1: the state-transition loop of src/automaton.rs:1491-1534 over DFA::next_state
-// (src/dfa.rs:218-226), sharded.  A shard starts cold (start state) a little more than
-// max_pattern_len-1 bytes before its first owned byte -- the Aho-Corasick state depends on at most
-// that many trailing bytes -- and only reports matches whose end lies inside the shard, so every
-// end offset is owned by exactly one shard.
-// The loop is one dependent table load per byte (an L2 hit for everything below the first trie
-// levels: ~250 cycles), so a lane that walks a single shard keeps one load in flight and the SM
-// idles (r01 ncu: 34 long-scoreboard stall cycles per issued instruction, issue slots 23 % busy).
-// Here every lane walks kWalkChains consecutive shards at once, byte k of each in turn: four
-// independent chains per lane, 16-byte vector loads of each shard, byte classes in shared memory.
-// (A variant that staged the start / depth-1 rows in shared memory behind a flagged table copy was
-// measured in r02 and lost: 4.68 ms against 2.75 ms per GiB on cfg 2, profiles/r02a_ab_walk.jsonl.)
-__global__ void __launch_bounds__(kWalkThreads, 4)
+// One lane per haystack shard.  A lane starts cold (start state) at most
+// max_pattern_len-1 bytes before its shard -- the Aho-Corasick state depends on
+// at most that many trailing bytes -- and only reports matches whose end lies
+// inside its shard, so every end offset is owned by exactly one lane.
+// The loop is one dependent table load per byte.  Everything below the first two trie levels (42 % of
+// the transitions on cfg 2) is an L2 hit, one 32-byte sector per byte: at 2.75 ms per GiB the kernel
+// moves 5.2 TB/s of sectors out of L2, which is where random-sector traffic saturates on this part
+// -- more loads in flight do not help.  Measured in r02 and gone (profiles/r02a_ab_walk.jsonl,
+// r02e_walk_cfg2.jsonl, r02f_walk2.jsonl): the start / depth-1 rows staged in shared memory behind a
+// flagged table copy (4.68 ms per GiB), and four independent shards per lane with speculative
+// 16-byte blocks (3.46-3.73 ms per GiB; ncu: long-scoreboard stalls unchanged at 23 per issue).
+__global__ void __launch_bounds__(kWalkThreads, 5)
 walk_overlapping_kernel(DfaDev d, WalkLaunch p) {
   __shared__ uint8_t s_cls[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = d.classes[i];
   __syncthreads();
 
-  const uint32_t* __restrict__ trans = d.trans;
-  const uint8_t* __restrict__ hay = p.hay;
-  const uint32_t max_match = d.max_match_id;
-  const int64_t span_start = (int64_t)p.span_start, span_end = (int64_t)p.span_end;
-  // shard grid: origin at the 16-byte boundary at or before the span start, so that every block of
-  // every shard is a 16-byte aligned address; shard k = [origin + k * seg_len, + seg_len) cut to the span
-  const int64_t origin = span_start - (int64_t)(reinterpret_cast<uintptr_t>(hay + p.span_start) & 15);
-  const int64_t seg_len = (int64_t)p.seg_len;
-  const int64_t back16 = ((d.max_pattern_len > 0 ? (int64_t)d.max_pattern_len - 1 : 0) + 15) & ~(int64_t)15;
-  const uint64_t first_seg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kWalkChains;
-  if (first_seg >= p.n_segs) return;
-  auto report = [&](uint32_t sid, int64_t pos) {
-    emit_state_matches(d.match_offsets, d.match_pids, (sid >> d.stride2) - 2, (uint64_t)(pos + 1 - span_start),
-                       p.keys, p.pids, p.counter, p.cap);
-  };
-  // matches of the start state itself (empty patterns) at the very beginning of the span are
-  // reported before the first byte (src/automaton.rs:1456-1464)
-  if (first_seg == 0 && d.start_unanchored_id != 0 && d.start_unanchored_id <= max_match)
-    report(d.start_unanchored_id, span_start - 1);
+  const uint64_t seg = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= p.n_segs) return;
+  const uint64_t g0 = p.span_start + seg * p.seg_len;
+  uint64_t g1 = g0 + p.seg_len;
+  if (g1 > p.span_end) g1 = p.span_end;
+  const uint64_t back = d.max_pattern_len > 0 ? (uint64_t)d.max_pattern_len - 1 : 0;
+  uint64_t pos = (g0 - p.span_start > back) ? g0 - back : p.span_start;
 
-  uint32_t sid[kWalkChains];
+  const uint32_t* __restrict__ trans = d.trans;
+  const uint32_t max_match = d.max_match_id;
+  uint32_t sid = d.start_unanchored_id;
+
+  // matches of the start state itself (empty patterns) at the very beginning of
+  // the span are reported before the first byte (src/automaton.rs:1456-1464)
+  if (seg == 0 && sid != 0 && sid <= max_match)
+    emit_state_matches(d.match_offsets, d.match_pids, (sid >> d.stride2) - 2, 0, p.keys, p.pids, p.counter, p.cap);
+
+  auto next = [&](uint32_t from, uint32_t byte) -> uint32_t { return __ldg(trans + from + s_cls[byte]); };
+
+#define ACB_STEP(byte_expr)                                                          \
+  do {                                                                               \
+    sid = next(sid, (byte_expr));                                                    \
+    if (sid <= max_match) {                                                          \
+      if (sid == 0) { pos = g1; break; }                                             \
+      if (pos >= g0)                                                                 \
+        emit_state_matches(d.match_offsets, d.match_pids, (sid >> d.stride2) - 2, pos + 1 - p.span_start, p.keys, p.pids, p.counter, p.cap); \
+    }                                                                                \
+    ++pos;                                                                           \
+  } while (0)
+
+  const uint8_t* __restrict__ hay = p.hay;
+  while (pos < g1 && ((reinterpret_cast<uintptr_t>(hay + pos)) & 15)) ACB_STEP(hay[pos]);
+  while (pos + 16 <= g1) {
+    const uint4 v = ptx::ld_nc_u4(hay + pos);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    bool dead = false;
 #pragma unroll
-  for (int c = 0; c < kWalkChains; ++c) sid[c] = d.start_unanchored_id;
-  const int64_t g00 = origin + (int64_t)first_seg * seg_len;  // first owned byte of chain 0; chain c: + c * seg_len
-  const int64_t n_blocks = (back16 + seg_len) >> 4;
-  for (int64_t j = 0; j < n_blocks; ++j) {
-    const int64_t blk0 = g00 - back16 + (j << 4);  // this block of chain 0
-    const bool warm = (j << 4) < back16;           // cold-start run-in: nothing is reported
-    // every chain has a whole block inside the span (then also inside its shard): 16 x 4 transitions
-    // with no per-byte checks, tracking only the smallest state id each chain saw -- match states are
-    // the smallest ids (src/dfa.rs:229-247), so one comparison per chain and block tells whether
-    // anything is to be reported; the rare chain that has something walks its 16 bytes again, carefully
-    if (blk0 >= span_start && blk0 + (kWalkChains - 1) * seg_len + 16 <= span_end) {
-      uint32_t at[kWalkChains], lowest[kWalkChains];
-#pragma unroll
-      for (int c = 0; c < kWalkChains; ++c) { at[c] = sid[c]; lowest[c] = 0xFFFFFFFFu; }
-      const uint8_t* src = hay + blk0;
-#pragma unroll 1
-      for (int wi = 0; wi < 4; ++wi, src += 4) {  // rolled: keeps the live set to one word per chain
-        uint32_t w[kWalkChains];
-#pragma unroll
-        for (int c = 0; c < kWalkChains; ++c) w[c] = __ldg(reinterpret_cast<const uint32_t*>(src + c * seg_len));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int c = 0; c < kWalkChains; ++c) {
-            const uint32_t b = __byte_perm(w[c], 0, 0x4440 + k);
-            sid[c] = __ldg(trans + sid[c] + s_cls[b]);
-            lowest[c] = min(lowest[c], sid[c]);
-          }
-        }
+    for (int k = 0; k < 16; ++k) {
+      const uint32_t b = (w[k >> 2] >> ((k & 3) * 8)) & 0xFF;
+      sid = next(sid, b);
+      if (sid <= max_match) {
+        if (sid == 0) { dead = true; break; }
+        if (pos >= g0)
+          emit_state_matches(d.match_offsets, d.match_pids, (sid >> d.stride2) - 2, pos + 1 - p.span_start, p.keys, p.pids, p.counter, p.cap);
       }
-      if (!warm) {
-#pragma unroll
-        for (int c = 0; c < kWalkChains; ++c) {
-          if (lowest[c] > max_match) continue;
-          uint32_t s = at[c];
-          const int64_t pos0 = blk0 + c * seg_len;
-#pragma unroll 1
-          for (int k = 0; k < 16; ++k) {
-            s = __ldg(trans + s + s_cls[hay[pos0 + k]]);
-            if (s <= max_match && s != 0) report(s, pos0 + k);
-          }
-        }
-      }
-    } else {
-      // a block that crosses the span's edges, or shards that do not exist: byte by byte, nothing
-      // outside [cold start, shard end) is read
-#pragma unroll 1
-      for (int k = 0; k < 16; ++k) {
-#pragma unroll
-        for (int c = 0; c < kWalkChains; ++c) {
-          const int64_t g0 = g00 + c * seg_len;
-          const int64_t pos = blk0 + c * seg_len + k;
-          if (g0 >= span_end || pos < span_start || pos >= min(g0 + seg_len, span_end)) continue;
-          const uint32_t s = __ldg(trans + sid[c] + s_cls[hay[pos]]);
-          sid[c] = s;
-          if (s <= max_match && s != 0 && pos >= g0) report(s, pos);
-        }
-      }
+      ++pos;
     }
+    if (dead) { pos = g1; break; }
   }
+  while (pos < g1) ACB_STEP(hay[pos]);
+#undef ACB_STEP
 }
 
 // ---- dense-table construction (one BFS level per launch) -------------------------
@@ -307,8 +274,7 @@ cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_
 }
 
 cudaError_t launch_walk_overlapping(const DfaDev& dfa, const WalkLaunch& p, cudaStream_t s) {
-  const uint64_t lanes = (p.n_segs + kWalkChains - 1) / kWalkChains;
-  const uint64_t blocks = (lanes + kWalkThreads - 1) / kWalkThreads;
+  const uint64_t blocks = (p.n_segs + kWalkThreads - 1) / kWalkThreads;
   ACB_LAUNCH(walk_overlapping_kernel, (unsigned)blocks, kWalkThreads, 0, s, dfa, p);
   return cudaGetLastError();
 }

@@ -74,6 +74,10 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
   return x;
 }
 
+// second bit selector of the dense variant's blocked filter: high half of gram * kDenseMult2.
+// Must match acb_api.cu.
+constexpr uint32_t kDenseMult2 = 0x85EBCA6Bu;
+
 constexpr int kPfStages = 2;            // ring depth per warp (TMA bulk copies + mbarriers, acb_ptx.cuh)
 
 struct Emitter {
@@ -218,27 +222,24 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // is verified 32 at a time, so the dependent DFA walks always run with full warps.  There is no
 // block-wide barrier in the steady state: a warp waiting on a verification overlaps with the
 // other warps' fingerprint work.
-// Second-stage organisation S2 (stride 2, narrow geometry):
-//   0  compacted (hit, start offset) items, one per lane, tested with two more Bloom hashes of the
-//      4-byte fingerprint in the shared-memory bitmap
-//   1  ANCHOR: the same items looked up in the anchor map instead (exact: one L2 access tells whether
-//      the 4 bytes begin a pattern and at which trie state) -- the bitmap then holds first-stage keys
-//      only, which lowers its density and with it the first-stage hits per step
-// (A lane-local second stage without compaction was measured in r02 and lost on cfg 2 and, once the
-// 27-bit keys were in, on cfg 3: profiles/r02a_ab_*.jsonl, r02b_cfg3.jsonl.)
+// Second stage: compacted (hit, start offset) items, one per lane.  Stride 1 / stride 2: tested with
+// one / two more Bloom hashes of the 4-byte fingerprint in the shared-memory bitmap.  DENSE: looked up
+// in the anchor map (exact: one L2 access tells whether the k bytes begin a pattern and at which
+// trie state), two items per lane in flight.
+// (Measured in r02 and gone: a lane-local second stage without compaction, a paired one, and the
+// anchor-map second stage for the stride-2 kernel -- 2.10 ms against 1.81 ms on cfg 2, the L2 latency
+// outweighs the sparser bitmap: profiles/r02a_ab_*.jsonl, r02b_cfg3.jsonl, r02f_cfg2.jsonl.)
 // Tile distribution DYN: false -- warp w of a CTA takes the tiles w, w + W, w + 2W, ... of the CTA's
 // chunk; true -- the warps of a CTA draw tile numbers from a shared-memory counter.  With the static
 // split the warps of a CTA finish up to 25 % apart (ncu r02a: 27.8 of 32 warps active on average,
 // the least busy SM sub-partition active 74 % of the kernel), because the scheduler favours some
 // warps and nothing hands their neighbours' work over; the kernel ends with its slowest warp.
-enum : int { kS2Compact = 0, kS2Anchor = 1 };
-template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int S2 = kS2Compact, bool DYN = false>
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, bool DYN = false>
 __global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
   static_assert(GEOM == kGeomNarrow || STRIDE == 2, "the 2 KiB tile needs the stride-2 first stage (32 hit bits per lane)");
-  static_assert(S2 == kS2Compact || (STRIDE == 2 && !DENSE), "the anchor second stage is an option of the stride-2 first stage (dense sets always use it)");
-  constexpr bool ANCH = DENSE || S2 == kS2Anchor;  // second stage = anchor-map lookup, queue entries carry the trie state
+  constexpr bool ANCH = DENSE;  // second stage = anchor-map lookup, queue entries carry the trie state
   constexpr int kPfThreads = PfGeom<GEOM>::kThreads;
   constexpr int kPfWarps = PfGeom<GEOM>::kWarps;
   constexpr int kPfTile = PfGeom<GEOM>::kTile;
@@ -427,9 +428,14 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     if constexpr (DENSE) {                                                                    \
       /* blocked filter: one word per key (top bits of the product), two bits inside it (low    \
          bits of the product's high half) -- both tested with this one load */                  \
+      /* the ALU pipe (shifts, logic) is what saturates here, so everything that can be a         \
+         multiply is one: word index and both bit selectors are high halves of products (FMA     \
+         pipe), and the hit bit enters the mask through a multiply-add (first probe ends up in   \
+         the top bit; the mask is bit-reversed once after the last probe) */                     \
       const uint32_t ph = __umulhi(gm, mult);                                                  \
-      const uint32_t bw = s_bitmap[h >> (kBloomShift + 2)];                                    \
-      mask = __funnelshift_r(mask, __funnelshift_r(bw, bw, ph) & __funnelshift_r(bw, bw, ph >> 5), 1); \
+      const uint32_t ph2 = __umulhi(gm, kDenseMult2);                                          \
+      const uint32_t bw = s_bitmap[__umulhi(h, 1u << (32 - kBloomShift - 2))];                 \
+      mask = mask * 2u + (__funnelshift_r(bw, bw, ph) & __funnelshift_r(bw, bw, ph2) & 1u);    \
     } else {                                                                                  \
       const uint32_t rep = (uint32_t)s_bytes[h >> kBloomShift] * 0x01010101u;                 \
       mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, sel), 1);                        \
@@ -450,7 +456,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 #undef ACB_PROBE
 #undef ACB_WIN
     // the probes were funnelled in from the top: move the first one down to bit 0
-    if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
+    if constexpr (DENSE) mask = __brev(mask);  // (dense: shifted in from the bottom, 32 probes)
+    else if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
     if (t + 1 == n_tiles) {
       // the last tile may be short: drop the hit bits of groups behind its end
       uint32_t ok_bits = 0;
@@ -510,6 +517,60 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
         const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
         const uint32_t n_items = total * STRIDE;
+        if constexpr (ANCH) {
+          // Anchor-map second stage: the answer is an L2 access away, so every lane takes two items
+          // per round and has both first probes of the table in flight before it looks at either.
+          for (uint32_t base = 0; base < n_items; base += 64) {
+            uint32_t rel2[2], key2[2], slot2[2], sid2[2];
+            bool look[2], pass2[2];
+            uint2 ent[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const uint32_t w = base + 32u * u + lane;
+              const uint32_t j = STRIDE == 2 ? (w & 1u) : 0u;
+              look[u] = false; pass2[u] = false; rel2[u] = 0; key2[u] = 0; slot2[u] = 0; sid2[u] = 0;
+              ent[u] = make_uint2(0, 0);
+              if (w < n_items) {
+                const uint32_t raw = slots[STRIDE == 2 ? (w >> 1) : w];
+                const uint32_t e = hit_offset(raw & 31u, raw >> 5);
+                rel2[u] = wrel + e - j;
+                if (STRIDE == 2 && e < j) {
+                  // the start lies one byte before the tile (at most one item per step): the
+                  // verifier decides -- unless it would fall before the filter region
+                  pass2[u] = !region_first;
+                } else if (d.amap == nullptr) {
+                  pass2[u] = true;
+                } else if (chunk_base + rel2[u] + d.amap_k <= p.span_end) {
+                  const uint32_t off = e - j;
+                  const uint32_t sa = tile_a + (off & ~3u);
+                  key2[u] = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8) & d.amap_kmask;
+                  slot2[u] = bloom_hash3(key2[u]) >> d.amap_shift;
+                  look[u] = true;
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              if (look[u]) ent[u] = __ldg(d.amap + slot2[u]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (look[u]) {
+                while (ent[u].y != 0 && ent[u].x != key2[u]) {  // open addressing, empty slot = miss
+                  slot2[u] = (slot2[u] + 1) & d.amap_mask;
+                  ent[u] = __ldg(d.amap + slot2[u]);
+                }
+                sid2[u] = ent[u].y;
+                pass2[u] = sid2[u] != 0;
+              }
+              const uint32_t bal = __ballot_sync(0xffffffffu, pass2[u]);
+              if (bal) {
+                if (pass2[u]) q2[q2len + __popc(bal & lt)] = make_uint2(rel2[u], sid2[u]);
+                q2len += __popc(bal);
+                if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
+              }
+            }
+          }
+        } else
         for (uint32_t base = 0; base < n_items; base += 32) {
           const uint32_t w = base + lane;
           const uint32_t j = STRIDE == 2 ? (w & 1u) : 0u;
@@ -526,30 +587,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
               const uint32_t off = e - j;
               const uint32_t sa = tile_a + (off & ~3u);
               uint32_t gram = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8);
-              if constexpr (ANCH) {
-                // the exact answer is one L2 access away -- the anchor map says whether
-                // the k bytes at the offset begin a pattern, and at which trie state
-                const uint64_t s0 = chunk_base + (wrel + e - j);
-                if (d.amap == nullptr) pass = true;
-                else if (s0 + d.amap_k <= p.span_end) {
-                  gram_keep = anchor_lookup_key(d, gram & d.amap_kmask);
-                  pass = gram_keep != 0;
-                }
-              } else {
               if (MASKED) gram = (gram | fold) & kmask;
               // stride 2: the first stage saw only three of the four bytes, so the cheap
               // multiplicative hash of the whole fingerprint rejects most items before the mix
               if (STRIDE == 2) pass = bloom_test<kBloomShift>(s_bitmap, gram * mult) && bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
               else pass = bloom_test<kBloomShift>(s_bitmap, bloom_hash2(gram));
-              }
             }
           }
           const uint32_t bal = __ballot_sync(0xffffffffu, pass);
           if (bal) {
             if (pass) {
               const uint32_t rel = wrel + e - j;
-              if constexpr (ANCH) q2[q2len + __popc(bal & lt)] = make_uint2(rel, gram_keep);
-              else q2[q2len + __popc(bal & lt)] = rel;
+              if constexpr (!ANCH) q2[q2len + __popc(bal & lt)] = rel;
             }
             q2len += __popc(bal);
             if (q2len > (uint32_t)(kPfQ2 - 32)) drain2();
@@ -624,9 +673,23 @@ __global__ void __launch_bounds__(kBsThreads, 2) bytescan_kernel(DfaDev d, Prefi
   auto process = [&](uint64_t base, const uint4& v) {
     const bool in_range = base < load_end;
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    // flagged bytes, one 16-bit mask per needle (bit i = byte i of the lane's 16).  The zero-byte
-    // test (x - 0x01..) & ~x & 0x80.. may also flag the byte above a true hit: a spurious candidate
-    // the verifier rejects, never a missed one.
+    // Zero-byte test per word and needle: (x - 0x01..) & ~x & 0x80.. has bit 7 set in every byte of
+    // x = word ^ needle that is zero (and possibly in the byte above a true hit: a spurious
+    // candidate the verifier rejects, never a missed one).  Most steps have no needle in the warp's
+    // 512 bytes at all: one vote and on to the next load.
+    uint32_t zany = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= (int)n_needles) break;
+      const uint32_t needle = p.bs_needle[j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = w[k] ^ needle;
+        zany |= (x - 0x01010101u) & ~x & 0x80808080u;
+      }
+    }
+    if (!__any_sync(0xffffffffu, zany != 0 && in_range)) return;
+    // flagged bytes, one 16-bit mask per needle (bit i = byte i of the lane's 16)
     uint32_t cand = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -636,7 +699,7 @@ __global__ void __launch_bounds__(kBsThreads, 2) bytescan_kernel(DfaDev d, Prefi
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t x = w[k] ^ needle;
-        const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;  // bit 7 of every byte that is zero
+        const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;
         m |= ((((z >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * k);  // gather the four flags
       }
       if (!in_range) m = 0;
@@ -687,16 +750,19 @@ __global__ void __launch_bounds__(kBsThreads, 2) bytescan_kernel(DfaDev d, Prefi
       }
     }
   };
-  // two steps per iteration: two 512-byte loads of the warp in flight
+  // four steps per iteration: four 512-byte loads of the warp in flight
   const uint64_t stride = (uint64_t)gridDim.x * kBsWarps;
-  for (uint64_t st = (uint64_t)blockIdx.x * kBsWarps + warp; st < n_steps; st += 2 * stride) {
-    const uint64_t base0 = p.region_lo + st * step_bytes + (uint64_t)lane * 16;  // this lane's 16 bytes
-    const uint64_t base1 = base0 + stride * step_bytes;
-    const bool second = st + stride < n_steps;
-    const uint4 v0 = load(base0);
-    const uint4 v1 = second ? load(base1) : make_uint4(0, 0, 0, 0);
-    process(base0, v0);
-    if (second) process(base1, v1);
+  for (uint64_t st = (uint64_t)blockIdx.x * kBsWarps + warp; st < n_steps; st += 4 * stride) {
+    uint64_t base[4];
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      base[u] = p.region_lo + (st + u * stride) * step_bytes + (uint64_t)lane * 16;  // this lane's 16 bytes
+      v[u] = st + u * stride < n_steps ? load(base[u]) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (st + u * stride < n_steps) process(base[u], v[u]);
   }
   if (qlen) drain();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);
@@ -753,8 +819,6 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const bool dense = p.dense != 0;
   const int geom = p.stride == 2 ? p.geom : kGeomNarrow;
   if (geom < kGeomNarrow || geom > kGeomWide) return cudaErrorInvalidValue;
-  const int s2 = (p.stride == 2 && geom != kGeomWide) ? p.pair : kS2Compact;  // second-stage organisation
-  if (s2 != kS2Compact && s2 != kS2Anchor) return cudaErrorInvalidValue;
   const uint32_t want_log = geom == kGeomWide ? PfBloom<kGeomWide>::kLogBits : PfBloom<kGeomNarrow>::kLogBits;
   if (!p.brute && (p.log_bits != want_log || p.shift != 35 - want_log)) return cudaErrorInvalidValue;
   const size_t bitmap_bytes = p.brute ? 0 : (size_t(1) << (p.log_bits - 3));
@@ -765,26 +829,25 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int warps = threads / 32;
   const int stage_bytes = kStageOf[geom];
   const int tile = kTileOf[geom];
-  const int q2_bytes = (dense || s2 == kS2Anchor) ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
+  const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
   const int slot_bytes = PfCfg<false>::kSlots * 2;
   const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 12 + q2_bytes + slot_bytes) + 8 + bitmap_bytes;
   if (smem > 227 * 1024 - 1024) return cudaErrorInvalidValue;  // static shared memory: byte classes, tile numbers
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);
-  // [mode][masked][dyn][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide,
-  // 4 stride 2 narrow + anchor-map second stage (stride 2 is never combined with the dense variant)
+  // [mode][masked][dyn][variant]: 0 stride 1, 1 stride 1 + dense, 2 stride 2 narrow, 3 stride 2 wide
+  // (stride 2 is never combined with the dense variant)
 #define ACB_PF_ROW(M, K, D)                                                                                 \
-  {prefilter_kernel<M, K, false, 1, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, true, 1, kGeomNarrow, kS2Compact, D>, \
-   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Compact, D>, prefilter_kernel<M, K, false, 2, kGeomWide, kS2Compact, D>,  \
-   prefilter_kernel<M, K, false, 2, kGeomNarrow, kS2Anchor, D>}
-  static const KernT table[2][2][2][5] = {{{ACB_PF_ROW(0, false, false), ACB_PF_ROW(0, false, true)},
+  {prefilter_kernel<M, K, false, 1, kGeomNarrow, D>, prefilter_kernel<M, K, true, 1, kGeomNarrow, D>, \
+   prefilter_kernel<M, K, false, 2, kGeomNarrow, D>, prefilter_kernel<M, K, false, 2, kGeomWide, D>}
+  static const KernT table[2][2][2][4] = {{{ACB_PF_ROW(0, false, false), ACB_PF_ROW(0, false, true)},
                                            {ACB_PF_ROW(0, true, false), ACB_PF_ROW(0, true, true)}},
                                           {{ACB_PF_ROW(1, false, false), ACB_PF_ROW(1, false, true)},
                                            {ACB_PF_ROW(1, true, false), ACB_PF_ROW(1, true, true)}}};
 #undef ACB_PF_ROW
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
   int variant = dense ? 1 : 0;
-  if (p.stride == 2) variant = geom == kGeomWide ? 3 : (s2 == kS2Anchor ? 4 : 2);
+  if (p.stride == 2) variant = geom == kGeomWide ? 3 : 2;
   KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.dyn ? 1 : 0][variant];
 #ifdef ACB_EMULATE
   if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d dyn %d threads %d smem %zu\n", variant, (int)p.dyn, threads, smem);

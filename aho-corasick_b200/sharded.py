@@ -78,7 +78,7 @@ class Comm:
         if rc:
             ab.AhoCorasick._raise(rc)
         if host_out and self.rank == 0:
-            out = self.fetch()
+            out = self.fetch_view()
         stats = {k: getattr(st, k) for k, _ in ShardStats._fields_}
         return n.value, (dptr.value or 0), stats, out
 
@@ -90,6 +90,18 @@ class Comm:
         if rc:
             raise _ab().DeviceError(rc)
         return out
+
+    def fetch_view(self) -> np.ndarray:
+        """The gathered records as a view of the communicator's page-locked host buffer (valid until the
+        next fetch_view / search on this communicator)."""
+        n, ptr = C.c_uint64(), C.c_void_p()
+        rc = self._lib.acg_comm_fetch_view(self._h, C.byref(ptr), C.byref(n))
+        if rc:
+            raise _ab().DeviceError(rc)
+        if n.value == 0:
+            return np.zeros(0, MATCH_DTYPE)
+        buf = (C.c_uint8 * (n.value * MATCH_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=MATCH_DTYPE)
 
     def checksum(self):
         n, f = C.c_uint64(), C.c_uint64()

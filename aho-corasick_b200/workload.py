@@ -110,6 +110,10 @@ CONFIGS = {
     # over a synthetic haystack: the byte-set scan's workload
     "cfg1": dict(patterns=[b"apple", b"maple", b"Snapple"], n_patterns=3, pattern_seed=0, hay_seed=0xAC4611,
                  alphabet=(0x20, 0x7E)),
+    # three capitalised words in lower-case text: the reference gives this automaton a start-bytes
+    # prefilter (memchr for 'Q') and the needle is as rare as that heuristic hopes -- the byte-set scan's workload
+    "cfg1s": dict(patterns=[b"Quartz", b"Quebec", b"Quixote"], n_patterns=3, pattern_seed=0, hay_seed=0xAC4611,
+                  alphabet=(0x61, 0x7A)),
     # name: (n_patterns, pattern_seed, haystack_seed, alphabet)
     "cfg2": dict(n_patterns=5000, pattern_seed=0xAC5000, hay_seed=0xAC4611, alphabet=(0x20, 0x7E)),
     "cfg2b": dict(n_patterns=5000, pattern_seed=0xAC5000, hay_seed=0xAC4611, alphabet=(0x61, 0x7A)),

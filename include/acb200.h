@@ -242,6 +242,10 @@ int acg_find_overlapping_sharded(const acg_dfa* dfa, acg_comm* comm, const void*
                                  acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats);
 /* Rank 0: copy the records of the most recent sharded search to the host; *n_out = their number. */
 int acg_comm_fetch(const acg_comm* comm, acg_match* out, uint64_t cap, uint64_t* n_out);
+/* Rank 0: the same records in page-locked host memory owned by the communicator (one full-speed
+ * device-to-host copy, no staging through pageable memory); *view stays valid until the next
+ * acg_comm_fetch_view or sharded search on this communicator. */
+int acg_comm_fetch_view(acg_comm* comm, const acg_match** view, uint64_t* n_out);
 /* Count + FNV-1a of the ordered (pid, start, end) stream of the most recent sharded search
  * (rank 0), comparable with acg_count_overlapping_dev on one GPU over the same haystack. */
 int acg_comm_checksum(const acg_comm* comm, uint64_t* n_out, uint64_t* fnv);

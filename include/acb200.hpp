@@ -28,6 +28,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <string_view>
 #include <utility>
 #include <vector>
@@ -341,7 +342,10 @@ class AhoCorasick {
   using SearchFn = int (*)(const acg_dfa*, const uint8_t*, uint64_t, uint64_t, uint64_t, int, acg_match*, uint64_t, uint64_t*);
   Result<MatchIter> collect(SearchFn fn, const Input& in) const {
     Result<MatchIter> r;
-    std::vector<acg_match> buf(cap_hint_);
+    // room for one match per 256 haystack bytes from the start (the device sizes its own tuple buffer
+    // the same way): an ACG_E_OVERFLOW retry repeats the whole copy + scan, so it should be the exception
+    const uint64_t span_len = in.end() > in.start() ? in.end() - in.start() : 0;
+    std::vector<acg_match> buf(std::max<uint64_t>(cap_hint_, span_len / 256 + 64));
     uint64_t n = 0;
     for (;;) {
       int rc = fn(h_, hay(in), in.haystack().size(), in.start(), in.end(), int(in.get_anchored()), buf.data(),
@@ -439,7 +443,8 @@ class Searcher {
   bool find(std::string_view haystack, Match* out) const { return find_in(Input(haystack), out); }  // :491
   // find_iter, :580
   MatchIter find_iter(const Input& in) const {
-    std::vector<acg_match> buf(cap_hint_);
+    const uint64_t span_len = in.end() > in.start() ? in.end() - in.start() : 0;
+    std::vector<acg_match> buf(std::max<uint64_t>(cap_hint_, span_len / 256 + 64));
     uint64_t n = 0;
     for (;;) {
       const int rc = acg_packed_find_iter(h_, hay(in), in.haystack().size(), in.start(), in.end(), buf.data(),

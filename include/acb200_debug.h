@@ -34,8 +34,6 @@ typedef struct {
   uint32_t bs_n;           /* byte-set scan (start-bytes / rare-bytes role): number of needles, 0 = fingerprint filter */
   uint8_t bs_byte[3];
   uint8_t bs_back[3];      /* largest offset of the needle in any pattern (0 for start bytes) */
-  uint8_t pad_[2];
-  uint32_t anchor2;        /* stride 2: the second stage is the anchor-map lookup (no second-stage bits in the bitmap) */
 } acg_prefilter_plan;
 
 /* Fills *out with views of the handle's derived tables.  Works on host-only handles. */
@@ -47,11 +45,11 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 
 /* Kernel / plan variants that never change results, only which instantiation of the prefilter kernel
  * runs or how its first-stage keys are formed; kept switchable so that tools/ab_inproc.py can time
- * them against each other in one process.  (The r01 variants TALL = 1, PAIR = 2 and WALK_HOT = 4 were
- * measured in r02 -- profiles/r02a_ab_*.jsonl -- lost, and are gone.) */
+ * them against each other in one process.  (The r01 variants TALL = 1, PAIR = 2, WALK_HOT = 4 and
+ * LOCAL2 = 16, and an anchor-map second stage for the stride-2 kernel, were measured in r02 --
+ * profiles/r02a_ab_*.jsonl, r02b_*.jsonl, r02f_*.jsonl -- lost, and are gone.) */
 #define ACG_EXP_KEY24 8u         /* stride-2 first stage keyed by the 3 fingerprint bytes only; default: 27 bits (3 bytes +
                                   * low 3 bits of the fourth).  Rebuilds the bitmap. */
-#define ACG_EXP_ANCHOR2 16u      /* stride 2, narrow geometry: second stage = anchor-map lookup, bitmap without second-stage bits */
 #define ACG_EXP_STATIC_TILES 32u /* warp w of a CTA takes tiles w, w + W, ...; default: the warps of a CTA draw their tiles
                                   * from a shared-memory counter.  r02 A/B (profiles/r02b_*.jsonl): dynamic tiles + 27-bit
                                   * keys -7 % on cfg 2, -22 % on cfg 3, -15 % on cfg 5. */

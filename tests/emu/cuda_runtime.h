@@ -317,6 +317,7 @@ inline unsigned __shfl_down_sync(unsigned mask, unsigned v, unsigned delta) {
 // has no notion of convergence, so the caller alone it is.
 inline unsigned __activemask() { return 1u << (emu::g_cur->tid.x & 31); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
 inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
   const unsigned long long v = ((unsigned long long)y << 32) | x;
   unsigned r = 0;

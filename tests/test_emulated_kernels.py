@@ -251,18 +251,18 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_ANCHOR2 = 16,
-# ACG_EXP_STATIC_TILES = 32)
+# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_STATIC_TILES = 32,
+# ACG_EXP_NO_BYTESCAN = 64)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
     assert ab._lib.acg_debug_set_experiment(ac._h, flags) == 0
     return ac
 
 
-@pytest.mark.parametrize("flags", [8, 16, 24, 32, 40, 48, 56])
+@pytest.mark.parametrize("flags", [8, 32, 40])
 @pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
 def test_experimental_variants_match_the_oracle(name, flags):
-    """27-bit first-stage keys, the lane-local second stage and the dynamic tile distribution on the
+    """24-bit first-stage keys and the static tile split (the non-default variants) on the
     cfg 2 / cfg 3 pattern sets: overlapping, find_iter, sub-span, host path, count + FNV."""
     n, seed, nbytes, kind, ci = VARIANTS[name]
     pats, hay = workload(n, seed, nbytes, ci)
@@ -286,7 +286,7 @@ def test_experimental_variants_match_the_oracle(name, flags):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
 
 
-@pytest.mark.parametrize("flags", [8, 16, 24, 32, 56])
+@pytest.mark.parametrize("flags", [0, 8, 32, 40])
 def test_experimental_variants_at_every_alignment(flags):
     """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
     lane-local second stage, tiles drawn dynamically) at 18 pointer phases x 8 span ends."""
@@ -322,7 +322,7 @@ def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
 
 
-@pytest.mark.parametrize("flags", [16, 32, 48])
+@pytest.mark.parametrize("flags", [0, 32])
 def test_experimental_variants_unselective_steps(flags):
     pats = [b"abab", b"baba", b"ababab"] + W.make_patterns(5000, 0xAC5000)
     ac = set_experiment(build(pats, 0), flags)
@@ -557,11 +557,10 @@ def test_concurrent_searches_lease_separate_workspaces():
 
 # ---- byte-set scan: the start-bytes / rare-bytes prefilter role (bytescan_kernel) -----------------
 BYTESCAN_SETS = [
-    ("start3", [b"apple", b"maple", b"Snapple"], dict()),                       # README example: start bytes a, m, S
+    ("start3", [b"Quartz", b"Xenon", b"Zanzibar"], dict()),                     # start bytes Q, X, Z
     ("start1", [b"xylophone", b"xyz", b"xx"], dict()),
     ("start_ci", [b"Sam", b"samwise"], dict(ci=True)),                          # S, s
-    ("rare", [b"zebra", b"crazy", b"jazz", b"quiz"], dict()),                   # rare bytes z (and q?) with offsets
-    ("rare_long", [b"abcdefghijklmnoz", b"zabcdefghijklmno", b"hello world q"], dict()),
+    ("start2", [b"Quartz", b"Quebec", b"Zanzibar"], dict()),
     ("leftmost", [b"apple", b"app", b"maple syrup", b"ma"], dict(kind=1)),
     ("leftmost_longest", [b"apple", b"app", b"maple syrup", b"ma"], dict(kind=2)),
 ]
@@ -571,7 +570,7 @@ BYTESCAN_SETS = [
 def test_bytescan_engine(name, pats, kw):
     kind, ci = kw.get("kind", 0), kw.get("ci", False)
     rng = np.random.default_rng(len(name))
-    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz SM .,", dtype=np.uint8)
+    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz SMQ.,", dtype=np.uint8)
     hay = alpha[rng.integers(0, len(alpha), size=96 << 10)].copy()
     for i in range(0, hay.size - 64, 977):      # plant occurrences at many alignments
         p = pats[(i // 977) % len(pats)]
@@ -584,7 +583,7 @@ def test_bytescan_engine(name, pats, kw):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), name)
     assert ac.last_stats()["engine"] == int(ab.Engine.Prefilter)
     cand = ac.last_stats()["candidates"]
-    assert 0 < cand <= hay.size   # (rare bytes with large offsets in a 32-letter text: nearly every offset)
+    assert 0 < cand < hay.size // 4
     if kind == 0:
         eq(ac.find_overlapping_iter_dev_np(ptr, hay.size)[0], o.find_overlapping_iter_np(hay), name)
         eq(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay), (name, "host"))
@@ -609,6 +608,8 @@ def test_bytescan_retires_when_needles_are_everywhere():
     ac = ab.AhoCorasick.builder().build(pats)
     assert plan_of(ac).bs_n == 1
     hay = np.frombuffer(b"aaaaab" * 30000, dtype=np.uint8).copy()
+    assert ab.AhoCorasick.builder().build([b"apple", b"maple", b"Snapple"]).prefilter_kind() == 3   # rare bytes with
+    assert plan_of(ab.AhoCorasick.builder().build([b"apple", b"maple", b"Snapple"])).bs_n == 0       # offsets: fingerprints
     o = O.Oracle(pats)
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "dense needles")
     assert plan_of(ac).bs_n == 0

@@ -72,7 +72,7 @@ def test_packed_random_differential(okind, kind):
 
 def test_concurrent_searches_on_one_handle():
     """The reference's automata are Send + Sync and searched through &self from many threads
-    (src/lib.rs:274-326); an acg_dfa handle serialises concurrent searches internally.  Several
+    (src/lib.rs:274-326); an acg_dfa handle leases a workspace of its pool to every search.  Several
     threads share one AhoCorasick and one packed Searcher (ctypes releases the GIL during a call)."""
     from concurrent.futures import ThreadPoolExecutor
 

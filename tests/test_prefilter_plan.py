@@ -30,8 +30,7 @@ class Plan(C.Structure):
                 ("bitmap", C.POINTER(C.c_uint32)), ("bitmap_words", C.c_uint64),
                 ("amap", C.POINTER(C.c_uint64)), ("amap_log", C.c_uint32),
                 ("depth16", C.POINTER(C.c_uint16)), ("n_rows", C.c_uint64), ("dup_shift", C.c_uint32),
-                ("key_shift", C.c_uint32), ("bs_n", C.c_uint32), ("bs_byte", C.c_uint8 * 3), ("bs_back", C.c_uint8 * 3),
-                ("pad_", C.c_uint8 * 2), ("anchor2", C.c_uint32)]
+                ("key_shift", C.c_uint32), ("bs_n", C.c_uint32), ("bs_byte", C.c_uint8 * 3), ("bs_back", C.c_uint8 * 3)]
 
 
 def plan_of(ac):
@@ -82,15 +81,16 @@ def first_stage_hit(p, window):
         # blocked filter: the word from the top bits of the product, two bits from its high half
         prod = gm * p.mult
         lo, hi = prod & M32, (prod >> 32) & M32
+        hi2 = ((gm * 0x85EBCA6B) >> 32) & M32
         w = p.bitmap[lo >> (32 - (p.log_bits - 5))]
-        return (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1
+        return (w >> (hi & 31)) & (w >> (hi2 & 31)) & 1
     h = (gm * p.mult) & M32
     return bit_set(p, h >> p.shift, h & 7)
 
 
 def second_stage_hit(p, window):
-    if p.dense or p.anchor2:
-        return True   # the second stage is the (exact) anchor-map lookup
+    if p.dense:
+        return True   # the dense variant's second stage is the (exact) anchor-map lookup
     gram = (window | p.fold) & p.kmask
     ok = probe_full(p, hash2(gram))
     if p.stride == 2:

@@ -56,6 +56,9 @@ def run_ranks(world, pats, hay, span, on_device=True, engine=ab.Engine.Auto, who
             n, dptr, st, out = comm.find_overlapping(ac, local.ctypes.data, local.size, g0, span,
                                                      on_device=on_device, host_out=True)
             chk = comm.checksum() if rank == 0 else None
+            if out is not None:
+                assert np.array_equal(out, comm.fetch())   # the page-locked view and the copying fetch agree
+                out = out.copy()                           # (the view dies with the communicator)
             res[rank] = (n, out, st, chk)
             comm.close()
         except Exception as e:  # noqa: BLE001
