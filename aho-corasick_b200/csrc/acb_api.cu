@@ -183,6 +183,14 @@ struct WsLease {
     }
     if (rc == ACG_OK) { w->stats = acg_stats{}; tls_ws = w; }
   }
+  // Keep the workspace beyond this scope (a sharded step whose expand kernel is still reading its
+  // tuples); release_workspace() hands it back.
+  Workspace* detach() {
+    Workspace* out = w;
+    if (w) { tls_stats = w->stats; tls_stats_owner = a; tls_ws = prev; }
+    w = nullptr;
+    return out;
+  }
   ~WsLease() {
     if (!w) return;
     tls_stats = w->stats;
@@ -195,14 +203,19 @@ struct WsLease {
   }
 };
 
+void release_workspace(const acg_dfa* a, Workspace* w) {
+  if (!w) return;
+  std::lock_guard<std::mutex> lk(a->mu);
+  a->last_stats = w->stats;
+  a->ws_free.push_back(w);
+  a->ws_cv.notify_one();
+}
+
 int bits_for(uint64_t v) {
   int b = 0;
   while (v) { ++b; v >>= 1; }
   return b;
 }
-
-// second bit selector of the dense variant's blocked filter; must match acb_prefilter.cu
-constexpr uint32_t kDenseMult2 = 0x85EBCA6Bu;
 
 // second Bloom hash; must match bloom_hash2() in acb_prefilter.cu
 uint32_t bloom_hash2(uint32_t x) {
@@ -375,7 +388,7 @@ void derive_metadata(acg_dfa* a) {
   if (pf.k == 0) return;
   // Dense sets (more fingerprints than a two-probe Bloom filter of 2^20 bits can keep apart; cfg 5:
   // 10^5): a blocked filter instead -- every fingerprint owns one 32-bit word (top 15 bits of
-  // gram * mult) and two bits inside it (bits 0-4 of the high halves of gram * mult and gram * kDenseMult2), so that the
+  // gram * mult) and two bits inside it (bits 0-4 and 5-9 of the product's high half), so that the
   // per-position probe settles both with a single shared-memory load; the second stage is then the
   // exact anchor-map lookup.  Must match the DENSE branch of ACB_PROBE in acb_prefilter.cu.
   const bool dense = best_set.size() > 8192;
@@ -385,8 +398,7 @@ void derive_metadata(acg_dfa* a) {
     for (uint32_t g : best_set) {
       const uint64_t prod = uint64_t(g) * pf.mult;
       const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
-      const uint32_t hi2 = uint32_t((uint64_t(g) * kDenseMult2) >> 32);
-      pf.bitmap[lo >> word_shift] |= (1u << (hi & 31)) | (1u << (hi2 & 31));
+      pf.bitmap[lo >> word_shift] |= (1u << (hi & 31)) | (1u << ((hi >> 5) & 31));
     }
     // pass rate on text drawn from the bytes the patterns use at each fingerprint position
     std::vector<uint8_t> alpha[4];
@@ -405,9 +417,8 @@ void derive_metadata(acg_dfa* a) {
       }
       const uint64_t prod = uint64_t(g) * pf.mult;
       const uint32_t lo = uint32_t(prod), hi = uint32_t(prod >> 32);
-      const uint32_t hi2 = uint32_t((uint64_t(g) * kDenseMult2) >> 32);
       const uint32_t w = pf.bitmap[lo >> word_shift];
-      pass += (w >> (hi & 31)) & (w >> (hi2 & 31)) & 1u;
+      pass += (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1u;
     }
     pf.fill = double(pass) / kTrials;
   }
@@ -1268,15 +1279,13 @@ void shard_plan(uint64_t span_start, uint64_t span_end, int nranks, int rank, ui
   *read_lo = (*own_lo - span_start > back) ? *own_lo - back : span_start;
 }
 
-// The sharded overlapping search of one rank: scan the slice, keep the matches this rank owns,
-// learn the global offsets, and store the records into rank 0's buffer.
-int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
-                 uint64_t hay_off, uint64_t span_start, uint64_t span_end, const acg_match** d_matches,
-                 uint64_t* n_total, acg_match* h_out, uint64_t h_cap, acg_shard_stats* st) {
-  if (!a || !c || !n_total) return ACG_E_INVALID_ARG;
-  *n_total = 0;
-  if (d_matches) *d_matches = nullptr;
-  if (st) *st = acg_shard_stats{};
+// The sharded overlapping search of one rank, first half: scan the slice, keep the matches this
+// rank owns, learn the global offsets, and enqueue the expand kernel that stores the records into
+// rank 0's buffer (half `slot`) plus the closing barrier.  Returns without waiting for the transfer:
+// the step's workspace stays leased (the expand kernel reads its tuples) until sharded_wait.
+int sharded_begin(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
+                  uint64_t hay_off, uint64_t span_start, uint64_t span_end, int* slot_out) {
+  if (!a || !c || !slot_out) return ACG_E_INVALID_ARG;
   // checks that do not depend on the rank come first, so that all ranks fail together
   if (span_start > span_end) return ACG_E_INVALID_SPAN;
   if (a->h.match_kind != ACG_STANDARD) return ACG_E_UNSUPPORTED_OVERLAPPING;
@@ -1285,106 +1294,134 @@ int sharded_impl(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_
   if ((rc = check_start(a->h, 0))) return rc;
   if (!a->on_device) return ACG_E_NO_DEVICE;
   if (a->device != c->device) return ACG_E_INVALID_ARG;
+  const int slot = int(c->step_seq & 1);
+  acg_comm::Step& step = c->steps[slot];
+  if (step.active) return ACG_E_INVALID_ARG;  // two steps in flight at most: wait for the older one first
   uint64_t own_lo, own_hi, read_lo;
   shard_plan(span_start, span_end, c->nranks, c->rank, a->h.max_pattern_len, &own_lo, &own_hi, &read_lo);
   // an empty slice (more ranks than 64-byte blocks) still takes part in the collectives
   const bool covered = own_hi == own_lo || (read_lo >= hay_off && own_hi <= hay_off + hay_len);
-  // the local scan, in local offsets: span [read_lo, own_hi) - hay_off
   TupleResult r;
   uint64_t first = 0;
   uint64_t lspan_s = 0;
-  {
-    DeviceGuard guard(a->device);
-    WsLease lease(a);
-    if (lease.rc) return lease.rc;  // (a rank that cannot even get a stream cannot join the exchange either)
-    if (covered && own_hi > own_lo) {
-      lspan_s = read_lo - hay_off;
-      const uint64_t lspan_e = own_hi - hay_off;
-      int engine = a->engine_override;
-      if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) engine = ACG_ENGINE_AUTO;
-      if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
-        engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
-      cur_ws().stats.engine = engine;
-      const uint8_t* d_base = hay;
-      uint64_t readable = hay_len;
-      const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
-      if (!hay_on_device) {
-        rc = stage_host_span(a, hay, lspan_s, lspan_e, &d_base, pipelined);
-        readable = lspan_e + 32;
-      }
-      if (!rc) {
-        if (engine == ACG_ENGINE_PREFILTER)
-          rc = run_prefilter(a, d_base, readable, lspan_s, lspan_e, 0, &r, pipelined ? hay : nullptr);
-        else rc = run_walk_overlapping(a, d_base, readable, lspan_s, lspan_e, &r);
-      }
-      if (!rc && r.n && own_lo > read_lo) {
-        // ends <= own_lo belong to the previous rank: first key with end > own_lo
-        Workspace& w = cur_ws();
-        const uint64_t bound_key = (own_lo - read_lo + 1) << acb::kTieBits;
-        cudaError_t e = acb::launch_lower_bound(w.d_keys[r.sorted_buf], r.n, bound_key, w.d_counter, w.stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
-        if (e != cudaSuccess) { cudaGetLastError(); rc = ACG_E_CUDA; }
-        else first = *w.h_counter;
-      }
+  DeviceGuard guard(a->device);
+  WsLease lease(a);
+  if (lease.rc) return lease.rc;  // (a rank that cannot even get a stream cannot join the exchange either)
+  if (covered && own_hi > own_lo) {
+    // the local scan, in local offsets: span [read_lo, own_hi) - hay_off
+    lspan_s = read_lo - hay_off;
+    const uint64_t lspan_e = own_hi - hay_off;
+    int engine = a->engine_override;
+    if (engine == ACG_ENGINE_PREFILTER && !a->pf.supported) engine = ACG_ENGINE_AUTO;
+    if (engine != ACG_ENGINE_WALK && engine != ACG_ENGINE_PREFILTER)
+      engine = a->pf.supported ? ACG_ENGINE_PREFILTER : ACG_ENGINE_WALK;
+    cur_ws().stats.engine = engine;
+    const uint8_t* d_base = hay;
+    uint64_t readable = hay_len;
+    const bool pipelined = !hay_on_device && engine == ACG_ENGINE_PREFILTER;
+    if (!hay_on_device) {
+      rc = stage_host_span(a, hay, lspan_s, lspan_e, &d_base, pipelined);
+      readable = lspan_e + 32;
     }
-    if (!covered) rc = ACG_E_INVALID_SPAN;
-    // a failed rank still joins the exchange (with the error flag in the top bit) so that nobody hangs
-    const uint64_t mine = rc ? 0 : r.n - first;
-    DeviceGuard cguard(c->device);
-    cudaEventRecord(c->ev0, c->stream);
-    uint64_t total = 0, my_off = 0;
-    int rc2 = acb::comm_exchange_counts(c, mine | (rc ? (1ull << 63) : 0), &total, &my_off);
-    if (rc2) return rc ? rc : rc2;
-    bool any_failed = false;
-    total = 0; my_off = 0;
-    for (int g = 0; g < c->nranks; ++g) {
-      if (c->counts[size_t(g)] >> 63) any_failed = true;
-      c->counts[size_t(g)] &= ~(1ull << 63);
-      if (g < c->rank) my_off += c->counts[size_t(g)];
-      total += c->counts[size_t(g)];
+    if (!rc) {
+      if (engine == ACG_ENGINE_PREFILTER)
+        rc = run_prefilter(a, d_base, readable, lspan_s, lspan_e, 0, &r, pipelined ? hay : nullptr);
+      else rc = run_walk_overlapping(a, d_base, readable, lspan_s, lspan_e, &r);
     }
-    if (any_failed) return rc ? rc : ACG_E_CUDA;  // some other rank failed: nothing was gathered
-    if ((rc = acb::comm_ensure_recv(c, total))) return rc;
-    uint8_t* target = nullptr;
-    if ((rc = acb::comm_record_target(c, my_off, mine, &target))) return rc;
-    if (mine) {
+    if (!rc && r.n && own_lo > read_lo) {
+      // ends <= own_lo belong to the previous rank: first key with end > own_lo
       Workspace& w = cur_ws();
-      acb::ExpandLaunch e;
-      e.keys = w.d_keys[r.sorted_buf];
-      e.pids = w.d_pids[r.sorted_buf];
-      e.pattern_lens = a->d_plens;
-      e.n = r.n;
-      e.first = first;
-      e.span_start = lspan_s;
-      e.offset_add = hay_off;
-      e.out = reinterpret_cast<uint64_t*>(target);
-      CK(acb::launch_expand(e, c->stream));
+      const uint64_t bound_key = (own_lo - read_lo + 1) << acb::kTieBits;
+      cudaError_t e = acb::launch_lower_bound(w.d_keys[r.sorted_buf], r.n, bound_key, w.d_counter, w.stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(w.h_counter, w.d_counter, 8, cudaMemcpyDeviceToHost, w.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(w.stream);
+      if (e != cudaSuccess) { cudaGetLastError(); rc = ACG_E_CUDA; }
+      else first = *w.h_counter;
     }
-    if ((rc = acb::comm_finish_gather(c, my_off, mine))) return rc;
-    cudaEventRecord(c->ev1, c->stream);
-    cudaEventSynchronize(c->ev1);
-    float gms = 0;
-    cudaEventElapsedTime(&gms, c->ev0, c->ev1);
-    c->last_gather_ms = gms;
-    cur_ws().stats.launches += 3;
-    *n_total = total;
-    if (st) {
-      st->local_matches = mine;
-      st->total_matches = total;
-      st->candidates = cur_ws().stats.candidates;
-      st->scan_ms = cur_ws().stats.scan_ms;
-      st->order_ms = cur_ws().stats.order_ms;
-      st->gather_ms = gms;
-      st->transport = c->transport;
-      st->launches = cur_ws().stats.launches;
-    }
-    if (c->rank == 0) {
-      if (d_matches) *d_matches = reinterpret_cast<const acg_match*>(c->recv_own);
-      if (h_out) {
-        if (total > h_cap) return ACG_E_OVERFLOW;
-        if (total) CK(cudaMemcpy(h_out, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
-      }
+  }
+  if (!covered) rc = ACG_E_INVALID_SPAN;
+  // a failed rank still joins the exchange (with the error flag in the top bit) so that nobody hangs
+  const uint64_t mine = rc ? 0 : r.n - first;
+  cudaEventRecord(step.begun, c->stream);
+  uint64_t total = 0, my_off = 0;
+  int rc2 = acb::comm_exchange_counts(c, mine | (rc ? (1ull << 63) : 0), &total, &my_off);
+  if (rc2) return rc ? rc : rc2;
+  bool any_failed = false;
+  total = 0; my_off = 0;
+  for (int g = 0; g < c->nranks; ++g) {
+    if (c->counts[size_t(g)] >> 63) any_failed = true;
+    c->counts[size_t(g)] &= ~(1ull << 63);
+    if (g < c->rank) my_off += c->counts[size_t(g)];
+    total += c->counts[size_t(g)];
+  }
+  if (any_failed) return rc ? rc : ACG_E_CUDA;  // some other rank failed: nothing was gathered
+  if ((rc = acb::comm_ensure_recv(c, total))) return rc;  // every rank takes the same branch (same totals)
+  uint8_t* target = nullptr;
+  if ((rc = acb::comm_record_target(c, slot, my_off, mine, &target))) return rc;
+  if (mine) {
+    Workspace& w = cur_ws();
+    acb::ExpandLaunch e;
+    e.keys = w.d_keys[r.sorted_buf];
+    e.pids = w.d_pids[r.sorted_buf];
+    e.pattern_lens = a->d_plens;
+    e.n = r.n;
+    e.first = first;
+    e.span_start = lspan_s;
+    e.offset_add = hay_off;
+    e.out = reinterpret_cast<uint64_t*>(target);
+    CK(acb::launch_expand(e, c->stream));
+  }
+  if ((rc = acb::comm_enqueue_close(c, slot, my_off, mine))) return rc;
+  cudaEventRecord(step.done, c->stream);
+  cur_ws().stats.launches += 3;
+  step.mine = mine;
+  step.total = total;
+  step.scan_ms = cur_ws().stats.scan_ms;
+  step.order_ms = cur_ws().stats.order_ms;
+  step.candidates = cur_ws().stats.candidates;
+  step.launches = cur_ws().stats.launches;
+  step.dfa = a;
+  step.lease = lease.detach();
+  step.active = true;
+  ++c->step_seq;
+  *slot_out = slot;
+  return ACG_OK;
+}
+
+// Second half: wait until every rank's records of step `slot` are in rank 0's buffer.
+int sharded_wait(acg_comm* c, int slot, const acg_match** d_matches, uint64_t* n_total, acg_match* h_out,
+                 uint64_t h_cap, acg_shard_stats* st) {
+  if (!c || slot < 0 || slot > 1 || !n_total) return ACG_E_INVALID_ARG;
+  acg_comm::Step& step = c->steps[slot];
+  if (!step.active) return ACG_E_INVALID_ARG;
+  DeviceGuard guard(c->device);
+  const cudaError_t e = cudaEventSynchronize(step.done);
+  release_workspace(static_cast<const acg_dfa*>(step.dfa), static_cast<Workspace*>(step.lease));
+  step.lease = nullptr;
+  step.active = false;
+  if (e != cudaSuccess) { cudaGetLastError(); return ACG_E_CUDA; }
+  float gms = 0;
+  cudaEventElapsedTime(&gms, step.begun, step.done);
+  c->last_gather_ms = gms;
+  *n_total = step.total;
+  if (d_matches) *d_matches = nullptr;
+  if (st) {
+    st->local_matches = step.mine;
+    st->total_matches = step.total;
+    st->candidates = step.candidates;
+    st->scan_ms = step.scan_ms;
+    st->order_ms = step.order_ms;
+    st->gather_ms = gms;
+    st->transport = c->transport;
+    st->launches = step.launches;
+  }
+  if (c->rank == 0) {
+    c->last_result = acb::comm_half(c, slot);
+    c->last_total = step.total;
+    if (d_matches) *d_matches = reinterpret_cast<const acg_match*>(c->last_result);
+    if (h_out) {
+      if (step.total > h_cap) return ACG_E_OVERFLOW;
+      if (step.total) CK(cudaMemcpy(h_out, c->last_result, size_t(step.total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
     }
   }
   return ACG_OK;
@@ -1982,7 +2019,17 @@ int acg_comm_unique_id(uint8_t id[ACG_COMM_ID_BYTES]) { return acb::comm_unique_
 int acg_comm_init(const uint8_t id[ACG_COMM_ID_BYTES], int rank, int nranks, acg_comm** out) {
   return acb::comm_create(id, rank, nranks, out);
 }
-void acg_comm_free(acg_comm* c) { acb::comm_destroy(c); }
+void acg_comm_free(acg_comm* c) {
+  if (!c) return;
+  for (auto& step : c->steps) {  // steps nobody waited for: let their kernels finish, hand the workspaces back
+    if (!step.active) continue;
+    DeviceGuard guard(c->device);
+    cudaEventSynchronize(step.done);
+    release_workspace(static_cast<const acg_dfa*>(step.dfa), static_cast<Workspace*>(step.lease));
+    step.active = false;
+  }
+  acb::comm_destroy(c);
+}
 int acg_comm_rank(const acg_comm* c) { return c ? c->rank : -1; }
 int acg_comm_size(const acg_comm* c) { return c ? c->nranks : 0; }
 int acg_comm_transport(const acg_comm* c) { return c ? c->transport : ACG_TRANSPORT_NONE; }
@@ -1999,26 +2046,45 @@ int acg_find_overlapping_sharded(const acg_dfa* a, acg_comm* c, const void* hay,
                                  uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
                                  uint64_t span_end, const acg_match** d_matches, uint64_t* n_total,
                                  acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats) {
-  return sharded_impl(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
-                      span_start, span_end, d_matches, n_total, h_out, h_cap, stats);
+  if (!n_total) return ACG_E_INVALID_ARG;
+  *n_total = 0;
+  if (d_matches) *d_matches = nullptr;
+  if (stats) *stats = acg_shard_stats{};
+  int slot = 0;
+  int rc = sharded_begin(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
+                         span_start, span_end, &slot);
+  if (rc == ACG_E_OVERFLOW && c && (c->steps[0].active || c->steps[1].active)) rc = ACG_E_INVALID_ARG;
+  if (rc) return rc;
+  return sharded_wait(c, slot, d_matches, n_total, h_out, h_cap, stats);
+}
+
+int acg_find_overlapping_sharded_begin(const acg_dfa* a, acg_comm* c, const void* hay, int hay_on_device,
+                                       uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
+                                       uint64_t span_end, int* ticket) {
+  return sharded_begin(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
+                       span_start, span_end, ticket);
+}
+int acg_find_overlapping_sharded_wait(acg_comm* c, int ticket, const acg_match** d_matches, uint64_t* n_total,
+                                      acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats) {
+  if (n_total) *n_total = 0;
+  if (stats) *stats = acg_shard_stats{};
+  return sharded_wait(c, ticket, d_matches, n_total, h_out, h_cap, stats);
 }
 
 int acg_comm_fetch(const acg_comm* c, acg_match* out, uint64_t cap, uint64_t* n_out) {
   if (!c || !n_out) return ACG_E_INVALID_ARG;
-  uint64_t total = 0;
-  for (uint64_t v : c->counts) total += v;
+  const uint64_t total = c->last_total;
   *n_out = total;
   if (c->rank != 0) return ACG_E_INVALID_ARG;
   if (total > cap || (total && !out)) return ACG_E_OVERFLOW;
   DeviceGuard guard(c->device);
-  if (total) CK(cudaMemcpy(out, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+  if (total) CK(cudaMemcpy(out, c->last_result, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost));
   return ACG_OK;
 }
 
 int acg_comm_fetch_view(acg_comm* c, const acg_match** view, uint64_t* n_out) {
   if (!c || !view || !n_out || c->rank != 0) return ACG_E_INVALID_ARG;
-  uint64_t total = 0;
-  for (uint64_t v : c->counts) total += v;
+  const uint64_t total = c->last_total;
   *n_out = total;
   *view = nullptr;
   DeviceGuard guard(c->device);
@@ -2029,7 +2095,7 @@ int acg_comm_fetch_view(acg_comm* c, const acg_match** view, uint64_t* n_out) {
     c->h_view_cap = cap;
   }
   if (total) {
-    CK(cudaMemcpyAsync(c->h_view, c->recv_own, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_view, c->last_result, size_t(total) * sizeof(acg_match), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   *view = reinterpret_cast<const acg_match*>(c->h_view);
@@ -2038,8 +2104,7 @@ int acg_comm_fetch_view(acg_comm* c, const acg_match** view, uint64_t* n_out) {
 
 int acg_comm_checksum(const acg_comm* c, uint64_t* n_out, uint64_t* fnv) {
   if (!c || !n_out || !fnv || c->rank != 0) return ACG_E_INVALID_ARG;
-  uint64_t total = 0;
-  for (uint64_t v : c->counts) total += v;
+  const uint64_t total = c->last_total;
   *n_out = total;
   uint64_t hsh = 0xcbf29ce484222325ull;
   auto mix = [&](uint64_t v) {
@@ -2051,7 +2116,7 @@ int acg_comm_checksum(const acg_comm* c, uint64_t* n_out, uint64_t* fnv) {
   try { buf.resize(size_t(std::min<uint64_t>(chunk, std::max<uint64_t>(total, 1)))); } catch (const std::bad_alloc&) { return ACG_E_NOMEM; }
   for (uint64_t i = 0; i < total; i += chunk) {
     const uint64_t m = std::min(chunk, total - i);
-    CK(cudaMemcpy(buf.data(), c->recv_own + i * sizeof(acg_match), size_t(m) * sizeof(acg_match), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(buf.data(), c->last_result + i * sizeof(acg_match), size_t(m) * sizeof(acg_match), cudaMemcpyDeviceToHost));
     for (uint64_t j = 0; j < m; ++j) { mix(buf[j].pid); mix(buf[j].start); mix(buf[j].end); }
   }
   *fnv = hsh;

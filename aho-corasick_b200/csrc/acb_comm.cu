@@ -178,6 +178,8 @@ int comm_create(const uint8_t* id128, int rank, int nranks, acg_comm** out) {
 #endif
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) return fail(ACG_E_CUDA);
+  for (auto& st : c->steps)
+    if (cudaEventCreate(&st.done) != cudaSuccess || cudaEventCreate(&st.begun) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaMalloc(&c->d_counts, (size_t(nranks) + 1) * 8) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaMallocHost(&c->h_counts, (size_t(nranks) + 1) * 8) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaMalloc(&c->d_handle, 64) != cudaSuccess) return fail(ACG_E_CUDA);
@@ -213,6 +215,10 @@ void comm_destroy(acg_comm* c) {
   if (c->h_view) cudaFreeHost(c->h_view);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (auto& st : c->steps) {
+    if (st.done) cudaEventDestroy(st.done);
+    if (st.begun) cudaEventDestroy(st.begun);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -248,9 +254,11 @@ int comm_exchange_counts(acg_comm* c, uint64_t mine, uint64_t* total, uint64_t* 
 
 int comm_ensure_recv(acg_comm* c, uint64_t total) {
   if (total <= c->recv_cap) return ACG_OK;
-  // every rank sees the same totals, so all of them take this branch together and agree on the size
+  // every rank sees the same totals, so all of them take this branch together and agree on the size.
+  // The buffer cannot move under a step that is still writing into it: the caller waits first.
+  if (c->steps[0].active || c->steps[1].active) return ACG_E_OVERFLOW;
   const uint64_t cap = total + total / 8 + 1024;
-  const size_t bytes = size_t(cap) * sizeof(acg_match);
+  const size_t bytes = 2 * size_t(cap) * sizeof(acg_match);  // two halves
 #ifndef ACB_EMULATE
   NcclComm comm = static_cast<NcclComm>(c->nccl);
   if (c->recv_peer) { cudaIpcCloseMemHandle(c->recv_peer); c->recv_peer = nullptr; }
@@ -311,11 +319,11 @@ int comm_ensure_recv(acg_comm* c, uint64_t total) {
   return ACG_OK;
 }
 
-int comm_record_target(acg_comm* c, uint64_t my_offset, uint64_t mine, uint8_t** target) {
+int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, uint8_t** target) {
   if (c->transport == ACG_TRANSPORT_PEER || c->rank == 0) {
     uint8_t* base = c->rank == 0 ? c->recv_own : c->recv_peer;
     if (!base) return ACG_E_CUDA;
-    *target = base + my_offset * sizeof(acg_match);
+    *target = base + (size_t(slot) * size_t(c->recv_cap) + my_offset) * sizeof(acg_match);
     return ACG_OK;
   }
   if (mine > c->send_cap) {
@@ -328,7 +336,7 @@ int comm_record_target(acg_comm* c, uint64_t my_offset, uint64_t mine, uint8_t**
   return ACG_OK;
 }
 
-int comm_finish_gather(acg_comm* c, uint64_t my_offset, uint64_t mine) {
+int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine) {
   (void)my_offset;
 #ifndef ACB_EMULATE
   NcclComm comm = static_cast<NcclComm>(c->nccl);
@@ -336,10 +344,11 @@ int comm_finish_gather(acg_comm* c, uint64_t my_offset, uint64_t mine) {
     if (c->transport == ACG_TRANSPORT_NCCL) {
       CKN(nccl().GroupStart());
       if (c->rank == 0) {
+        uint8_t* half = comm_half(c, slot);
         uint64_t off = c->counts[0];
         for (int r = 1; r < c->nranks; ++r) {
           if (c->counts[size_t(r)])
-            CKN(nccl().Recv(c->recv_own + off * sizeof(acg_match), size_t(c->counts[size_t(r)]) * sizeof(acg_match),
+            CKN(nccl().Recv(half + off * sizeof(acg_match), size_t(c->counts[size_t(r)]) * sizeof(acg_match),
                             kNcclUint8, r, comm, c->stream));
           off += c->counts[size_t(r)];
         }
@@ -352,9 +361,8 @@ int comm_finish_gather(acg_comm* c, uint64_t my_offset, uint64_t mine) {
     // ordered behind the expand kernel on every rank's stream
     CKN(nccl().AllGather(c->d_counts + c->nranks, c->d_counts, 1, kNcclUint64, comm, c->stream));
   }
-  CKC(cudaStreamSynchronize(c->stream));
 #else
-  (void)mine;
+  (void)mine; (void)slot;
   Fabric* f = static_cast<Fabric*>(c->nccl);
   CKC(cudaStreamSynchronize(c->stream));
   std::unique_lock<std::mutex> lk(f->mu);

@@ -24,9 +24,9 @@ struct acg_comm {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int transport = 0;               // ACG_TRANSPORT_*
   // receive buffer: owned by rank 0 (recv_own), mapped by the others (recv_peer)
-  uint8_t* recv_own = nullptr;
+  uint8_t* recv_own = nullptr;     // 2 * recv_cap records: two halves, one per step in flight
   uint8_t* recv_peer = nullptr;
-  uint64_t recv_cap = 0;           // records; identical on every rank
+  uint64_t recv_cap = 0;           // records per half; identical on every rank
   // nccl transport: local staging of this rank's records
   uint8_t* send_buf = nullptr;
   uint64_t send_cap = 0;
@@ -36,6 +36,22 @@ struct acg_comm {
   std::vector<uint64_t> counts;            // last call: records per rank
   uint8_t* h_view = nullptr;               // pinned host copy of the gathered records (acg_comm_fetch_view)
   uint64_t h_view_cap = 0;                 // records
+  // Steps in flight (acg_find_overlapping_sharded_begin / _wait): at most two, slot = step parity.
+  // The scan of step k + 1 overlaps the transfer of step k's records into rank 0's buffer.
+  struct Step {
+    bool active = false;
+    void* lease = nullptr;                 // the workspace of the handle whose tuples the expand kernel reads
+    const void* dfa = nullptr;
+    uint64_t mine = 0, total = 0;
+    cudaEvent_t done = nullptr;            // behind the closing barrier of the step on `stream`
+    cudaEvent_t begun = nullptr;           // before the count exchange of the step
+    float scan_ms = 0, order_ms = 0;
+    uint64_t candidates = 0;
+    int launches = 0;
+  } steps[2];
+  uint64_t step_seq = 0;                   // steps begun
+  const uint8_t* last_result = nullptr;    // rank 0: records of the step that was waited for last
+  uint64_t last_total = 0;
   float last_gather_ms = 0;
 };
 
@@ -49,11 +65,14 @@ void comm_destroy(acg_comm* c);
 int comm_exchange_counts(acg_comm* c, uint64_t mine, uint64_t* total, uint64_t* my_offset);
 // All ranks: make the receive buffer hold at least `total` records (collective when it must grow).
 int comm_ensure_recv(acg_comm* c, uint64_t total);
-// Where this rank's expand kernel writes record `my_offset` (peer transport), or its local staging
-// buffer (nccl transport; comm_ship_records then moves it).
-int comm_record_target(acg_comm* c, uint64_t my_offset, uint64_t mine, uint8_t** target);
-// After the expand kernel was enqueued on c->stream: move the payload if the transport needs it and
-// close the step (every rank's records are in rank 0's buffer when this returns).
-int comm_finish_gather(acg_comm* c, uint64_t my_offset, uint64_t mine);
+// Where this rank's expand kernel writes record `my_offset` of half `slot` (peer transport), or its
+// local staging buffer (nccl transport; comm_enqueue_close then moves it).
+int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, uint8_t** target);
+// After the expand kernel was enqueued on c->stream: enqueue the payload transfer if the transport
+// needs one and the closing barrier; nothing is waited for (the step's `done` event is recorded by
+// the caller behind it).
+int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine);
+// Rank 0's half `slot` of the receive buffer.
+inline uint8_t* comm_half(acg_comm* c, int slot) { return c->recv_own + size_t(slot) * size_t(c->recv_cap) * 24; }
 
 }  // namespace acb

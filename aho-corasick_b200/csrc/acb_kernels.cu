@@ -218,13 +218,16 @@ __global__ void seq_find_kernel(DfaDev d, SeqLaunch p) {
   *p.counter = n;
 }
 
-// 256 records per CTA, built in shared memory and stored as 16-byte vectors: the target may be
+// 128 records per CTA, built in shared memory and stored as 16-byte vectors: the target may be
 // another GPU's HBM (peer mapping of rank 0's receive buffer, acb_comm.hpp), where full 128-byte
-// lines per warp store matter more than at home.  Record = acg_match { u32 pid; u32 pad; u64 start; u64 end }.
-__global__ void __launch_bounds__(256) expand_kernel(ExpandLaunch e) {
-  __shared__ uint64_t s_rec[256 * 3];
+// lines per warp store matter more than at home.  Small on purpose -- 128 threads, 3 KB of shared
+// memory -- so that a CTA fits beside the persistent scan CTA of the next sharded step on the same SM
+// and the transfer overlaps that scan.  Record = acg_match { u32 pid; u32 pad; u64 start; u64 end }.
+constexpr int kExpandThreads = 128;
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(ExpandLaunch e) {
+  __shared__ uint64_t s_rec[kExpandThreads * 3];
   const uint64_t m = e.n - e.first;
-  const uint64_t base = (uint64_t)blockIdx.x * 256;
+  const uint64_t base = (uint64_t)blockIdx.x * kExpandThreads;
   const uint64_t i = base + threadIdx.x;
   if (i < m) {
     const uint64_t key = e.keys[e.first + i];
@@ -235,15 +238,15 @@ __global__ void __launch_bounds__(256) expand_kernel(ExpandLaunch e) {
     s_rec[threadIdx.x * 3 + 2] = end;
   }
   __syncthreads();
-  const uint64_t cnt = m - base < 256 ? m - base : 256;  // records of this CTA
+  const uint64_t cnt = m - base < kExpandThreads ? m - base : kExpandThreads;  // records of this CTA
   uint64_t* dst = e.out + base * 3;
   const uint32_t words = (uint32_t)cnt * 3;  // 8-byte words; base * 24 is a multiple of 16
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    for (uint32_t w = threadIdx.x * 2; w + 1 < words; w += 512)
+    for (uint32_t w = threadIdx.x * 2; w + 1 < words; w += 2 * kExpandThreads)
       *reinterpret_cast<ulonglong2*>(dst + w) = make_ulonglong2(s_rec[w], s_rec[w + 1]);
     if ((words & 1) && threadIdx.x == 0) dst[words - 1] = s_rec[words - 1];
   } else {
-    for (uint32_t w = threadIdx.x; w < words; w += 256) dst[w] = s_rec[w];
+    for (uint32_t w = threadIdx.x; w < words; w += kExpandThreads) dst[w] = s_rec[w];
   }
 }
 
@@ -264,7 +267,7 @@ __global__ void lower_bound_kernel(const uint64_t* keys, uint64_t n, uint64_t bo
 cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s) {
   const uint64_t m = e.n - e.first;
   if (m == 0) return cudaSuccess;
-  ACB_LAUNCH(expand_kernel, (unsigned)((m + 255) / 256), 256, 0, s, e);
+  ACB_LAUNCH(expand_kernel, (unsigned)((m + kExpandThreads - 1) / kExpandThreads), kExpandThreads, 0, s, e);
   return cudaGetLastError();
 }
 cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_key,

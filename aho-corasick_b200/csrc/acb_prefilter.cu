@@ -74,10 +74,6 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
   return x;
 }
 
-// second bit selector of the dense variant's blocked filter: high half of gram * kDenseMult2.
-// Must match acb_api.cu.
-constexpr uint32_t kDenseMult2 = 0x85EBCA6Bu;
-
 constexpr int kPfStages = 2;            // ring depth per warp (TMA bulk copies + mbarriers, acb_ptx.cuh)
 
 struct Emitter {
@@ -428,14 +424,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     if constexpr (DENSE) {                                                                    \
       /* blocked filter: one word per key (top bits of the product), two bits inside it (low    \
          bits of the product's high half) -- both tested with this one load */                  \
-      /* the ALU pipe (shifts, logic) is what saturates here, so everything that can be a         \
-         multiply is one: word index and both bit selectors are high halves of products (FMA     \
-         pipe), and the hit bit enters the mask through a multiply-add (first probe ends up in   \
-         the top bit; the mask is bit-reversed once after the last probe) */                     \
       const uint32_t ph = __umulhi(gm, mult);                                                  \
-      const uint32_t ph2 = __umulhi(gm, kDenseMult2);                                          \
-      const uint32_t bw = s_bitmap[__umulhi(h, 1u << (32 - kBloomShift - 2))];                 \
-      mask = mask * 2u + (__funnelshift_r(bw, bw, ph) & __funnelshift_r(bw, bw, ph2) & 1u);    \
+      const uint32_t bw = s_bitmap[h >> (kBloomShift + 2)];                                    \
+      mask = __funnelshift_r(mask, __funnelshift_r(bw, bw, ph) & __funnelshift_r(bw, bw, ph >> 5), 1); \
     } else {                                                                                  \
       const uint32_t rep = (uint32_t)s_bytes[h >> kBloomShift] * 0x01010101u;                 \
       mask = __funnelshift_r(mask, __funnelshift_r(rep, rep, sel), 1);                        \
@@ -456,8 +447,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
 #undef ACB_PROBE
 #undef ACB_WIN
     // the probes were funnelled in from the top: move the first one down to bit 0
-    if constexpr (DENSE) mask = __brev(mask);  // (dense: shifted in from the bottom, 32 probes)
-    else if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
+    if constexpr (kHitBits < 32) mask >>= (32 - kHitBits);
     if (t + 1 == n_tiles) {
       // the last tile may be short: drop the hit bits of groups behind its end
       uint32_t ok_bits = 0;
@@ -750,19 +740,26 @@ __global__ void __launch_bounds__(kBsThreads, 2) bytescan_kernel(DfaDev d, Prefi
       }
     }
   };
-  // four steps per iteration: four 512-byte loads of the warp in flight
+  // Software pipeline: the loads of the next two steps are issued before the current two are
+  // examined, so every warp keeps 1-2 KiB in flight while it computes (the compare phase of a warp is
+  // about as long as a DRAM round trip; without the prefetch half of the latency is exposed).
   const uint64_t stride = (uint64_t)gridDim.x * kBsWarps;
-  for (uint64_t st = (uint64_t)blockIdx.x * kBsWarps + warp; st < n_steps; st += 4 * stride) {
-    uint64_t base[4];
-    uint4 v[4];
+  auto base_of = [&](uint64_t st) { return p.region_lo + st * step_bytes + (uint64_t)lane * 16; };  // this lane's 16 bytes
+  uint64_t st = (uint64_t)blockIdx.x * kBsWarps + warp;
+  uint4 cur[2], nxt[2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      base[u] = p.region_lo + (st + u * stride) * step_bytes + (uint64_t)lane * 16;  // this lane's 16 bytes
-      v[u] = st + u * stride < n_steps ? load(base[u]) : make_uint4(0, 0, 0, 0);
+  for (int u = 0; u < 2; ++u) cur[u] = st + u * stride < n_steps ? load(base_of(st + u * stride)) : make_uint4(0, 0, 0, 0);
+  for (; st < n_steps; st += 2 * stride) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint64_t sn = st + (2 + u) * stride;
+      nxt[u] = sn < n_steps ? load(base_of(sn)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (st + u * stride < n_steps) process(base[u], v[u]);
+    for (int u = 0; u < 2; ++u)
+      if (st + u * stride < n_steps) process(base_of(st + u * stride), cur[u]);
+    cur[0] = nxt[0];
+    cur[1] = nxt[1];
   }
   if (qlen) drain();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);

@@ -82,6 +82,24 @@ class Comm:
         stats = {k: getattr(st, k) for k, _ in ShardStats._fields_}
         return n.value, (dptr.value or 0), stats, out
 
+    def begin(self, ac, hay_ptr, hay_len, hay_global_offset, span, on_device=True) -> int:
+        """Collective, first half of find_overlapping (acg_find_overlapping_sharded_begin): returns a
+        ticket once this rank's records are on their way; at most two steps in flight."""
+        t = C.c_int()
+        rc = self._lib.acg_find_overlapping_sharded_begin(ac._h, self._h, hay_ptr, 1 if on_device else 0, hay_len,
+                                                          hay_global_offset, span[0], span[1], C.byref(t))
+        if rc:
+            _ab().AhoCorasick._raise(rc)
+        return t.value
+
+    def wait(self, ticket: int):
+        """Collective, second half: (n_total, device pointer on rank 0, stats)."""
+        dptr, n, st = C.c_void_p(), C.c_uint64(), ShardStats()
+        rc = self._lib.acg_find_overlapping_sharded_wait(self._h, ticket, C.byref(dptr), C.byref(n), None, 0, C.byref(st))
+        if rc:
+            _ab().AhoCorasick._raise(rc)
+        return n.value, (dptr.value or 0), {k: getattr(st, k) for k, _ in ShardStats._fields_}
+
     def fetch(self) -> np.ndarray:
         n = C.c_uint64()
         self._lib.acg_comm_fetch(self._h, None, 0, C.byref(n))

@@ -240,6 +240,17 @@ int acg_find_overlapping_sharded(const acg_dfa* dfa, acg_comm* comm, const void*
                                  uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
                                  uint64_t span_end, const acg_match** d_matches, uint64_t* n_total,
                                  acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats);
+/* The same search in two halves, for callers that run one sharded search after another (a stream of
+ * haystack batches): _begin returns once this rank's records are on their way into rank 0's buffer,
+ * _wait completes the step.  Up to two steps may be in flight, so the scan of batch k + 1 overlaps
+ * the NVLink transfer of batch k's records (rank 0's buffer has two halves; the records of a step
+ * stay valid until the step after the next begins).  Both are collective; every rank must issue
+ * begin / wait in the same order.  *ticket identifies the step for _wait. */
+int acg_find_overlapping_sharded_begin(const acg_dfa* dfa, acg_comm* comm, const void* hay, int hay_on_device,
+                                       uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
+                                       uint64_t span_end, int* ticket);
+int acg_find_overlapping_sharded_wait(acg_comm* comm, int ticket, const acg_match** d_matches, uint64_t* n_total,
+                                      acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats);
 /* Rank 0: copy the records of the most recent sharded search to the host; *n_out = their number. */
 int acg_comm_fetch(const acg_comm* comm, acg_match* out, uint64_t cap, uint64_t* n_out);
 /* Rank 0: the same records in page-locked host memory owned by the communicator (one full-speed

@@ -79,6 +79,22 @@ def main():
     # a second call on the same communicator (buffers reused, counts differ per rank) must agree
     n2, _, st2, _ = comm.find_overlapping(ac, d_hay.data_ptr(), min(n_local, hi - g0), g0, span)
     assert n2 == n, (n, n2)
+    blocking_chk = comm.checksum() if rank == 0 else None
+    # pipelined form: three steps, two in flight (the scan of step k + 1 overlaps the transfer of step k)
+    args_b = (ac, d_hay.data_ptr(), min(n_local, hi - g0), g0, span)
+    t0 = comm.begin(*args_b)
+    t1 = comm.begin(*args_b)
+    r0 = comm.wait(t0)
+    c0 = comm.checksum() if rank == 0 else None
+    t2 = comm.begin(*args_b)
+    r1 = comm.wait(t1)
+    c1 = comm.checksum() if rank == 0 else None
+    r2 = comm.wait(t2)
+    c2 = comm.checksum() if rank == 0 else None
+    assert r0[0] == r1[0] == r2[0] == n, (r0[0], r1[0], r2[0], n)
+    if rank == 0:
+        assert c0 == c1 == c2 == blocking_chk, (c0, c1, c2, blocking_chk)
+    pipe_gather_ms = r2[2]["gather_ms"]
     if rank == 0:
         got_n, got_fnv = comm.checksum()
         assert got_n == n
@@ -107,7 +123,7 @@ def main():
             hits = rec[rec["end"] == end]
             assert len(hits) >= 1 and len(np.unique(hits[["pid", "start", "end"]])) == len(hits), (kind, b, end)
         print(f"MULTIRANK OK world={world} workload={workload} total={total} matches={n} transport={comm.transport()} "
-              f"scan_ms={st['scan_ms']:.3f} gather_ms={st['gather_ms']:.3f} gather_ms_2nd={st2['gather_ms']:.3f}", flush=True)
+              f"scan_ms={st['scan_ms']:.3f} gather_ms={st['gather_ms']:.3f} gather_ms_2nd={st2['gather_ms']:.3f} pipelined_ok gather_ms_in_pipeline={pipe_gather_ms:.3f}", flush=True)
     comm.close()
 
 

@@ -81,9 +81,8 @@ def first_stage_hit(p, window):
         # blocked filter: the word from the top bits of the product, two bits from its high half
         prod = gm * p.mult
         lo, hi = prod & M32, (prod >> 32) & M32
-        hi2 = ((gm * 0x85EBCA6B) >> 32) & M32
         w = p.bitmap[lo >> (32 - (p.log_bits - 5))]
-        return (w >> (hi & 31)) & (w >> (hi2 & 31)) & 1
+        return (w >> (hi & 31)) & (w >> ((hi >> 5) & 31)) & 1
     h = (gm * p.mult) & M32
     return bit_set(p, h >> p.shift, h & 7)
 

@@ -167,3 +167,65 @@ def test_slice_does_not_cover_plan_is_an_error_on_every_rank():
     [t.start() for t in ts]
     [t.join(timeout=120) for t in ts]
     assert out[1] == "ValueError" and out[0] in ("DeviceError", "ValueError"), out
+
+
+def test_pipelined_steps_two_in_flight():
+    """acg_find_overlapping_sharded_begin / _wait over a stream of haystack batches: step k + 1 begins
+    before step k is waited for (two halves of rank 0's buffer, one leased workspace per step); every
+    step's gathered list is the oracle's for its batch; a third begin without a wait is refused."""
+    world = 3
+    pats = W.make_patterns(300, 5)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    batches = []
+    for b in range(5):
+        h = np.empty((24 << 10) + 4096 * b, dtype=np.uint8)
+        W.fill_haystack(h, 100 + b)
+        W.plant(h, pats, 200 + b, period=256, window=128)
+        batches.append(h)
+    wants = [o.find_overlapping_iter_np(h) for h in batches]
+    uid = S.unique_id()
+    got, errs = [None] * len(batches), []
+
+    def work(rank):
+        try:
+            ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats)
+            comm = S.Comm(uid, rank, world)
+            # the buffer must not have to grow with steps in flight: one blocking step sizes it
+            h = batches[-1]
+            comm.find_overlapping(ac, h.ctypes.data, h.size, 0, (0, h.size))
+            tickets = []
+            for k, h in enumerate(batches):
+                tickets.append(comm.begin(ac, h.ctypes.data, h.size, 0, (0, h.size)))
+                if k == 1 and rank == 0:
+                    pass
+                if k >= 1:
+                    n, dptr, st = comm.wait(tickets[k - 1])
+                    if rank == 0:
+                        got[k - 1] = comm.fetch()
+                        assert n == len(got[k - 1])
+            n, dptr, st = comm.wait(tickets[-1])
+            if rank == 0:
+                got[-1] = comm.fetch()
+            comm.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append((rank, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=600) for t in ts]
+    assert not errs, errs
+    for g, w in zip(got, wants):
+        eq(g, w)
+    # protocol errors: a third step without a wait, waiting twice
+    ac = ab.AhoCorasick.builder().kind(ab.AhoCorasickKind.DFA).build(pats)
+    comm = S.Comm(S.unique_id(), 0, 1)
+    h = batches[0]
+    comm.find_overlapping(ac, h.ctypes.data, h.size, 0, (0, h.size))
+    t0 = comm.begin(ac, h.ctypes.data, h.size, 0, (0, h.size))
+    t1 = comm.begin(ac, h.ctypes.data, h.size, 0, (0, h.size))
+    with pytest.raises(ab.DeviceError):
+        comm.begin(ac, h.ctypes.data, h.size, 0, (0, h.size))
+    assert comm.wait(t0)[0] == len(wants[0]) and comm.wait(t1)[0] == len(wants[0])
+    with pytest.raises(ab.DeviceError):
+        comm.wait(t1)
+    comm.close()
