@@ -897,6 +897,8 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
     for (uint32_t i = 0; i < pf.bs_n; ++i) { p.bs_needle[i] = uint32_t(pf.bs_byte[i]) * 0x01010101u; p.bs_back[i] = pf.bs_back[i]; }
     CK(acb::launch_bytescan(a->dev, p, dev_sms, w.stream));
   } else {
+    // counter[2]: the launch's global super-tile counter (dynamic tile distribution), zero at launch
+    if (p.dyn) CK(cudaMemsetAsync(w.d_counter + 2, 0, 8, w.stream));
     CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
   }
   cur_ws().stats.launches += 1;

@@ -124,9 +124,9 @@ struct PrefilterLaunch {
   uint64_t region_lo, region_hi;  // 16-byte aligned filter region inside [scan_lo, scan_hi)
   uint64_t* keys;
   uint32_t* pids;
-  unsigned long long* counter;  // [0] tuples, [1] candidates
+  unsigned long long* counter;  // [0] tuples, [1] candidates, [2] super-tiles handed out (dynamic tile distribution)
   uint64_t cap;
-  uint32_t dyn;                 // 1: the warps of a CTA draw their tiles from a shared counter (see prefilter_kernel)
+  uint32_t dyn;                 // 1: tiles are handed out dynamically, super-tiles per CTA from counter[2] (see prefilter_kernel)
   // byte-set scan (bytescan_kernel, the memchr-class start-bytes / rare-bytes prefilter): bs_n needles,
   // each replicated into the four bytes of a word; a pattern that shows needle i at offset q starts in
   // [q - bs_back[i], q] (0 for start bytes, <= 15)

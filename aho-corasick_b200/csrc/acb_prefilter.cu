@@ -74,6 +74,14 @@ __device__ __forceinline__ uint32_t bloom_hash3(uint32_t x) {
   return x;
 }
 
+// Queued offsets are 32-bit, inside a window of 2^kWinShift bytes of the chunk (prefilter_kernel).
+// The dry run can shrink the window (ACB_EMU_WINSHIFT) so that small inputs cross many of them.
+#ifdef ACB_EMULATE
+static const uint32_t kWinShift = getenv("ACB_EMU_WINSHIFT") ? (uint32_t)atoi(getenv("ACB_EMU_WINSHIFT")) : 31u;
+#else
+constexpr uint32_t kWinShift = 31;
+#endif
+
 constexpr int kPfStages = 2;            // ring depth per warp (TMA bulk copies + mbarriers, acb_ptx.cuh)
 
 struct Emitter {
@@ -263,7 +271,9 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   for (uint32_t i = tid; i < bitmap_words; i += kPfThreads) s_bitmap[i] = p.bitmap[i];
   if (tid < 256) s_cls[tid] = d.classes[tid];
   if (tid < kPfWarps * kPfStages) ptx::mbar_init(ptx::smem_addr(&s_bars[tid]), 1);
-  if (tid == 0) *s_next_tile = 0;
+  // DYN draw state (64 bits at s_next_tile): this CTA starts with super-tile blockIdx.x; whether that
+  // one exists is checked when the first batch is drawn (tiles >= n_tiles are skipped)
+  if (tid == 0) *reinterpret_cast<uint64_t*>(s_next_tile) = (uint64_t)blockIdx.x << 32;
   ptx::mbar_init_fence();
   ptx::fence_proxy_async();
   __syncthreads();
@@ -284,13 +294,15 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     }
   }
 
-  // this CTA's chunk, in units of 16-byte blocks
+  // The chunk of the span this CTA's tile numbers refer to.  Static split: a contiguous 1/gridDim of
+  // the region, in units of 16-byte blocks.  DYN: the whole region -- tiles are handed out globally.
   const uint64_t n_blocks16 = (p.region_hi - p.region_lo) >> 4;
   const uint64_t per_cta = (n_blocks16 + gridDim.x - 1) / gridDim.x;
   const uint64_t b0 = (uint64_t)blockIdx.x * per_cta;
   const uint64_t b1 = min(b0 + per_cta, n_blocks16);
-  const uint64_t chunk_lo = p.region_lo + (b0 << 4);
-  const uint64_t chunk_hi = b0 < b1 ? p.region_lo + (b1 << 4) : chunk_lo;
+  const bool whole = DYN && !p.brute;
+  const uint64_t chunk_lo = whole ? p.region_lo : p.region_lo + (b0 << 4);
+  const uint64_t chunk_hi = whole ? p.region_hi : (b0 < b1 ? p.region_lo + (b1 << 4) : p.region_lo + (b0 << 4));
 
   if (p.brute) {
     for (uint64_t s = chunk_lo + tid; s < chunk_hi; s += kPfThreads) verify_at<MODE>(d, p, s_cls, s, em);
@@ -305,25 +317,31 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint32_t mult8 = p.mult3 << p.key_shift;  // 8: 24-bit keys; 5: 27-bit keys (experiment)
   // queue offsets are relative to chunk_base: a stride-2 probe at the first byte of the chunk
   // also owns the start one byte before it
-  const uint64_t chunk_base = chunk_lo - (uint64_t)(STRIDE - 1) * (chunk_lo > 0 ? 1 : 0);
-  const uint32_t rel_bias = (uint32_t)(chunk_lo - chunk_base);
+  // (unsigned arithmetic: for chunk_lo == 0 the base wraps to 2^64 - 1 and base + rel, rel >= 1, is the
+  // offset again; rel == 0 -- the byte before the region -- is never queued, the head owns it)
+  const uint64_t chunk_base = chunk_lo - (uint64_t)(STRIDE - 1);
+  const uint32_t rel_bias = (uint32_t)(STRIDE - 1);
   const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bitmap);
   unsigned char* ring = s_ring + warp * (kPfStages * kPfStageBytes);
   uint64_t* bars = s_bars + warp * kPfStages;
   uint16_t* slots = s_slots + warp * kSlotsAlloc;
   Q2Entry* q2 = s_queue2 + warp * kPfQ2;
   uint32_t q2len = 0;  // warp-uniform
+  // queued offsets are 32-bit, relative to chunk_base + (q2win << kWinShift): a warp's tiles only
+  // move forward, so the queue is drained when a tile lies in the next 2 GiB window of the chunk
+  uint32_t q2win = 0;  // warp-uniform
 
   auto drain2 = [&]() {  // verify the queued survivors (K3b), one per lane
     __syncwarp();
+    const uint64_t win_base = chunk_base + ((uint64_t)q2win << kWinShift);
     for (uint32_t i = lane; i < q2len; i += 32) {
       if constexpr (ANCH) {
         // (offset, trie state of its first k bytes): the anchor map was consulted when the entry was queued
         const uint2 e = q2[i];
-        if (e.y != 0) verify_from<MODE>(d, p, s_cls, chunk_base + e.x, e.y, d.amap_k, em);
-        else verify_at<MODE>(d, p, s_cls, chunk_base + e.x, em);
+        if (e.y != 0) verify_from<MODE>(d, p, s_cls, win_base + e.x, e.y, d.amap_k, em);
+        else verify_at<MODE>(d, p, s_cls, win_base + e.x, em);
       } else {
-        verify_at<MODE>(d, p, s_cls, chunk_base + q2[i], em);
+        verify_at<MODE>(d, p, s_cls, win_base + q2[i], em);
       }
     }
     cand_total += q2len;
@@ -355,20 +373,44 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     ptx::mbar_arrive_expect_tx(bar, bytes);
     ptx::tma_load_1d(dst, chunk_src + (uint64_t)t * kPfTile, bytes, bar);
   };
-  // DYN: lane 0 draws tile numbers from the CTA's counter -- kDrawBatch consecutive tiles per atomic
-  // -- leaves the number for a stage in s_tile_of[warp][stage] for the warp to read when it gets to
-  // that stage, and requests the tile
-  constexpr uint32_t kDrawBatch = 4;
+  // DYN: tiles are numbered over the whole region and handed out on two levels.  A CTA holds one
+  // super-tile of kSuper consecutive tiles at a time (shared 64-bit state: super-tile index | next
+  // offset inside it) and takes the next one from a global counter when it runs out; lane 0 of a warp
+  // draws kDrawBatch consecutive tiles per shared-memory atomic.  A CTA that starts late, or shares
+  // its SM with another kernel, simply ends up with fewer super-tiles: no second wave, no straggler.
+  // The tile number for a stage is left in s_tile_of[warp][stage] for the warp to read when it gets
+  // to that stage.
+  constexpr uint32_t kDrawBatch = 4, kSuper = 256;
+  static_assert(kSuper % kDrawBatch == 0, "batches never straddle a super-tile");
   uint32_t* tile_of = s_tile_of + warp * kPfStages;
-  const uint32_t next_tile_a = ptx::smem_addr(s_next_tile);
+  const uint32_t draw_a = ptx::smem_addr(s_next_tile);
+  const uint32_t n_super = (n_tiles + kSuper - 1) / kSuper;
+  constexpr uint64_t kNoMore = 0xFFFFFFFFull << 32;
   uint32_t batch_next = 0, batch_left = 0;  // lane 0's current batch
+  bool exhausted = false;
   auto draw = [&](uint32_t stage) {  // lane 0 only
-    if (batch_left == 0) {
-      batch_next = ptx::atoms_add(next_tile_a, kDrawBatch);
-      batch_left = kDrawBatch;
+    while (batch_left == 0 && !exhausted) {
+      const uint64_t v = ptx::atoms_add64(draw_a, kDrawBatch);
+      const uint32_t sup = (uint32_t)(v >> 32), off = (uint32_t)v;
+      if (sup == 0xFFFFFFFFu) { exhausted = true; break; }
+      if (off < kSuper) { batch_next = sup * kSuper + off; batch_left = kDrawBatch; break; }
+      if (off == kSuper) {
+        // the first draw past the end fetches the CTA's next super-tile
+        const unsigned long long g = atomicAdd(p.counter + 2, 1ull) + gridDim.x;
+        if (g < n_super) {
+          ptx::atoms_exch64(draw_a, (g << 32) | kDrawBatch);  // (this warp keeps the first batch)
+          batch_next = (uint32_t)g * kSuper;
+          batch_left = kDrawBatch;
+        } else {
+          ptx::atoms_exch64(draw_a, kNoMore);
+          exhausted = true;
+        }
+        break;
+      }
+      while ((uint32_t)(ptx::lds64_volatile(draw_a) >> 32) == sup) {}  // a refill is under way: ~1 us
     }
-    const uint32_t t = batch_next++;
-    --batch_left;
+    uint32_t t = n_tiles;
+    if (!exhausted) { t = batch_next++; --batch_left; }
     tile_of[stage] = t;
     if (t < n_tiles) issue(t, stage);
   };
@@ -392,6 +434,11 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     else t = (uint32_t)warp + it * (uint32_t)kPfWarps;
     if (t >= n_tiles) break;  // tile numbers only grow: nothing is in flight for this warp any more
     const uint64_t wbase = chunk_lo + (uint64_t)t * kPfTile;
+    const uint32_t win = (uint32_t)(((uint64_t)t * kPfTile) >> kWinShift);
+    if (win != q2win) {  // warp-uniform
+      if (q2len) drain2();
+      q2win = win;
+    }
     while (!ptx::mbar_try_wait(bar0 + stage * 8, parity)) {}
     const uint32_t stage_off = stage * (uint32_t)kPfStageBytes;
     const uint32_t tile_a = ring0 + stage_off;
@@ -477,7 +524,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     if (__any_sync(0xffffffffu, (cnt >> kPlanes) != 0)) total = (uint32_t)kPfSlots + 1;
     if (total) {
       // the very first probe of the region has no start before it
-      const bool region_first = blockIdx.x == 0 && t == 0;
+      const bool region_first = (whole || blockIdx.x == 0) && t == 0;
       if (total > (uint32_t)kPfSlots) {
         // fingerprints not selective here: verify this step's hits in place
         uint32_t nver = 0;
@@ -505,7 +552,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         // second stage, compacted: the work items are (hit, start offset the hit owns) -- the
         // probed offset and, with stride 2, the one before it -- one per lane.  Each is tested
         // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
-        const uint32_t wrel = (uint32_t)(wbase - chunk_lo) + rel_bias;
+        const uint32_t wrel = (uint32_t)((wbase - chunk_lo) - ((uint64_t)win << kWinShift)) + rel_bias;
         const uint32_t n_items = total * STRIDE;
         if constexpr (ANCH) {
           // Anchor-map second stage: the answer is an L2 access away, so every lane takes two items
@@ -530,7 +577,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
                   pass2[u] = !region_first;
                 } else if (d.amap == nullptr) {
                   pass2[u] = true;
-                } else if (chunk_base + rel2[u] + d.amap_k <= p.span_end) {
+                } else if (chunk_base + ((uint64_t)win << kWinShift) + rel2[u] + d.amap_k <= p.span_end) {
                   const uint32_t off = e - j;
                   const uint32_t sa = tile_a + (off & ~3u);
                   key2[u] = __funnelshift_r(ptx::lds32(sa), ptx::lds32(sa + 4), (off & 3) * 8) & d.amap_kmask;

@@ -72,6 +72,21 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t addr, uint32_t v) {
   asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
+// 64-bit shared-memory fetch-and-add / exchange (the CTA's tile-draw state: super-tile | offset)
+__device__ __forceinline__ uint64_t atoms_add64(uint32_t addr, uint64_t v) {
+  uint64_t old;
+  asm volatile("atom.shared.add.u64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void atoms_exch64(uint32_t addr, uint64_t v) {
+  uint64_t old;
+  asm volatile("atom.shared.exch.b64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t lds64_volatile(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
 // make three values opaque to the compiler so that they stay in registers instead of being
 // re-derived (from the thread index) at every use
 __device__ __forceinline__ void keep_in_registers(uint32_t& a, uint32_t& b, uint32_t& c) {

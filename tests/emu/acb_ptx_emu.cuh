@@ -57,6 +57,17 @@ inline uint32_t atoms_add(uint32_t a, uint32_t v) {
   *p = old + v;
   return old;
 }
+inline uint64_t atoms_add64(uint32_t a, uint64_t v) {
+  uint64_t* p = reinterpret_cast<uint64_t*>(smem_ptr(a, 8));
+  const uint64_t old = *p;
+  *p = old + v;
+  return old;
+}
+inline void atoms_exch64(uint32_t a, uint64_t v) { *reinterpret_cast<uint64_t*>(smem_ptr(a, 8)) = v; }
+inline uint64_t lds64_volatile(uint32_t a) {
+  emu::yield();   // a spin on this value must let the thread that changes it run
+  return *reinterpret_cast<uint64_t*>(smem_ptr(a, 8));
+}
 inline void keep_in_registers(uint32_t&, uint32_t&, uint32_t&) {}
 inline uint4 ld_nc_u4(const void* p) {
   if ((uintptr_t)p & 15) emu::die("misaligned 16-byte global load");

@@ -614,3 +614,15 @@ def test_bytescan_retires_when_needles_are_everywhere():
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "dense needles")
     assert plan_of(ac).bs_n == 0
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "after retiring")
+
+
+@pytest.mark.parametrize("shift", [12, 14])
+def test_queue_windows_on_small_inputs(shift):
+    """The 32-bit queued offsets of the prefilter kernel live in windows of the chunk (2 GiB on the
+    device); tests/emu_window_check.py runs the variants with the window shrunk to 4 / 16 KiB."""
+    import os
+    import subprocess
+    env = dict(os.environ, ACB_EMU_WINSHIFT=str(shift))
+    r = subprocess.run([sys.executable, str(ROOT / "tests" / "emu_window_check.py")], capture_output=True, text=True,
+                       env=env, timeout=1200)
+    assert r.returncode == 0 and "WINDOWS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
