@@ -1371,6 +1371,14 @@ int sharded_begin(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on
     e.span_start = lspan_s;
     e.offset_add = hay_off;
     e.out = reinterpret_cast<uint64_t*>(target);
+    // a stream of steps (the previous one is still in flight, so another will follow): leave room on
+    // every SM for the next step's scan CTA, which starts while these records travel
+    e.small = 0;
+    if (c->steps[slot ^ 1].active || getenv("ACB_EXPAND_SMALL")) {
+      int sms = 148;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      e.small = sms;
+    }
     CK(acb::launch_expand(e, c->stream));
   }
   if ((rc = acb::comm_enqueue_close(c, slot, my_off, mine))) return rc;

@@ -172,6 +172,8 @@ struct ExpandLaunch {
   uint64_t span_start;
   uint64_t offset_add;
   uint64_t* out;         // [ (n-first) * 3 ] as (pid, start, end) u64 triples == acg_match layout
+  int small = 0;         // > 0: that many 128-thread CTAs at most (one per SM: each fits beside a persistent scan
+                         // CTA, pipelined sharded steps); 0: one 256-thread CTA per 256 records
 };
 cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s);
 // number of leading tuples whose end_rel <= bound (keys sorted ascending)

@@ -218,35 +218,38 @@ __global__ void seq_find_kernel(DfaDev d, SeqLaunch p) {
   *p.counter = n;
 }
 
-// 128 records per CTA, built in shared memory and stored as 16-byte vectors: the target may be
-// another GPU's HBM (peer mapping of rank 0's receive buffer, acb_comm.hpp), where full 128-byte
-// lines per warp store matter more than at home.  Small on purpose -- 128 threads, 3 KB of shared
-// memory -- so that a CTA fits beside the persistent scan CTA of the next sharded step on the same SM
-// and the transfer overlaps that scan.  Record = acg_match { u32 pid; u32 pad; u64 start; u64 end }.
-constexpr int kExpandThreads = 128;
+// Records built in shared memory and stored as 16-byte vectors: the target may be another GPU's HBM
+// (peer mapping of rank 0's receive buffer, acb_comm.hpp), where full lines per warp store matter
+// more than at home.  Two sizes: 256 records per CTA, and a small one -- 128 threads, 3 KB of shared
+// memory -- that fits beside the persistent scan CTA of the next sharded step on the same SM, so that
+// the transfer overlaps that scan.  Record = acg_match { u32 pid; u32 pad; u64 start; u64 end }.
+template <int kExpandThreads>
 __global__ void __launch_bounds__(kExpandThreads) expand_kernel(ExpandLaunch e) {
   __shared__ uint64_t s_rec[kExpandThreads * 3];
   const uint64_t m = e.n - e.first;
-  const uint64_t base = (uint64_t)blockIdx.x * kExpandThreads;
-  const uint64_t i = base + threadIdx.x;
-  if (i < m) {
-    const uint64_t key = e.keys[e.first + i];
-    const uint32_t pid = e.pids[e.first + i];
-    const uint64_t end = e.span_start + (key >> kTieBits) + e.offset_add;
-    s_rec[threadIdx.x * 3 + 0] = (uint64_t)pid;
-    s_rec[threadIdx.x * 3 + 1] = end - e.pattern_lens[pid];
-    s_rec[threadIdx.x * 3 + 2] = end;
-  }
-  __syncthreads();
-  const uint64_t cnt = m - base < kExpandThreads ? m - base : kExpandThreads;  // records of this CTA
-  uint64_t* dst = e.out + base * 3;
-  const uint32_t words = (uint32_t)cnt * 3;  // 8-byte words; base * 24 is a multiple of 16
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    for (uint32_t w = threadIdx.x * 2; w + 1 < words; w += 2 * kExpandThreads)
+  // grid-stride over blocks of kExpandThreads records (the small form runs one CTA per SM)
+  for (uint64_t base = (uint64_t)blockIdx.x * kExpandThreads; base < m; base += (uint64_t)gridDim.x * kExpandThreads) {
+    const uint64_t i = base + threadIdx.x;
+    if (i < m) {
+      const uint64_t key = e.keys[e.first + i];
+      const uint32_t pid = e.pids[e.first + i];
+      const uint64_t end = e.span_start + (key >> kTieBits) + e.offset_add;
+      s_rec[threadIdx.x * 3 + 0] = (uint64_t)pid;
+      s_rec[threadIdx.x * 3 + 1] = end - e.pattern_lens[pid];
+      s_rec[threadIdx.x * 3 + 2] = end;
+    }
+    __syncthreads();
+    const uint64_t cnt = m - base < kExpandThreads ? m - base : kExpandThreads;  // records of this block
+    uint64_t* dst = e.out + base * 3;
+    const uint32_t words = (uint32_t)cnt * 3;  // 8-byte words
+    // 16-byte vector stores from the first 16-byte boundary of the destination on (a rank's offset
+    // in the global list can be odd, and a record is 24 bytes)
+    const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(dst) >> 3) & 1);  // 8-byte words before the boundary
+    if (head && threadIdx.x == 0 && words) dst[0] = s_rec[0];
+    for (uint32_t w = head + threadIdx.x * 2; w + 1 < words; w += 2 * kExpandThreads)
       *reinterpret_cast<ulonglong2*>(dst + w) = make_ulonglong2(s_rec[w], s_rec[w + 1]);
-    if ((words & 1) && threadIdx.x == 0) dst[words - 1] = s_rec[words - 1];
-  } else {
-    for (uint32_t w = threadIdx.x; w < words; w += kExpandThreads) dst[w] = s_rec[w];
+    if (words > head && ((words - head) & 1) && threadIdx.x == 0) dst[words - 1] = s_rec[words - 1];
+    __syncthreads();
   }
 }
 
@@ -267,7 +270,13 @@ __global__ void lower_bound_kernel(const uint64_t* keys, uint64_t n, uint64_t bo
 cudaError_t launch_expand(const ExpandLaunch& e, cudaStream_t s) {
   const uint64_t m = e.n - e.first;
   if (m == 0) return cudaSuccess;
-  ACB_LAUNCH(expand_kernel, (unsigned)((m + kExpandThreads - 1) / kExpandThreads), kExpandThreads, 0, s, e);
+  if (e.small) {
+    // one small CTA per SM at most: the persistent scan CTA of the next step must still fit beside it
+    const uint64_t blocks = (m + 127) / 128;
+    ACB_LAUNCH(expand_kernel<128>, (unsigned)(blocks < (uint64_t)e.small ? blocks : (uint64_t)e.small), 128, 0, s, e);
+  } else {
+    ACB_LAUNCH(expand_kernel<256>, (unsigned)((m + 255) / 256), 256, 0, s, e);
+  }
   return cudaGetLastError();
 }
 cudaError_t launch_lower_bound(const uint64_t* keys, uint64_t n, uint64_t bound_key,

@@ -258,8 +258,8 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   unsigned char* s_ring = smem_raw;                                    // [kPfWarps][kPfStages][kPfStageBytes]
   uint64_t* s_bars = reinterpret_cast<uint64_t*>(s_ring + kPfWarps * kPfStages * kPfStageBytes);  // [kPfWarps][kPfStages]
   uint32_t* s_tile_of = reinterpret_cast<uint32_t*>(s_bars + kPfWarps * kPfStages);  // DYN: tile number staged in [warp][stage]
-  uint32_t* s_next_tile = s_tile_of + kPfWarps * kPfStages;                        // DYN: next tile number of this CTA's chunk (+ pad)
-  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_next_tile + 2);  // [kPfWarps][kPfQ2]
+  uint32_t* s_next_tile = s_tile_of + kPfWarps * kPfStages;                        // DYN: draw state (u64), prefetched super-tile (u32), pad
+  Q2Entry* s_queue2 = reinterpret_cast<Q2Entry*>(s_next_tile + 4);  // [kPfWarps][kPfQ2]
   uint16_t* s_slots = reinterpret_cast<uint16_t*>(s_queue2 + kPfWarps * kPfQ2);  // [kPfWarps][kSlotsAlloc]
   uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(s_slots + kPfWarps * kSlotsAlloc);
   __shared__ uint8_t s_cls[256];
@@ -273,7 +273,10 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   if (tid < kPfWarps * kPfStages) ptx::mbar_init(ptx::smem_addr(&s_bars[tid]), 1);
   // DYN draw state (64 bits at s_next_tile): this CTA starts with super-tile blockIdx.x; whether that
   // one exists is checked when the first batch is drawn (tiles >= n_tiles are skipped)
-  if (tid == 0) *reinterpret_cast<uint64_t*>(s_next_tile) = (uint64_t)blockIdx.x << 32;
+  if (tid == 0) {
+    *reinterpret_cast<uint64_t*>(s_next_tile) = (uint64_t)blockIdx.x << 32;
+    s_next_tile[2] = 0xFFFFFFFEu;  // no super-tile prefetched yet
+  }
   ptx::mbar_init_fence();
   ptx::fence_proxy_async();
   __syncthreads();
@@ -381,25 +384,41 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   // The tile number for a stage is left in s_tile_of[warp][stage] for the warp to read when it gets
   // to that stage.
   constexpr uint32_t kDrawBatch = 4, kSuper = 256;
-  static_assert(kSuper % kDrawBatch == 0, "batches never straddle a super-tile");
+  static_assert(kSuper % (2 * kDrawBatch) == 0, "batches never straddle a super-tile or its half-way mark");
   uint32_t* tile_of = s_tile_of + warp * kPfStages;
-  const uint32_t draw_a = ptx::smem_addr(s_next_tile);
+  const uint32_t draw_a = ptx::smem_addr(s_next_tile), next_a = draw_a + 8;
   const uint32_t n_super = (n_tiles + kSuper - 1) / kSuper;
   constexpr uint64_t kNoMore = 0xFFFFFFFFull << 32;
+  constexpr uint32_t kUnpublished = 0xFFFFFFFEu, kNone = 0xFFFFFFFFu;
   uint32_t batch_next = 0, batch_left = 0;  // lane 0's current batch
   bool exhausted = false;
+  // The global fetch-and-add for the CTA's next super-tile is issued half-way through the current
+  // one by whichever warp draws that batch, and its result is only looked at one step later, when
+  // that warp publishes it in shared memory: the ~1 us round trip to L2 never stalls anybody.
+  unsigned long long pend_g = 0;
+  bool have_pend = false;
+  auto publish = [&]() {  // lane 0 only
+    if (have_pend) {
+      ptx::sts32_volatile(next_a, pend_g < n_super ? (uint32_t)pend_g : kNone);
+      have_pend = false;
+    }
+  };
   auto draw = [&](uint32_t stage) {  // lane 0 only
+    publish();
     while (batch_left == 0 && !exhausted) {
       const uint64_t v = ptx::atoms_add64(draw_a, kDrawBatch);
       const uint32_t sup = (uint32_t)(v >> 32), off = (uint32_t)v;
-      if (sup == 0xFFFFFFFFu) { exhausted = true; break; }
+      if (sup == kNone) { exhausted = true; break; }
+      if (off == kSuper / 2) { pend_g = atomicAdd(p.counter + 2, 1ull) + gridDim.x; have_pend = true; }
       if (off < kSuper) { batch_next = sup * kSuper + off; batch_left = kDrawBatch; break; }
       if (off == kSuper) {
-        // the first draw past the end fetches the CTA's next super-tile
-        const unsigned long long g = atomicAdd(p.counter + 2, 1ull) + gridDim.x;
-        if (g < n_super) {
-          ptx::atoms_exch64(draw_a, (g << 32) | kDrawBatch);  // (this warp keeps the first batch)
-          batch_next = (uint32_t)g * kSuper;
+        // the first draw past the end installs the prefetched super-tile (published long ago, normally)
+        uint32_t g;
+        while ((g = ptx::lds32_volatile(next_a)) == kUnpublished) {}
+        ptx::sts32_volatile(next_a, kUnpublished);
+        if (g != kNone) {
+          ptx::atoms_exch64(draw_a, ((uint64_t)g << 32) | kDrawBatch);  // (this warp keeps the first batch)
+          batch_next = g * kSuper;
           batch_left = kDrawBatch;
         } else {
           ptx::atoms_exch64(draw_a, kNoMore);
@@ -407,7 +426,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         }
         break;
       }
-      while ((uint32_t)(ptx::lds64_volatile(draw_a) >> 32) == sup) {}  // a refill is under way: ~1 us
+      while ((uint32_t)(ptx::lds64_volatile(draw_a) >> 32) == sup) {}  // the install is under way
     }
     uint32_t t = n_tiles;
     if (!exhausted) { t = batch_next++; --batch_left; }
@@ -649,6 +668,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       else if (t + 2 * kPfWarps < n_tiles) issue(t + 2 * kPfWarps, stage);
     }
   }
+  if constexpr (DYN) { if (lane == 0) publish(); }  // a prefetched super-tile index somebody may be waiting for
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
 }
@@ -875,7 +895,7 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
   const int tile = kTileOf[geom];
   const int q2_bytes = dense ? PfCfg<true>::kQ2 * 8 : PfCfg<false>::kQ2 * 4;
   const int slot_bytes = PfCfg<false>::kSlots * 2;
-  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 12 + q2_bytes + slot_bytes) + 8 + bitmap_bytes;
+  const size_t smem = size_t(warps) * (kPfStages * stage_bytes + kPfStages * 12 + q2_bytes + slot_bytes) + 16 + bitmap_bytes;
   if (smem > 227 * 1024 - 1024) return cudaErrorInvalidValue;  // static shared memory: byte classes, tile numbers
   const bool masked = p.fold != 0 || p.kmask != 0xFFFFFFFFu;
   using KernT = void (*)(DfaDev, PrefilterLaunch);

@@ -82,6 +82,14 @@ __device__ __forceinline__ void atoms_exch64(uint32_t addr, uint64_t v) {
   uint64_t old;
   asm volatile("atom.shared.exch.b64 %0, [%1], %2;" : "=l"(old) : "r"(addr), "l"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint64_t lds64_volatile(uint32_t addr) {
   uint64_t v;
   asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");

@@ -29,7 +29,7 @@ inline void mbar_arrive_expect_tx(uint32_t bar, uint32_t) { (void)smem_ptr(bar, 
 inline bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   const uint64_t done = *reinterpret_cast<uint64_t*>(smem_ptr(bar, 8));
   if ((done & 1) != (parity & 1)) return true;  // the phase with this parity has completed
-  emu::yield();
+  emu::yield("mbarrier wait");
   return false;
 }
 inline void tma_load_1d(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
@@ -64,8 +64,13 @@ inline uint64_t atoms_add64(uint32_t a, uint64_t v) {
   return old;
 }
 inline void atoms_exch64(uint32_t a, uint64_t v) { *reinterpret_cast<uint64_t*>(smem_ptr(a, 8)) = v; }
+inline uint32_t lds32_volatile(uint32_t a) {
+  emu::yield_poll("spin on a 32-bit shared word");   // a spin on this value must let the thread that changes it run
+  return *reinterpret_cast<uint32_t*>(smem_ptr(a, 4));
+}
+inline void sts32_volatile(uint32_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(smem_ptr(a, 4)) = v; }
 inline uint64_t lds64_volatile(uint32_t a) {
-  emu::yield();   // a spin on this value must let the thread that changes it run
+  emu::yield_poll("spin on a 64-bit shared word");   // a spin on this value must let the thread that changes it run
   return *reinterpret_cast<uint64_t*>(smem_ptr(a, 8));
 }
 inline void keep_in_registers(uint32_t&, uint32_t&, uint32_t&) {}

@@ -114,6 +114,7 @@ struct Fiber {
   void* stack = nullptr;
   bool done = false;
   dim3 tid;
+  const char* where = "running";  // what the thread last waited for (deadlock report)
 };
 
 struct Warp {
@@ -133,6 +134,7 @@ struct Cta {
   unsigned alive_threads = 0, bar_arrived = 0;
   uint64_t bar_gen = 0;
   uint64_t progress = 0;   // bumped whenever a collective completes or a fiber finishes
+  uint64_t spins = 0;      // polls of shared words (each counts as progress until the budget is spent)
   std::function<void()> body;
 };
 
@@ -143,7 +145,14 @@ inline std::mutex g_one_launch_at_a_time;
 inline unsigned char* g_dyn_smem = nullptr;  // exactly the requested bytes per launch: overruns are visible to ASAN
 inline size_t g_dyn_smem_bytes = 0;
 
-inline void yield() { swapcontext(&g_cur->ctx, &g_sched); }
+inline void yield(const char* where = "yield") { g_cur->where = where; swapcontext(&g_cur->ctx, &g_sched); }
+// A thread that polls a shared word lets the others run first.  The poll itself is progress (the
+// value may have changed while the thread was away) -- up to a budget, so that a spin nobody ever
+// satisfies still ends in the deadlock report instead of a hang.
+inline void yield_poll(const char* where) {
+  if (++g_cta->spins < (1ull << 24)) g_cta->progress++;
+  yield(where);
+}
 [[noreturn]] inline void die(const char* what) {
   std::fprintf(stderr, "emu: %s\n", what);
   std::abort();
@@ -281,7 +290,12 @@ inline void launch(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t, A
         swapcontext(&g_sched, &f.ctx);
         if (!f.done) ++remaining;
       }
-      if (remaining && cta.progress == before) die("deadlock: no thread of the CTA can make progress");
+      if (remaining && cta.progress == before) {
+        for (unsigned t = 0; t < block.x; ++t)
+          if (!cta.fibers[t].done && (t % 32 == 0 || std::strcmp(cta.fibers[t].where, cta.fibers[t - 1].where)))
+            std::fprintf(stderr, "emu: cta %u thread %u waits in %s\n", b, t, cta.fibers[t].where);
+        die("deadlock: no thread of the CTA can make progress");
+      }
     }
     g_cta = nullptr;
     g_cur = nullptr;
