@@ -870,7 +870,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
   // kernel geometry as planned; second-stage organisation and tile distribution: see prefilter_kernel
   p.geom = pf.wide ? 1 : 0;
   p.pair = 0;
-  p.dyn = (a->experiment & ACG_EXP_STATIC_TILES) ? 0 : 1;
+  p.dyn = (a->experiment & ACG_EXP_STATIC_TILES) ? 0 : ((a->experiment & ACG_EXP_GLOBAL_TILES) ? 2 : 1);
   p.kmask = pf.kmask;
   p.fold = pf.fold;
   p.mult = pf.mult;
@@ -898,7 +898,7 @@ int enqueue_prefilter_range(const acg_dfa* a, const uint8_t* d_hay, uint64_t rea
     CK(acb::launch_bytescan(a->dev, p, dev_sms, w.stream));
   } else {
     // counter[2]: the launch's global super-tile counter (dynamic tile distribution), zero at launch
-    if (p.dyn) CK(cudaMemsetAsync(w.d_counter + 2, 0, 8, w.stream));
+    if (p.dyn == 2) CK(cudaMemsetAsync(w.d_counter + 2, 0, 8, w.stream));
     CK(acb::launch_prefilter(a->dev, p, dev_sms, w.stream));
   }
   cur_ws().stats.launches += 1;
@@ -1729,7 +1729,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* a, uint64_t bytes) {
 }
 
 int acg_debug_set_experiment(acg_dfa* a, uint32_t flags) {
-  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_STATIC_TILES | ACG_EXP_NO_BYTESCAN))) return ACG_E_INVALID_ARG;
+  if (!a || (flags & ~uint32_t(ACG_EXP_KEY24 | ACG_EXP_STATIC_TILES | ACG_EXP_NO_BYTESCAN | ACG_EXP_GLOBAL_TILES))) return ACG_E_INVALID_ARG;
   std::lock_guard<std::mutex> lock(a->mu);
   const uint32_t changed = a->experiment ^ flags;
   a->experiment = flags;

@@ -126,7 +126,7 @@ struct PrefilterLaunch {
   uint32_t* pids;
   unsigned long long* counter;  // [0] tuples, [1] candidates, [2] super-tiles handed out (dynamic tile distribution)
   uint64_t cap;
-  uint32_t dyn;                 // 1: tiles are handed out dynamically, super-tiles per CTA from counter[2] (see prefilter_kernel)
+  uint32_t dyn;                 // tile distribution: 0 static, 1 per-CTA counter, 2 global super-tiles from counter[2] (see prefilter_kernel)
   // byte-set scan (bytescan_kernel, the memchr-class start-bytes / rare-bytes prefilter): bs_n needles,
   // each replicated into the four bytes of a word; a pattern that shows needle i at offset q starts in
   // [q - bs_back[i], q] (0 for start bytes, <= 15)

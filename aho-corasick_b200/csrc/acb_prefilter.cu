@@ -233,12 +233,20 @@ __device__ __forceinline__ bool bloom_test(const uint32_t* s_bitmap, uint32_t h)
 // (Measured in r02 and gone: a lane-local second stage without compaction, a paired one, and the
 // anchor-map second stage for the stride-2 kernel -- 2.10 ms against 1.81 ms on cfg 2, the L2 latency
 // outweighs the sparser bitmap: profiles/r02a_ab_*.jsonl, r02b_cfg3.jsonl, r02f_cfg2.jsonl.)
-// Tile distribution DYN: false -- warp w of a CTA takes the tiles w, w + W, w + 2W, ... of the CTA's
-// chunk; true -- the warps of a CTA draw tile numbers from a shared-memory counter.  With the static
-// split the warps of a CTA finish up to 25 % apart (ncu r02a: 27.8 of 32 warps active on average,
-// the least busy SM sub-partition active 74 % of the kernel), because the scheduler favours some
-// warps and nothing hands their neighbours' work over; the kernel ends with its slowest warp.
-template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, bool DYN = false>
+// Tile distribution DYN:
+//   0  static: warp w of a CTA takes the tiles w, w + W, w + 2W, ... of the CTA's chunk.  ncu (r02a):
+//      27.8 of 32 warps active on average, the least busy SM sub-partition active 74 % of the kernel --
+//      the scheduler favours some warps, nothing hands their neighbours' work over, and the kernel
+//      ends with its slowest warp.
+//   1  (default) the warps of a CTA draw tiles of the CTA's chunk from a shared-memory counter, four
+//      per atomic: -9 % on cfg 2, -7 % cfg 3, -15 % cfg 5 against the static split.
+//   2  tiles numbered over the whole region, super-tiles of 256 per CTA from a global counter
+//      (prefetched half-way through the current one), batches of four per warp from a 64-bit
+//      shared-memory word.  A CTA that starts late or shares its SM with another kernel simply ends
+//      up with fewer super-tiles -- meant for the pipelined multi-GPU steps -- but the heavier draw
+//      costs what the better balance wins: 1.95 ms against 1.80 ms (1) and 1.97 ms (0) on cfg 2
+//      (profiles/r02k_*.jsonl, r02l_*.jsonl).  Kept selectable (ACG_EXP_GLOBAL_TILES).
+template <int MODE, bool MASKED, bool DENSE, int STRIDE, int GEOM, int DYN = 0>
 __global__ void __launch_bounds__(PfGeom<GEOM>::kThreads, PfGeom<GEOM>::kMinCtas)  // wide: two CTAs per SM (64 registers)
 prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   static_assert(STRIDE == 1 || STRIDE == 2, "fingerprint stride");
@@ -274,7 +282,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   // DYN draw state (64 bits at s_next_tile): this CTA starts with super-tile blockIdx.x; whether that
   // one exists is checked when the first batch is drawn (tiles >= n_tiles are skipped)
   if (tid == 0) {
-    *reinterpret_cast<uint64_t*>(s_next_tile) = (uint64_t)blockIdx.x << 32;
+    *reinterpret_cast<uint64_t*>(s_next_tile) = DYN == 2 ? (uint64_t)blockIdx.x << 32 : 0ull;  // (DYN 1: a 32-bit tile counter)
     s_next_tile[2] = 0xFFFFFFFEu;  // no super-tile prefetched yet
   }
   ptx::mbar_init_fence();
@@ -303,7 +311,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint64_t per_cta = (n_blocks16 + gridDim.x - 1) / gridDim.x;
   const uint64_t b0 = (uint64_t)blockIdx.x * per_cta;
   const uint64_t b1 = min(b0 + per_cta, n_blocks16);
-  const bool whole = DYN && !p.brute;
+  const bool whole = DYN == 2 && !p.brute;
   const uint64_t chunk_lo = whole ? p.region_lo : p.region_lo + (b0 << 4);
   const uint64_t chunk_hi = whole ? p.region_hi : (b0 < b1 ? p.region_lo + (b1 << 4) : p.region_lo + (b0 << 4));
 
@@ -404,6 +412,18 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     }
   };
   auto draw = [&](uint32_t stage) {  // lane 0 only
+    if constexpr (DYN == 1) {
+      // tiles of this CTA's chunk from the CTA's counter, kDrawBatch per atomic
+      if (batch_left == 0) {
+        batch_next = ptx::atoms_add(draw_a, kDrawBatch);
+        batch_left = kDrawBatch;
+      }
+      const uint32_t t = batch_next++;
+      --batch_left;
+      tile_of[stage] = t;
+      if (t < n_tiles) issue(t, stage);
+      return;
+    }
     publish();
     while (batch_left == 0 && !exhausted) {
       const uint64_t v = ptx::atoms_add64(draw_a, kDrawBatch);
@@ -668,7 +688,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
       else if (t + 2 * kPfWarps < n_tiles) issue(t + 2 * kPfWarps, stage);
     }
   }
-  if constexpr (DYN) { if (lane == 0) publish(); }  // a prefetched super-tile index somebody may be waiting for
+  if constexpr (DYN == 2) { if (lane == 0) publish(); }  // a prefetched super-tile index somebody may be waiting for
   if (q2len) drain2();
   if (lane == 0 && cand_total) atomicAdd(p.counter + 1, cand_total);  // cand_total is warp-uniform
 }
@@ -904,15 +924,17 @@ cudaError_t launch_prefilter(const DfaDev& dfa, const PrefilterLaunch& p, int sm
 #define ACB_PF_ROW(M, K, D)                                                                                 \
   {prefilter_kernel<M, K, false, 1, kGeomNarrow, D>, prefilter_kernel<M, K, true, 1, kGeomNarrow, D>, \
    prefilter_kernel<M, K, false, 2, kGeomNarrow, D>, prefilter_kernel<M, K, false, 2, kGeomWide, D>}
-  static const KernT table[2][2][2][4] = {{{ACB_PF_ROW(0, false, false), ACB_PF_ROW(0, false, true)},
-                                           {ACB_PF_ROW(0, true, false), ACB_PF_ROW(0, true, true)}},
-                                          {{ACB_PF_ROW(1, false, false), ACB_PF_ROW(1, false, true)},
-                                           {ACB_PF_ROW(1, true, false), ACB_PF_ROW(1, true, true)}}};
+  static const KernT table[2][2][3][4] = {
+      {{ACB_PF_ROW(0, false, 0), ACB_PF_ROW(0, false, 1), ACB_PF_ROW(0, false, 2)},
+       {ACB_PF_ROW(0, true, 0), ACB_PF_ROW(0, true, 1), ACB_PF_ROW(0, true, 2)}},
+      {{ACB_PF_ROW(1, false, 0), ACB_PF_ROW(1, false, 1), ACB_PF_ROW(1, false, 2)},
+       {ACB_PF_ROW(1, true, 0), ACB_PF_ROW(1, true, 1), ACB_PF_ROW(1, true, 2)}}};
 #undef ACB_PF_ROW
+  if (p.dyn > 2) return cudaErrorInvalidValue;
   if (p.stride == 2 && dense) return cudaErrorInvalidValue;
   int variant = dense ? 1 : 0;
   if (p.stride == 2) variant = geom == kGeomWide ? 3 : 2;
-  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.dyn ? 1 : 0][variant];
+  KernT kern = table[p.mode ? 1 : 0][masked ? 1 : 0][p.dyn][variant];
 #ifdef ACB_EMULATE
   if (getenv("ACB_EMU_TRACE")) fprintf(stderr, "launch_prefilter variant %d dyn %d threads %d smem %zu\n", variant, (int)p.dyn, threads, smem);
 #endif

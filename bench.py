@@ -314,45 +314,20 @@ def run_workload(rig, args, wl, steps, warmup, want_e2e=True, check=True):
         step()
     rig.barrier()
     kernel_ms, scan_ms, gather_ms = [], [], []
-    pipelined_s = None
     with ClockSampler(rig.local) as clocks:
         t0 = time.perf_counter()
-        if world > 1:
-            # a stream of batches: step k + 1 begins before step k is waited for, so its scan overlaps
-            # the NVLink transfer of step k's records (acg_find_overlapping_sharded_begin / _wait)
-            args_b = (ac, d_hay.data_ptr(), n_local, gen_lo, (0, total))
-            tk = rig.comm.begin(*args_b)
-            for k in range(1, steps):
-                tk_next = rig.comm.begin(*args_b)
-                cnt, _, sst = rig.comm.wait(tk)
-                tk = tk_next
-                kernel_ms.append(sst["scan_ms"] + sst["order_ms"]); scan_ms.append(sst["scan_ms"]); gather_ms.append(sst["gather_ms"])
-            cnt, _, sst = rig.comm.wait(tk)
-            kernel_ms.append(sst["scan_ms"] + sst["order_ms"]); scan_ms.append(sst["scan_ms"]); gather_ms.append(sst["gather_ms"])
-            rig.barrier()
-            pipelined_s = time.perf_counter() - t0
-        else:
-            for _ in range(steps):
-                cnt, ms, gms, sst = step()
-                st = ac.last_stats()
-                kernel_ms.append(ms)
-                scan_ms.append(st["scan_ms"])
-                gather_ms.append(gms)
+        for _ in range(steps):
+            cnt, ms, gms, sst = step()
+            st = ac.last_stats()
+            kernel_ms.append(ms)
+            scan_ms.append(sst["scan_ms"] if sst else st["scan_ms"])
+            gather_ms.append(gms)
         rig.barrier()
         wall = time.perf_counter() - t0
-    blocking_gather_ms = None
-    if world > 1:
-        # the same step issued blocking (nothing to overlap with): the exposed cost of the gather
-        g = []
-        for _ in range(3):
-            _, _, gms, _ = step()
-            g.append(gms)
-        blocking_gather_ms = sum(g) / len(g)
     stats = ac.last_stats()
-    # N = 1: CUDA-event times of the library's kernels; N > 1: the pipelined loop has no per-step device
-    # interval that could be summed, so the host clock between the two barriers (each with a device
-    # synchronize) times the K steps, launch gaps included
-    dev_s, wall = rig.max_over_ranks(pipelined_s if world > 1 else sum(kernel_ms) / 1e3, wall)
+    # CUDA-event times taken inside the library: scan + order on the search stream, and (N > 1) count
+    # exchange + expand into rank 0's buffer + closing barrier on the communicator's stream
+    dev_s, wall = rig.max_over_ranks((sum(kernel_ms) + sum(gather_ms)) / 1e3, wall)
     value = total * steps / GIB / dev_s
     total_matches = cnt if world > 1 else rig.sum_over_ranks(cnt)
     transport = rig.comm.transport() if world > 1 else None
@@ -415,8 +390,8 @@ def run_workload(rig, args, wl, steps, warmup, want_e2e=True, check=True):
     scan_s = sum(scan_ms) / len(scan_ms) / 1e3
     res = {"workload": wl, "value": value, "dev_s": dev_s, "wall": wall, "steps": steps, "matches": total_matches,
            "candidates": int(stats["candidates"]), "scan_ms": sum(scan_ms) / len(scan_ms),
-           "order_ms": float(stats["order_ms"]), "gather_ms": blocking_gather_ms if world > 1 else 0.0,
-           "gather_ms_in_pipeline": sum(gather_ms) / len(gather_ms) if world > 1 else None, "build_s": build_s,
+           "order_ms": float(stats["order_ms"]), "gather_ms": sum(gather_ms) / len(gather_ms),
+           "gather_ms_samples": [round(g, 4) for g in gather_ms] if world > 1 else None, "build_s": build_s,
            "engine": int(stats["engine"]), "launches": int(stats["launches"]), "achieved": n_bytes / scan_s / 1e9,
            "n_bytes": n_bytes, "per_gpu": per_gpu, "total": total, "e2e": e2e, "clocks": clocks.summary(),
            "table_bytes": ac.memory_usage(), "states": ac.state_len(), "transport": transport, "checked": checked,
@@ -516,11 +491,9 @@ def main():
                    "numa_node": rig.numa},
         "matches": r["matches"], "matches_per_s": r["matches"] * args.steps / r["dev_s"],
         "candidates": r["candidates"], "scan_ms": r["scan_ms"], "order_ms": r["order_ms"], "gather_ms": r["gather_ms"],
-        "timing": ("N=1: CUDA events inside the library around scan + order; " if world == 1 else
-                   "N>1: host clock between two barriers (each with a device synchronize) around K pipelined steps "
-                   "(begin(k+1) before wait(k): scan k+1 overlaps the peer-memory gather of step k); gather_ms = the "
-                   "gather of a blocking step, gather_ms_in_pipeline = begin-of-exchange to records-landed inside the loop"),
-        "gather_ms_in_pipeline": r["gather_ms_in_pipeline"],
+        "timing": "CUDA events inside the library: scan + order on the search stream; N > 1: + count exchange, expand "
+                  "into rank 0's buffer over peer memory and closing barrier on the communicator's stream; max over ranks",
+        "gather_ms_samples": r["gather_ms_samples"],
         "build_s": r["build_s"], "wall_ms_per_step": r["wall"] / args.steps * 1e3,
         "roofline": roofline(r),
         "gpu_launches": r["launches"] * args.steps,
@@ -538,7 +511,7 @@ def main():
             line["configs"][x] = {"workload": f"{x}: {DESC[x]}", "value": xr["value"], "unit": "GiB/s",
                                   "global_haystack_bytes": xr["total"], "scan_ms": xr["scan_ms"],
                                   "order_ms": xr["order_ms"], "gather_ms": xr["gather_ms"],
-                                  "gather_ms_in_pipeline": xr["gather_ms_in_pipeline"], "matches": xr["matches"],
+                                  "gather_ms_samples": xr["gather_ms_samples"], "matches": xr["matches"],
                                   "candidates": xr["candidates"], "build_s": xr["build_s"],
                                   "device_fill": xr["device_fill"], "states": xr["states"],
                                   "table_bytes": xr["table_bytes"], "roofline": roofline(xr),

@@ -53,6 +53,7 @@ int acg_debug_set_pipeline_chunk(acg_dfa* dfa, uint64_t bytes);
 #define ACG_EXP_STATIC_TILES 32u /* warp w of a CTA takes tiles w, w + W, ...; default: the warps of a CTA draw their tiles
                                   * from a shared-memory counter.  r02 A/B (profiles/r02b_*.jsonl): dynamic tiles + 27-bit
                                   * keys -7 % on cfg 2, -22 % on cfg 3, -15 % on cfg 5. */
+#define ACG_EXP_GLOBAL_TILES 16u  /* tiles numbered over the whole region, super-tiles per CTA from a global counter */
 #define ACG_EXP_NO_BYTESCAN 64u  /* automata with a start-bytes / rare-bytes set: use the fingerprint filter anyway */
 int acg_debug_set_experiment(acg_dfa* dfa, uint32_t flags);
 

@@ -37,7 +37,7 @@ for n_pat, seed, kind, ci, nbytes in ((5000, 0xAC5000, 0, False, 512 << 10), (50
     W.fill_haystack(hay, 5)
     W.plant(hay, pats, 6, period=512, window=256)
     o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
-    for flags in (0, 32):
+    for flags in (0, 16, 32):
         ac = (ab.AhoCorasick.builder().match_kind(kind).ascii_case_insensitive(ci).kind(ab.AhoCorasickKind.DFA).build(pats))
         assert lib.acg_debug_set_experiment(ac._h, flags) == 0
         for phase in (0, 1, 15):

@@ -251,7 +251,7 @@ def test_unselective_steps_verify_in_place(kind):
         eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), stride)
 
 
-# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_STATIC_TILES = 32,
+# ---- switchable kernel / plan variants (include/acb200_debug.h: ACG_EXP_KEY24 = 8, ACG_EXP_GLOBAL_TILES = 16, ACG_EXP_STATIC_TILES = 32,
 # ACG_EXP_NO_BYTESCAN = 64)
 def set_experiment(ac, flags):
     ab._lib.acg_debug_set_experiment.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
@@ -259,7 +259,7 @@ def set_experiment(ac, flags):
     return ac
 
 
-@pytest.mark.parametrize("flags", [8, 32, 40])
+@pytest.mark.parametrize("flags", [8, 16, 24, 32, 40])
 @pytest.mark.parametrize("name", ["stride2_narrow", "stride2_narrow_ci_leftmost"])
 def test_experimental_variants_match_the_oracle(name, flags):
     """24-bit first-stage keys and the static tile split (the non-default variants) on the
@@ -286,7 +286,7 @@ def test_experimental_variants_match_the_oracle(name, flags):
     eq(ac.find_iter_dev_np(ptr, hay.size)[0], o.find_iter_np(hay), (name, "default"))
 
 
-@pytest.mark.parametrize("flags", [0, 8, 32, 40])
+@pytest.mark.parametrize("flags", [0, 8, 16, 32, 40])
 def test_experimental_variants_at_every_alignment(flags):
     """Ownership of the start one byte before a tile / chunk / region (the e == 0 corner of the
     lane-local second stage, tiles drawn dynamically) at 18 pointer phases x 8 span ends."""
@@ -322,7 +322,7 @@ def test_27_bit_keys_on_the_wide_geometry_and_short_pattern_tails():
     eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), "tails")
 
 
-@pytest.mark.parametrize("flags", [0, 32])
+@pytest.mark.parametrize("flags", [0, 16, 32])
 def test_experimental_variants_unselective_steps(flags):
     pats = [b"abab", b"baba", b"ababab"] + W.make_patterns(5000, 0xAC5000)
     ac = set_experiment(build(pats, 0), flags)
@@ -335,13 +335,15 @@ def test_experimental_variants_unselective_steps(flags):
 
 @pytest.mark.parametrize("name", ["stride2_wide", "stride1_short_patterns", "dense"])
 def test_dynamic_tiles_on_the_other_variants(name):
-    """ACG_EXP_STATIC_TILES = 32 with the wide, stride-1 and dense instantiations."""
+    """ACG_EXP_STATIC_TILES = 32 and ACG_EXP_GLOBAL_TILES = 16 with the wide, stride-1 and dense instantiations."""
     n, seed, nbytes, kind, ci = VARIANTS[name]
     pats, hay = workload(n, seed, min(nbytes, 256 << 10), ci)
     if name == "stride1_short_patterns":
         pats = [p[:3] for p in pats[:150]] + pats[150:]
-    ac = set_experiment(build(pats, kind, ci), 32)
     o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, kind=O.KIND_DFA)
+    ac = set_experiment(build(pats, kind, ci), 16)
+    eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), (name, 'global tiles'))
+    ac = set_experiment(build(pats, kind, ci), 32)
     eq(ac.find_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_iter_np(hay), name)
     if kind == 0:
         eq(ac.find_overlapping_iter_dev_np(hay.ctypes.data, hay.size)[0], o.find_overlapping_iter_np(hay), name)

@@ -21,7 +21,7 @@ def set_experiment(ac, flags):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("flags", [8, 32, 40])
+@pytest.mark.parametrize("flags", [8, 16, 32, 40])
 @pytest.mark.parametrize("cfg,kind,ci", [("cfg2", 0, False), ("cfg3", 1, True)])
 def test_experimental_prefilter_variants(cfg, kind, ci, flags):
     import torch

@@ -39,7 +39,7 @@ def ptxas_info(source):
 
 def test_prefilter_kernel_register_budget():
     info = {k: v for k, v in ptxas_info("acb_prefilter.cu").items() if "prefilter_kernel" in k}
-    assert len(info) == 32   # [mode][masked][static / dynamic tiles] x {stride 1, dense, stride 2 narrow, wide}
+    assert len(info) == 48   # [mode][masked][static / per-CTA / global tiles] x {stride 1, dense, stride 2 narrow, wide}
     for name, v in info.items():
         assert v["spill"] == 0, name
         # 65 536 registers per SM: 1 024 threads (narrow) or 2 x 512 threads (wide) => 64 per thread
