@@ -370,6 +370,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
   const uint64_t chunk_bytes = chunk_hi - chunk_lo;
   const uint32_t n_tiles = (uint32_t)((chunk_bytes + kPfTile - 1) / kPfTile);
   const uint32_t last_valid = n_tiles ? (uint32_t)(chunk_bytes - (uint64_t)(n_tiles - 1) * kPfTile) : 0;
+  const bool use_windows = (chunk_bytes >> kWinShift) != 0;  // queued 32-bit offsets need more than one window
   // shared addresses of this warp's barriers and ring, and of the lane's first 16-byte group;
   // opaque to the compiler so that they stay in registers instead of being re-derived from the
   // thread index at every use
@@ -473,10 +474,13 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
     else t = (uint32_t)warp + it * (uint32_t)kPfWarps;
     if (t >= n_tiles) break;  // tile numbers only grow: nothing is in flight for this warp any more
     const uint64_t wbase = chunk_lo + (uint64_t)t * kPfTile;
-    const uint32_t win = (uint32_t)(((uint64_t)t * kPfTile) >> kWinShift);
-    if (win != q2win) {  // warp-uniform
-      if (q2len) drain2();
-      q2win = win;
+    uint32_t win = 0;
+    if (use_windows) {  // (a chunk below 2 GiB -- every CTA chunk of a span under 296 GiB -- has one window)
+      win = (uint32_t)(((uint64_t)t * kPfTile) >> kWinShift);
+      if (win != q2win) {  // warp-uniform
+        if (q2len) drain2();
+        q2win = win;
+      }
     }
     while (!ptx::mbar_try_wait(bar0 + stage * 8, parity)) {}
     const uint32_t stage_off = stage * (uint32_t)kPfStageBytes;
@@ -591,7 +595,7 @@ prefilter_kernel(DfaDev d, PrefilterLaunch p) {
         // second stage, compacted: the work items are (hit, start offset the hit owns) -- the
         // probed offset and, with stride 2, the one before it -- one per lane.  Each is tested
         // with two Bloom hashes of its 4-byte fingerprint, re-read from the staged tile.
-        const uint32_t wrel = (uint32_t)((wbase - chunk_lo) - ((uint64_t)win << kWinShift)) + rel_bias;
+        const uint32_t wrel = (use_windows ? (uint32_t)((wbase - chunk_lo) - ((uint64_t)win << kWinShift)) : (uint32_t)(wbase - chunk_lo)) + rel_bias;
         const uint32_t n_items = total * STRIDE;
         if constexpr (ANCH) {
           // Anchor-map second stage: the answer is an L2 access away, so every lane takes two items
