@@ -163,6 +163,8 @@ def _declare(lib):
                                                   C.POINTER(_u64), _vp, _u64, _vp]
     lib.acg_find_overlapping_sharded_begin.argtypes = [_vp, _vp, _vp, _i, _u64, _u64, _u64, _u64, C.POINTER(_i)]
     lib.acg_find_overlapping_sharded_wait.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_u64), _vp, _u64, _vp]
+    lib.acg_comm_mark.argtypes = [_vp, _i]
+    lib.acg_comm_mark_elapsed_ms.argtypes = [_vp, C.POINTER(C.c_float)]
     lib.acg_comm_fetch.argtypes = [_vp, _vp, _u64, C.POINTER(_u64)]
     lib.acg_comm_fetch_view.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_u64)]
     lib.acg_comm_checksum.argtypes = [_vp, C.POINTER(_u64), C.POINTER(_u64)]

@@ -7,8 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -58,6 +61,10 @@ struct Workspace {
   uint64_t* h_seq = nullptr;
   uint64_t h_seq_cap = 0;
   acg_stats stats{};  // of the search that holds (or last held) this workspace
+  // pageable host haystacks: page-locked staging ring filled by host threads (run_prefilter)
+  uint8_t* h_stage[2] = {nullptr, nullptr};
+  uint64_t h_stage_cap = 0;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 }  // namespace
@@ -149,6 +156,10 @@ void destroy_workspace(Workspace& w) {
   if (w.h_keys) cudaFreeHost(w.h_keys);
   if (w.h_pids) cudaFreeHost(w.h_pids);
   if (w.h_seq) cudaFreeHost(w.h_seq);
+  for (int i = 0; i < 2; ++i) {
+    if (w.h_stage[i]) cudaFreeHost(w.h_stage[i]);
+    if (w.stage_ev[i]) cudaEventDestroy(w.stage_ev[i]);
+  }
   if (w.ev0) cudaEventDestroy(w.ev0);
   if (w.ev1) cudaEventDestroy(w.ev1);
   if (w.ev2) cudaEventDestroy(w.ev2);
@@ -929,6 +940,92 @@ int order_tuples(const acg_dfa* a, uint64_t want, uint64_t n_bytes, TupleResult*
   return ACG_OK;
 }
 
+// ---- pageable host haystacks ---------------------------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver through its own page-locked buffers by
+// a single thread (~10 GiB/s on the bench box against 49 GiB/s from pinned memory).  A caller that
+// hands over an ordinary allocation (a Rust Vec<u8>, a numpy array) gets the same pipeline with the
+// staging done here: host threads copy each chunk into a page-locked ring buffer while the previous
+// chunk is on its way over PCIe.
+class CopyPool {
+ public:
+  static CopyPool& get() {
+    // never destroyed: the workers wait on its condition variable for the life of the process, and
+    // destroying a condition variable that has waiters blocks (exit would hang)
+    static CopyPool* pool = new CopyPool;
+    return *pool;
+  }
+  // dst[0, n) = src[0, n), split over the pool's threads; returns when done
+  void copy(uint8_t* dst, const uint8_t* src, size_t n) {
+    if (n < (4u << 20) || workers_.empty()) { std::memcpy(dst, src, n); return; }
+    std::unique_lock<std::mutex> lk(mu_);
+    busy_cv_.wait(lk, [&] { return !active_; });  // one copy at a time: the pool is shared by all handles
+    active_ = true;
+    dst_ = dst; src_ = src; n_ = n;
+    next_.store(0);
+    pending_ = int(workers_.size());
+    ++epoch_;
+    cv_.notify_all();
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    active_ = false;
+    busy_cv_.notify_one();
+  }
+
+ private:
+  CopyPool() {
+    unsigned n = std::thread::hardware_concurrency();
+    n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 0);
+    for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    for (auto& t : workers_) t.detach();  // process-lifetime pool
+  }
+  void run() {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return epoch_ != seen; });
+      seen = epoch_;
+      uint8_t* dst = dst_;
+      const uint8_t* src = src_;
+      const size_t n = n_;
+      lk.unlock();
+      constexpr size_t kSlice = 1u << 20;
+      for (;;) {
+        const size_t off = next_.fetch_add(kSlice);
+        if (off >= n) break;
+        std::memcpy(dst + off, src + off, std::min(kSlice, n - off));
+      }
+      lk.lock();
+      if (--pending_ == 0) done_cv_.notify_one();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_, busy_cv_;
+  std::vector<std::thread> workers_;
+  uint8_t* dst_ = nullptr;
+  const uint8_t* src_ = nullptr;
+  size_t n_ = 0;
+  std::atomic<size_t> next_{0};
+  int pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool active_ = false;
+};
+
+bool is_pageable_host(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_stage(Workspace& w, uint64_t bytes) {
+  if (bytes <= w.h_stage_cap) return ACG_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (w.h_stage[i]) { cudaFreeHost(w.h_stage[i]); w.h_stage[i] = nullptr; }
+    CK(cudaMallocHost(&w.h_stage[i], bytes));
+    if (!w.stage_ev[i]) CK(cudaEventCreateWithFlags(&w.stage_ev[i], cudaEventDisableTiming));
+  }
+  w.h_stage_cap = bytes;
+  return ACG_OK;
+}
+
 // K3/K3b (+ K4): prefilter engine.  mode 0 leaves all occurrences ordered like
 // find_overlapping_iter; mode 1 leaves the best match per start offset ordered by start (input of
 // the chain resolution).  When `h_hay` is given the span is first copied from (pinned) host
@@ -962,11 +1059,27 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
       const uint64_t chunk = a->pipeline_chunk;
       const uint64_t tail = std::min<uint64_t>(a->h.max_pattern_len, 1u << 30) + 64;
       uint64_t scanned = span_start;
+      // pageable source: the chunk goes through a page-locked ring buffer filled by host threads
+      const bool staged = span_end - span_start >= std::min<uint64_t>(8u << 20, chunk) && is_pageable_host(h_hay + span_start);
+      if (staged && (rc = ensure_stage(w, chunk))) return rc;
+      bool stage_used[2] = {false, false};
+      int stage_i = 0;
       CK(cudaEventRecord(w.ev2, w.copy_stream));
       for (uint64_t c0 = span_start; c0 < span_end; c0 += chunk) {
         const uint64_t c1 = std::min(span_end, c0 + chunk);
-        CK(cudaMemcpyAsync(const_cast<uint8_t*>(d_hay) + c0, h_hay + c0, c1 - c0, cudaMemcpyHostToDevice,
+        const uint8_t* src = h_hay + c0;
+        if (staged) {
+          if (stage_used[stage_i]) CK(cudaEventSynchronize(w.stage_ev[stage_i]));  // its previous H2D copy has left the buffer
+          CopyPool::get().copy(w.h_stage[stage_i], h_hay + c0, size_t(c1 - c0));
+          src = w.h_stage[stage_i];
+        }
+        CK(cudaMemcpyAsync(const_cast<uint8_t*>(d_hay) + c0, src, c1 - c0, cudaMemcpyHostToDevice,
                            w.copy_stream));
+        if (staged) {
+          CK(cudaEventRecord(w.stage_ev[stage_i], w.copy_stream));
+          stage_used[stage_i] = true;
+          stage_i ^= 1;
+        }
         CK(cudaEventRecord(w.ev3, w.copy_stream));
         CK(cudaStreamWaitEvent(w.stream, w.ev3, 0));
         const uint64_t upto = c1 == span_end ? span_end : (c1 > scanned + tail ? c1 - tail : scanned);
@@ -1286,7 +1399,7 @@ void shard_plan(uint64_t span_start, uint64_t span_end, int nranks, int rank, ui
 // rank 0's buffer (half `slot`) plus the closing barrier.  Returns without waiting for the transfer:
 // the step's workspace stays leased (the expand kernel reads its tuples) until sharded_wait.
 int sharded_begin(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on_device, uint64_t hay_len,
-                  uint64_t hay_off, uint64_t span_start, uint64_t span_end, int* slot_out) {
+                  uint64_t hay_off, uint64_t span_start, uint64_t span_end, bool streaming, int* slot_out) {
   if (!a || !c || !slot_out) return ACG_E_INVALID_ARG;
   // checks that do not depend on the rank come first, so that all ranks fail together
   if (span_start > span_end) return ACG_E_INVALID_SPAN;
@@ -1359,7 +1472,7 @@ int sharded_begin(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on
   if (any_failed) return rc ? rc : ACG_E_CUDA;  // some other rank failed: nothing was gathered
   if ((rc = acb::comm_ensure_recv(c, total))) return rc;  // every rank takes the same branch (same totals)
   uint8_t* target = nullptr;
-  if ((rc = acb::comm_record_target(c, slot, my_off, mine, &target))) return rc;
+  if ((rc = acb::comm_record_target(c, slot, my_off, mine, streaming, &target))) return rc;
   if (mine) {
     Workspace& w = cur_ws();
     acb::ExpandLaunch e;
@@ -1371,18 +1484,17 @@ int sharded_begin(const acg_dfa* a, acg_comm* c, const uint8_t* hay, bool hay_on
     e.span_start = lspan_s;
     e.offset_add = hay_off;
     e.out = reinterpret_cast<uint64_t*>(target);
-    // a stream of steps (the previous one is still in flight, so another will follow): leave room on
-    // every SM for the next step's scan CTA, which starts while these records travel
+    // blocking step: the kernel stores the records straight into rank 0's buffer.  Stream of steps
+    // (begin / wait): it expands into local memory -- short, HBM-bound -- and a copy engine ships the
+    // records, so that the next step's scan, which starts right behind, finds every SM free.
     e.small = 0;
-    if (c->steps[slot ^ 1].active || getenv("ACB_EXPAND_SMALL")) {
-      int sms = 148;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-      e.small = sms;
-    }
     CK(acb::launch_expand(e, c->stream));
   }
-  if ((rc = acb::comm_enqueue_close(c, slot, my_off, mine))) return rc;
+  bool flagged = false;
+  if ((rc = acb::comm_enqueue_close(c, slot, my_off, mine, streaming, c->step_seq + 1, &flagged))) return rc;
   cudaEventRecord(step.done, c->stream);
+  step.seq = c->step_seq + 1;
+  step.flagged = flagged;
   cur_ws().stats.launches += 3;
   step.mine = mine;
   step.total = total;
@@ -1410,6 +1522,11 @@ int sharded_wait(acg_comm* c, int slot, const acg_match** d_matches, uint64_t* n
   step.lease = nullptr;
   step.active = false;
   if (e != cudaSuccess) { cudaGetLastError(); return ACG_E_CUDA; }
+  // begin / wait form: the other ranks' records are in once their flag words say so
+  if (step.flagged) {
+    const int frc = acb::comm_wait_flags(c, step.seq);
+    if (frc) return frc;
+  }
   float gms = 0;
   cudaEventElapsedTime(&gms, step.begun, step.done);
   c->last_gather_ms = gms;
@@ -2062,7 +2179,7 @@ int acg_find_overlapping_sharded(const acg_dfa* a, acg_comm* c, const void* hay,
   if (stats) *stats = acg_shard_stats{};
   int slot = 0;
   int rc = sharded_begin(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
-                         span_start, span_end, &slot);
+                         span_start, span_end, /*streaming=*/false, &slot);
   if (rc == ACG_E_OVERFLOW && c && (c->steps[0].active || c->steps[1].active)) rc = ACG_E_INVALID_ARG;
   if (rc) return rc;
   return sharded_wait(c, slot, d_matches, n_total, h_out, h_cap, stats);
@@ -2071,8 +2188,29 @@ int acg_find_overlapping_sharded(const acg_dfa* a, acg_comm* c, const void* hay,
 int acg_find_overlapping_sharded_begin(const acg_dfa* a, acg_comm* c, const void* hay, int hay_on_device,
                                        uint64_t hay_len, uint64_t hay_global_offset, uint64_t span_start,
                                        uint64_t span_end, int* ticket) {
+  // ACB_GATHER_STORE=1: ship the records with the expand kernel's own peer stores, as the blocking
+  // call does (kept for measurements; the copy-engine payload is what lets the next scan run undisturbed)
+  static const bool store = getenv("ACB_GATHER_STORE") != nullptr;
   return sharded_begin(a, c, static_cast<const uint8_t*>(hay), hay_on_device != 0, hay_len, hay_global_offset,
-                       span_start, span_end, ticket);
+                       span_start, span_end, /*streaming=*/!store, ticket);
+}
+
+int acg_comm_mark(acg_comm* c, int which) {
+  if (!c || which < 0 || which > 1) return ACG_E_INVALID_ARG;
+  DeviceGuard guard(c->device);
+  if (!c->mark[which]) CK(cudaEventCreate(&c->mark[which]));
+  // behind everything the device has been given so far (searches run on their handles' own streams)
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(c->mark[which], c->stream));
+  CK(cudaEventSynchronize(c->mark[which]));
+  return ACG_OK;
+}
+
+int acg_comm_mark_elapsed_ms(const acg_comm* c, float* ms) {
+  if (!c || !ms || !c->mark[0] || !c->mark[1]) return ACG_E_INVALID_ARG;
+  DeviceGuard guard(c->device);
+  CK(cudaEventElapsedTime(ms, c->mark[0], c->mark[1]));
+  return ACG_OK;
 }
 int acg_find_overlapping_sharded_wait(acg_comm* c, int ticket, const acg_match** d_matches, uint64_t* n_total,
                                       acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats) {

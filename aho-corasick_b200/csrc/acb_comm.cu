@@ -2,6 +2,9 @@
 // traffic, cudaIpc peer mapping (NVLink / NVSwitch) for the match records.
 #include "acb_comm.hpp"
 
+#include <chrono>
+#include <thread>
+
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -183,6 +186,10 @@ int comm_create(const uint8_t* id128, int rank, int nranks, acg_comm** out) {
   if (cudaMalloc(&c->d_counts, (size_t(nranks) + 1) * 8) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaMallocHost(&c->h_counts, (size_t(nranks) + 1) * 8) != cudaSuccess) return fail(ACG_E_CUDA);
   if (cudaMalloc(&c->d_handle, 64) != cudaSuccess) return fail(ACG_E_CUDA);
+  if (cudaMallocHost(&c->h_flag_src, 16) != cudaSuccess || cudaMalloc(&c->d_flag_src, 16) != cudaSuccess ||
+      cudaMallocHost(&c->h_flags, size_t(nranks) * 8) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->poll, cudaStreamNonBlocking) != cudaSuccess)
+    return fail(ACG_E_CUDA);
   c->transport = ACG_TRANSPORT_PEER;  // until a mapping fails (comm_ensure_recv)
   int rc = comm_ensure_recv(c, 1 << 16);
   if (rc) return fail(rc);
@@ -213,8 +220,13 @@ void comm_destroy(acg_comm* c) {
   cudaFree(c->d_handle);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->h_view) cudaFreeHost(c->h_view);
+  if (c->h_flag_src) cudaFreeHost(c->h_flag_src);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
+  cudaFree(c->d_flag_src);
+  if (c->poll) cudaStreamDestroy(c->poll);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (auto& m : c->mark) if (m) cudaEventDestroy(m);
   for (auto& st : c->steps) {
     if (st.done) cudaEventDestroy(st.done);
     if (st.begun) cudaEventDestroy(st.begun);
@@ -258,7 +270,9 @@ int comm_ensure_recv(acg_comm* c, uint64_t total) {
   // The buffer cannot move under a step that is still writing into it: the caller waits first.
   if (c->steps[0].active || c->steps[1].active) return ACG_E_OVERFLOW;
   const uint64_t cap = total + total / 8 + 1024;
-  const size_t bytes = 2 * size_t(cap) * sizeof(acg_match);  // two halves
+  // two halves + the completion flags of the begin / wait form (8 bytes per rank, comm_flags)
+  const size_t flag_bytes = (size_t(c->nranks) * 8 + 255) & ~size_t(255);
+  const size_t bytes = 2 * size_t(cap) * sizeof(acg_match) + flag_bytes;
 #ifndef ACB_EMULATE
   NcclComm comm = static_cast<NcclComm>(c->nccl);
   if (c->recv_peer) { cudaIpcCloseMemHandle(c->recv_peer); c->recv_peer = nullptr; }
@@ -268,6 +282,7 @@ int comm_ensure_recv(acg_comm* c, uint64_t total) {
   if (c->rank == 0) {
     if (c->recv_own) { cudaFree(c->recv_own); c->recv_own = nullptr; }
     CKC(cudaMalloc(&c->recv_own, bytes));
+    CKC(cudaMemset(c->recv_own + (bytes - flag_bytes), 0, flag_bytes));  // sequence numbers only grow
     if (c->transport == ACG_TRANSPORT_PEER && c->nranks > 1) {
       if (cudaIpcGetMemHandle(&handle, c->recv_own) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     }
@@ -306,6 +321,7 @@ int comm_ensure_recv(acg_comm* c, uint64_t total) {
   if (c->rank == 0) {
     if (c->recv_own) { cudaFree(c->recv_own); c->recv_own = nullptr; }
     CKC(cudaMalloc(&c->recv_own, bytes));
+    CKC(cudaMemset(c->recv_own + (bytes - flag_bytes), 0, flag_bytes));
   }
   {
     std::unique_lock<std::mutex> lk(f->mu);
@@ -319,14 +335,17 @@ int comm_ensure_recv(acg_comm* c, uint64_t total) {
   return ACG_OK;
 }
 
-int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, uint8_t** target) {
-  if (c->transport == ACG_TRANSPORT_PEER || c->rank == 0) {
+int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, bool staged, uint8_t** target) {
+  const bool direct = c->rank == 0 || (c->transport == ACG_TRANSPORT_PEER && !staged);
+  if (direct) {
     uint8_t* base = c->rank == 0 ? c->recv_own : c->recv_peer;
     if (!base) return ACG_E_CUDA;
     *target = base + (size_t(slot) * size_t(c->recv_cap) + my_offset) * sizeof(acg_match);
     return ACG_OK;
   }
+  if (c->transport == ACG_TRANSPORT_PEER && !c->recv_peer) return ACG_E_CUDA;
   if (mine > c->send_cap) {
+    // (cudaFree waits for the device: a copy of the previous step that still reads the buffer ends first)
     if (c->send_buf) { cudaFree(c->send_buf); c->send_buf = nullptr; }
     const uint64_t cap = mine + mine / 8 + 1024;
     CKC(cudaMalloc(&c->send_buf, size_t(cap) * sizeof(acg_match)));
@@ -336,8 +355,25 @@ int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine,
   return ACG_OK;
 }
 
-int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine) {
-  (void)my_offset;
+int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, bool staged, uint64_t seq,
+                       bool* flagged) {
+  *flagged = false;
+  if (staged && c->transport == ACG_TRANSPORT_PEER && c->nranks > 1) {
+    if (c->rank != 0) {
+      // copy-engine payload: the records expanded into the local staging buffer travel to their place
+      // in rank 0's buffer as one device-to-device copy over NVLink -- no SM is held while they do --
+      // and the step's sequence number follows them into this rank's flag word on the same stream
+      if (mine) {
+        uint8_t* dst = c->recv_peer + (size_t(slot) * size_t(c->recv_cap) + my_offset) * sizeof(acg_match);
+        CKC(cudaMemcpyAsync(dst, c->send_buf, size_t(mine) * sizeof(acg_match), cudaMemcpyDeviceToDevice, c->stream));
+      }
+      c->h_flag_src[slot] = seq;
+      CKC(cudaMemcpyAsync(c->d_flag_src + slot, c->h_flag_src + slot, 8, cudaMemcpyHostToDevice, c->stream));
+      CKC(cudaMemcpyAsync(comm_flags(c) + c->rank, c->d_flag_src + slot, 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    *flagged = true;
+    return ACG_OK;
+  }
 #ifndef ACB_EMULATE
   NcclComm comm = static_cast<NcclComm>(c->nccl);
   if (c->nranks > 1) {
@@ -369,6 +405,28 @@ int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine)
   f->barrier(lk);
 #endif
   return ACG_OK;
+}
+
+int comm_wait_flags(acg_comm* c, uint64_t seq) {
+  if (c->rank != 0 || c->nranks < 2) return ACG_OK;
+  const uint64_t* flags = comm_flags(c);
+  if (!flags) return ACG_E_CUDA;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    CKC(cudaMemcpyAsync(c->h_flags, flags, size_t(c->nranks) * 8, cudaMemcpyDeviceToHost, c->poll));
+    CKC(cudaStreamSynchronize(c->poll));
+    bool all = true;
+    for (int r = 1; r < c->nranks; ++r) all = all && c->h_flags[r] >= seq;
+    if (all) return ACG_OK;
+    // a peer that died must not hang this rank forever
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) {
+      std::fprintf(stderr, "acb200: a rank's records of step %llu did not arrive within 60 s\n", (unsigned long long)seq);
+      return ACG_E_CUDA;
+    }
+#ifdef ACB_EMULATE
+    std::this_thread::yield();
+#endif
+  }
 }
 
 }  // namespace acb

@@ -46,6 +46,8 @@ struct acg_comm {
     cudaEvent_t done = nullptr;            // behind the closing barrier of the step on `stream`
     cudaEvent_t begun = nullptr;           // before the count exchange of the step
     float scan_ms = 0, order_ms = 0;
+    uint64_t seq = 0;                      // 1-based sequence number of the step
+    bool flagged = false;                  // closed by completion flags instead of the NCCL barrier
     uint64_t candidates = 0;
     int launches = 0;
   } steps[2];
@@ -53,6 +55,15 @@ struct acg_comm {
   const uint8_t* last_result = nullptr;    // rank 0: records of the step that was waited for last
   uint64_t last_total = 0;
   float last_gather_ms = 0;
+  cudaEvent_t mark[2] = {nullptr, nullptr};  // acg_comm_mark: device timestamps around a stream of steps
+  // Completion flags of the begin / wait form (peer transport): one 64-bit word per rank behind the two
+  // halves of rank 0's buffer.  A rank's copy engine writes the step's sequence number there right
+  // behind its records; rank 0 polls the words with small device-to-host copies.  No kernel takes part,
+  // so nothing sits on an SM waiting for a peer while the next step's scan wants that SM.
+  uint64_t* h_flag_src = nullptr;   // pinned, [2]: the value in transit, by step parity
+  uint64_t* d_flag_src = nullptr;   // device, [2]
+  uint64_t* h_flags = nullptr;      // pinned, [nranks]: rank 0's poll target
+  cudaStream_t poll = nullptr;
 };
 
 namespace acb {
@@ -66,12 +77,22 @@ int comm_exchange_counts(acg_comm* c, uint64_t mine, uint64_t* total, uint64_t* 
 // All ranks: make the receive buffer hold at least `total` records (collective when it must grow).
 int comm_ensure_recv(acg_comm* c, uint64_t total);
 // Where this rank's expand kernel writes record `my_offset` of half `slot` (peer transport), or its
-// local staging buffer (nccl transport; comm_enqueue_close then moves it).
-int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, uint8_t** target);
+// local staging buffer (nccl transport, or peer transport with `staged`; comm_enqueue_close then moves
+// it: ncclSend / a copy-engine copy into the mapped buffer).  `staged` is what a stream of steps uses:
+// the scan of the next step owns the SMs while the records travel.
+int comm_record_target(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, bool staged, uint8_t** target);
 // After the expand kernel was enqueued on c->stream: enqueue the payload transfer if the transport
 // needs one and the closing barrier; nothing is waited for (the step's `done` event is recorded by
 // the caller behind it).
-int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine);
+int comm_enqueue_close(acg_comm* c, int slot, uint64_t my_offset, uint64_t mine, bool staged, uint64_t seq,
+                       bool* flagged);
+// Rank 0, step closed by flags: wait until every rank's flag word has reached `seq`.
+int comm_wait_flags(acg_comm* c, uint64_t seq);
+// The flag words (rank 0: own memory; others: the mapping), behind the two halves.
+inline uint64_t* comm_flags(acg_comm* c) {
+  uint8_t* base = c->rank == 0 ? c->recv_own : c->recv_peer;
+  return base ? reinterpret_cast<uint64_t*>(base + 2 * size_t(c->recv_cap) * 24) : nullptr;
+}
 // Rank 0's half `slot` of the receive buffer.
 inline uint8_t* comm_half(acg_comm* c, int slot) { return c->recv_own + size_t(slot) * size_t(c->recv_cap) * 24; }
 

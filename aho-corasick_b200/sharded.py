@@ -100,6 +100,19 @@ class Comm:
             _ab().AhoCorasick._raise(rc)
         return n.value, (dptr.value or 0), {k: getattr(st, k) for k, _ in ShardStats._fields_}
 
+    def mark(self, which: int) -> None:
+        """Device timestamp (acg_comm_mark): 0 before a stream of steps, 1 after it."""
+        rc = self._lib.acg_comm_mark(self._h, which)
+        if rc:
+            raise _ab().DeviceError(rc)
+
+    def mark_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        rc = self._lib.acg_comm_mark_elapsed_ms(self._h, C.byref(ms))
+        if rc:
+            raise _ab().DeviceError(rc)
+        return ms.value
+
     def fetch(self) -> np.ndarray:
         n = C.c_uint64()
         self._lib.acg_comm_fetch(self._h, None, 0, C.byref(n))

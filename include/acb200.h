@@ -251,6 +251,16 @@ int acg_find_overlapping_sharded_begin(const acg_dfa* dfa, acg_comm* comm, const
                                        uint64_t span_end, int* ticket);
 int acg_find_overlapping_sharded_wait(acg_comm* comm, int ticket, const acg_match** d_matches, uint64_t* n_total,
                                       acg_match* h_out, uint64_t h_cap, acg_shard_stats* stats);
+/* In the begin / wait form the records travel by copy engine: the expand kernel writes them into this
+ * rank's own HBM and one device-to-device copy over NVLink puts them at their place in rank 0's
+ * buffer, so the next step's scan has every SM while they are under way (the blocking call stores them
+ * from the kernel itself, which is the shorter path for a single step).
+ *
+ * Device timestamps around a stream of steps: acg_comm_mark(comm, 0) before the first _begin and
+ * acg_comm_mark(comm, 1) after the last _wait each wait for the device to drain and record a CUDA
+ * event; acg_comm_mark_elapsed_ms gives the time between them on the device's clock. */
+int acg_comm_mark(acg_comm* comm, int which);
+int acg_comm_mark_elapsed_ms(const acg_comm* comm, float* ms);
 /* Rank 0: copy the records of the most recent sharded search to the host; *n_out = their number. */
 int acg_comm_fetch(const acg_comm* comm, acg_match* out, uint64_t cap, uint64_t* n_out);
 /* Rank 0: the same records in page-locked host memory owned by the communicator (one full-speed

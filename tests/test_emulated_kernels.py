@@ -159,6 +159,20 @@ def test_pipelined_host_path_with_many_chunks():
     eq(lf.try_find_iter_np(hay), O.Oracle(pats, match_kind=1, kind=O.KIND_DFA).find_iter_np(hay), "leftmost-first")
 
 
+def test_pageable_host_source_goes_through_the_copy_pool():
+    """A host haystack in ordinary (not page-locked) memory is staged by the library's copy threads into
+    a page-locked ring, chunk by chunk (run_prefilter; every pointer counts as pageable in the dry run).
+    Chunks of 6 MiB are above the pool's threshold, so the worker threads really split them; the ring is
+    reused from the third chunk on, and the last chunk is partial."""
+    pats, hay = workload(5000, 0xAC5000, (20 << 20) + 12345)
+    o = O.Oracle(pats, kind=O.KIND_DFA)
+    ac = build(pats)
+    assert ab._lib.acg_debug_set_pipeline_chunk(ac._h, 6 << 20) == 0
+    eq(ac.try_find_overlapping_iter_np(hay), o.find_overlapping_iter_np(hay))
+    eq(ac.try_find_overlapping_iter_np(hay, span=(5 << 20, hay.size - 7)),
+       o.find_overlapping_iter_np(hay, span=(5 << 20, hay.size - 7)), "sub-span")
+
+
 def test_tuple_buffer_overflow_rescan_and_brute_mode():
     """More matches than the initial tuple capacity (counter overflow -> regrow -> rescan) and a
     pattern set whose fingerprints cannot be selective (every offset is verified)."""
