@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <pthread.h>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -950,9 +951,17 @@ class CopyPool {
  public:
   static CopyPool& get() {
     // never destroyed: the workers wait on its condition variable for the life of the process, and
-    // destroying a condition variable that has waiters blocks (exit would hang)
-    static CopyPool* pool = new CopyPool;
-    return *pool;
+    // destroying a condition variable that has waiters blocks (exit would hang).  A forked child has
+    // none of the parent's threads: it drops the inherited object and starts its own pool on demand.
+    static std::once_flag once;
+    std::call_once(once, [] { pthread_atfork(nullptr, nullptr, [] { instance().store(nullptr); }); });
+    CopyPool* p = instance().load(std::memory_order_acquire);
+    if (!p) {
+      CopyPool* fresh = new CopyPool;
+      if (instance().compare_exchange_strong(p, fresh)) p = fresh;
+      // (lost the race: `fresh` stays allocated -- its workers are parked for good, a few KB once)
+    }
+    return *p;
   }
   // dst[0, n) = src[0, n), split over the pool's threads; returns when done
   void copy(uint8_t* dst, const uint8_t* src, size_t n) {
@@ -971,6 +980,10 @@ class CopyPool {
   }
 
  private:
+  static std::atomic<CopyPool*>& instance() {
+    static std::atomic<CopyPool*> p{nullptr};
+    return p;
+  }
   CopyPool() {
     unsigned n = std::thread::hardware_concurrency();
     n = n >= 16 ? 8 : (n >= 4 ? n / 2 : 0);

@@ -31,40 +31,184 @@ struct Edge {
   uint32_t to;
 };
 
-// Explicit trie. Node ids are allocated exactly like the reference allocates
-// NFA states (src/nfa/noncontiguous.rs:977-985, 1132-1143): 0 DEAD, 1 FAIL,
-// 2 unanchored start, 3 anchored start, then one node per new trie edge in
-// pattern order.
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// Explicit trie on flat arrays (a 100 000-pattern set has 8 * 10^5 nodes: one heap block per node
+// and list was most of the build).  Node ids are allocated exactly like the reference allocates
+// NFA states (src/nfa/noncontiguous.rs:977-985, 1132-1143): 0 DEAD, 1 FAIL, 2 unanchored start,
+// 3 anchored start, then one node per new trie edge in pattern order.
+//
+// Two phases.  While patterns are inserted, a node's edges are a list sorted by byte threaded
+// through one pool (nodes with many children additionally get a 256-entry direct table, so that
+// the hot shallow nodes are one load per step).  freeze() then lays the edges out contiguously per
+// node (CSR); from there on edges_of() / find() / step() read that form.
+//
+// Match lists: the patterns that end at a node ("own", insertion order) are threaded through
+// pid_next; the lists the failure-link pass composes (own ++ list(fail), src/nfa/noncontiguous.rs:
+// 490-523) live in one pool as immutable segments (hoff, hlen) -- a node without own patterns
+// shares its failure state's segment.
 struct Trie {
-  std::vector<std::vector<Edge>> edges;     // sorted by byte
-  std::vector<std::vector<uint32_t>> hits;  // match list, in the reference's emission order
-  std::vector<uint32_t> fail;
+  struct PoolEdge { uint32_t to, next; uint8_t byte; };
+  struct BuildNode {             // insertion phase
+    uint32_t first_edge = kNone;  // head of the node's sorted edge list
+    uint32_t dense_of = kNone;    // index of its direct table
+    uint32_t own_head = kNone, own_tail = kNone;  // first / last pattern ending here
+    uint32_t n_edges = 0;
+    uint32_t depth = 0;
+  };
+  struct Node {                  // frozen form: everything a visit needs in one 32-byte record
+    uint32_t eoff = 0, ecnt = 0;  // its edges in `edges`
+    uint32_t fail = kRoot;
+    uint32_t hoff = 0, hlen = 0;  // its composed match list in hpool
+    uint32_t own_head = kNone;
+    uint32_t dense_of = kNone;
+    uint32_t depth = 0;
+  };
+  std::vector<BuildNode> bn;
+  std::vector<PoolEdge> pool;
+  std::vector<uint32_t> dense;     // [tables][256]: child + 1, 0 = no edge
+  std::vector<uint32_t> pid_next;  // per pattern: next pattern ending at the same node
+  std::vector<Node> nodes;
+  std::vector<Edge> edges;         // sorted by byte within a node
+  std::vector<uint32_t> hpool;
   bool root_loop_closed = false;  // src/nfa/noncontiguous.rs:1620-1638
 
+  static constexpr unsigned kDenseAt = 8;  // children beyond which a node gets a direct table
+
+  size_t size() const { return bn.size(); }
   uint32_t add_node() {
-    edges.emplace_back();
-    hits.emplace_back();
-    fail.push_back(kRoot);
-    return uint32_t(edges.size() - 1);
+    bn.emplace_back();
+    return uint32_t(bn.size() - 1);
   }
-  int find(uint32_t s, uint8_t b) const {
-    const auto& e = edges[s];
-    auto it = std::lower_bound(e.begin(), e.end(), b, [](const Edge& x, uint8_t v) { return x.byte < v; });
-    return (it != e.end() && it->byte == b) ? int(it - e.begin()) : -1;
+  void reserve(size_t n_nodes, size_t pats) {
+    bn.reserve(n_nodes);
+    pool.reserve(n_nodes);
+    pid_next.reserve(pats);
+  }
+  // ---- insertion phase ----
+  uint32_t child(uint32_t s, uint8_t b) const {  // kNone if there is no edge
+    const BuildNode& n = bn[s];
+    if (n.dense_of != kNone) return dense[size_t(n.dense_of) * 256 + b] - 1u;  // 0 - 1 == kNone
+    for (uint32_t e = n.first_edge; e != kNone; e = pool[e].next) {
+      const PoolEdge& pe = pool[e];
+      if (pe.byte >= b) return pe.byte == b ? pe.to : kNone;
+    }
+    return kNone;
   }
   void link(uint32_t s, uint8_t b, uint32_t to) {
-    auto& e = edges[s];
-    auto it = std::lower_bound(e.begin(), e.end(), b, [](const Edge& x, uint8_t v) { return x.byte < v; });
-    if (it != e.end() && it->byte == b) it->to = to; else e.insert(it, Edge{b, to});
+    BuildNode& n = bn[s];
+    uint32_t prev = kNone, e = n.first_edge;
+    while (e != kNone && pool[e].byte < b) { prev = e; e = pool[e].next; }
+    if (e != kNone && pool[e].byte == b) {
+      pool[e].to = to;
+    } else {
+      const uint32_t ne = uint32_t(pool.size());
+      pool.push_back(PoolEdge{to, e, b});
+      if (prev == kNone) n.first_edge = ne; else pool[prev].next = ne;
+      ++n.n_edges;
+    }
+    if (n.dense_of == kNone && n.n_edges > kDenseAt) {
+      n.dense_of = uint32_t(dense.size() / 256);
+      dense.resize(dense.size() + 256, 0);
+      for (uint32_t x = n.first_edge; x != kNone; x = pool[x].next) dense[size_t(n.dense_of) * 256 + pool[x].byte] = pool[x].to + 1;
+    } else if (n.dense_of != kNone) {
+      dense[size_t(n.dense_of) * 256 + b] = to + 1;
+    }
+  }
+  bool has_own(uint32_t s) const { return bn[s].own_head != kNone; }
+  void add_own(uint32_t s, uint32_t pid) {  // pids arrive in ascending order, one call per pattern
+    if (pid_next.size() <= pid) pid_next.resize(size_t(pid) + 1, kNone);
+    BuildNode& n = bn[s];
+    if (n.own_tail == kNone) n.own_head = pid; else pid_next[n.own_tail] = pid;
+    n.own_tail = pid;
+  }
+  // ---- frozen form ----
+  void freeze() {
+    const size_t ns = size();
+    nodes.assign(ns, Node{});
+    edges.clear();
+    edges.reserve(pool.size() + 256);
+    for (size_t v = 0; v < ns; ++v) {
+      // (a node's edges sit wherever its children were created: ask for them a few nodes ahead)
+      if (v + 16 < ns && bn[v + 16].first_edge != kNone) __builtin_prefetch(&pool[bn[v + 16].first_edge]);
+      // the anchored start mirrors the root's edges (src/nfa/noncontiguous.rs:1561-1586)
+      const BuildNode& src = bn[v == kAnchoredRoot ? kRoot : v];
+      Node& n = nodes[v];
+      n.eoff = uint32_t(edges.size());
+      for (uint32_t e = src.first_edge; e != kNone; e = pool[e].next) edges.push_back(Edge{pool[e].byte, pool[e].to});
+      n.ecnt = uint32_t(edges.size()) - n.eoff;
+      n.own_head = bn[v].own_head;
+      n.depth = bn[v].depth;
+      n.dense_of = src.dense_of;
+    }
+    std::vector<BuildNode>().swap(bn);
+    std::vector<PoolEdge>().swap(pool);
+  }
+  struct EdgeSpan {
+    const Edge* b; const Edge* e;
+    const Edge* begin() const { return b; }
+    const Edge* end() const { return e; }
+  };
+  EdgeSpan edges_of(uint32_t s) const {
+    const Edge* b = edges.data() + nodes[s].eoff;
+    return EdgeSpan{b, b + nodes[s].ecnt};
+  }
+  uint32_t& fail(uint32_t s) { return nodes[s].fail; }
+  uint32_t fail(uint32_t s) const { return nodes[s].fail; }
+  uint32_t find(uint32_t s, uint8_t b) const {  // kNone if there is no edge
+    const Node& n = nodes[s];
+    if (n.dense_of != kNone) return dense[size_t(n.dense_of) * 256 + b] - 1u;
+    for (const Edge* e = edges.data() + n.eoff, *end = e + n.ecnt; e != end; ++e)
+      if (e->byte >= b) return e->byte == b ? e->to : kNone;
+    return kNone;
   }
   // goto function used while computing failure links: the root loops on
   // undefined bytes (src/nfa/noncontiguous.rs:1597-1606), DEAD is absorbing
   // (:1643-1646), everything else reports "undefined" as kFailId.
   uint32_t step(uint32_t s, uint8_t b) const {
     if (s == kDead) return kDead;
-    int i = find(s, b);
-    if (i >= 0) return edges[s][size_t(i)].to;
+    const uint32_t to = find(s, b);
+    if (to != kNone) return to;
     return s == kRoot ? kRoot : kFailId;
+  }
+  // composed match lists
+  bool has_hits(uint32_t s) const { return nodes[s].hlen != 0; }
+  uint32_t hlen(uint32_t s) const { return nodes[s].hlen; }
+  void share_list(uint32_t s, uint32_t of) { nodes[s].hoff = nodes[of].hoff; nodes[s].hlen = nodes[of].hlen; }
+  void start_list(uint32_t s) {  // list(s) = own(s), at the end of the pool
+    Node& n = nodes[s];
+    n.hoff = uint32_t(hpool.size());
+    uint32_t c = 0;
+    for (uint32_t p = n.own_head; p != kNone; p = pid_next[p]) { hpool.push_back(p); ++c; }
+    n.hlen = c;
+  }
+  // list(s) ++= list(f).  list(s) is either empty or the pool's last segment (start_list just ran).
+  void append_list(uint32_t s, uint32_t f) {
+    if (nodes[f].hlen == 0) return;
+    if (nodes[s].hlen == 0) { share_list(s, f); return; }
+    append_copy(s, f);
+  }
+  // the same for a list(s) that may sit anywhere: a fresh segment list(s) ++ list(f)
+  void extend_list(uint32_t s, uint32_t f) {
+    if (nodes[f].hlen == 0) return;
+    Node& n = nodes[s];
+    if (n.hlen == 0) { share_list(s, f); return; }
+    if (size_t(n.hoff) + n.hlen != hpool.size()) {
+      const size_t from = n.hoff, cnt = n.hlen;
+      n.hoff = uint32_t(hpool.size());
+      hpool.resize(hpool.size() + cnt);
+      std::memmove(hpool.data() + n.hoff, hpool.data() + from, cnt * sizeof(uint32_t));
+    }
+    append_copy(s, f);
+  }
+  const uint32_t* list(uint32_t s) const { return hpool.data() + nodes[s].hoff; }
+
+ private:
+  void append_copy(uint32_t s, uint32_t f) {
+    const size_t from = nodes[f].hoff, cnt = nodes[f].hlen, at = hpool.size();
+    hpool.resize(at + cnt);  // may move the pool: copy by index afterwards
+    std::memmove(hpool.data() + at, hpool.data() + from, cnt * sizeof(uint32_t));
+    nodes[s].hlen += uint32_t(cnt);
   }
 };
 
@@ -228,12 +372,12 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   d.start_kind = opts.start_kind;
 
   Trie t;
+  {
+    size_t total_bytes = 0;
+    for (const PatternRef& pr : patterns) total_bytes += size_t(pr.n);
+    t.reserve(total_bytes + 4, patterns.size());
+  }
   for (int i = 0; i < 4; ++i) t.add_node();
-  t.fail[kDead] = kDead;
-  t.fail[kFailId] = kDead;       // allocated before the start id was known (:977-982)
-  t.fail[kRoot] = kDead;
-  t.fail[kAnchoredRoot] = kDead;  // :1584
-  std::vector<uint32_t> depth(4, 0);
 
   bool boundary[256] = {false};  // ByteClassSet, src/util/alphabet.rs:207-230
   auto mark_byte = [&](uint8_t b) { if (b > 0) boundary[b - 1] = true; boundary[b] = true; };
@@ -253,27 +397,33 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     uint32_t cur = kRoot;
     bool passed_match = false, shadowed = false;
     for (uint64_t i = 0; i < n; ++i) {
-      passed_match = passed_match || !t.hits[cur].empty();
+      passed_match = passed_match || t.has_own(cur);
       if (opts.match_kind == kLeftmostFirst && passed_match) { shadowed = true; break; }  // :1109-1114
       const uint8_t b = p[i];
       mark_byte(b);
       if (ci) mark_byte(flip_ascii_case(b));
-      int e = t.find(cur, b);
-      if (e >= 0) {
-        cur = t.edges[cur][size_t(e)].to;
+      const uint32_t to = t.child(cur, b);
+      if (to != kNone) {
+        cur = to;
       } else {
-        if (t.edges.size() > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;
+        if (t.size() > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;
         uint32_t nn = t.add_node();
-        depth.push_back(uint32_t(i + 1));
+        t.bn[nn].depth = uint32_t(i + 1);
         t.link(cur, b, nn);
         if (ci) t.link(cur, flip_ascii_case(b), nn);
         cur = nn;
       }
     }
-    if (!shadowed) t.hits[cur].push_back(uint32_t(pid));
+    if (!shadowed) t.add_own(cur, uint32_t(pid));
   }
-  const size_t ns = t.edges.size();
+  const size_t ns = t.size();
   lap("trie");
+  t.freeze();  // the anchored start mirrors the root's edges (:1561-1586)
+  t.fail(kDead) = kDead;
+  t.fail(kFailId) = kDead;       // allocated before the start id was known (:977-982)
+  t.fail(kRoot) = kDead;
+  t.fail(kAnchoredRoot) = kDead;  // :1584
+  lap("trie: contiguous form");
 
   // byte classes (src/util/alphabet.rs:235-250); `byte_classes(false)` => singletons (src/dfa.rs:436-440)
   uint8_t nfa_classes[256];
@@ -288,40 +438,49 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   while ((1u << d.stride2) < d.alphabet_len) ++d.stride2;
   const uint32_t s2 = d.stride2, stride = 1u << s2;
 
-  // anchored start mirrors the root's edges and matches (:1561-1586)
-  t.edges[kAnchoredRoot] = t.edges[kRoot];
-  t.hits[kAnchoredRoot] = t.hits[kRoot];
+  // ... and its matches
+  t.start_list(kRoot);
+  t.share_list(kAnchoredRoot, kRoot);
 
   // ---- failure links + match propagation (:1275-1374), BFS in ascending byte order ----
   std::vector<uint32_t> bfs;  // visit order, reused to fill DFA rows
   bfs.reserve(ns);
   {
     std::vector<uint8_t> seen(ci ? ns : 0, 0);
-    for (const Edge& e : t.edges[kRoot]) {
+    for (const Edge& e : t.edges_of(kRoot)) {
       if (e.to == kRoot || (ci && seen[e.to])) continue;
       bfs.push_back(e.to);
       if (ci) seen[e.to] = 1;
-      if (leftmost && !t.hits[e.to].empty()) t.fail[e.to] = kDead;
+      t.start_list(e.to);
+      if (leftmost && t.has_hits(e.to)) t.fail(e.to) = kDead;
     }
+    const bool root_hits = !leftmost && t.has_hits(kRoot);
     for (size_t qi = 0; qi < bfs.size(); ++qi) {
+      // the queue is known ahead: node records eight entries on, their edges four on, the records of
+      // those edges' targets two on -- by the time a node is dequeued its lines are in flight or here
+      if (qi + 8 < bfs.size()) __builtin_prefetch(&t.nodes[bfs[qi + 8]]);
+      if (qi + 4 < bfs.size()) __builtin_prefetch(t.edges.data() + t.nodes[bfs[qi + 4]].eoff);
+      if (qi + 2 < bfs.size())
+        for (const Edge& e : t.edges_of(bfs[qi + 2])) __builtin_prefetch(&t.nodes[e.to], 1);
       const uint32_t v = bfs[qi];
-      for (const Edge& e : t.edges[v]) {
+      const uint32_t fv = t.fail(v);
+      for (const Edge& e : t.edges_of(v)) {
         if (ci && seen[e.to]) continue;
         bfs.push_back(e.to);
         if (ci) seen[e.to] = 1;
-        if (leftmost && !t.hits[e.to].empty()) { t.fail[e.to] = kDead; continue; }
-        uint32_t f = t.fail[v];
-        while (t.step(f, e.byte) == kFailId) f = t.fail[f];
+        t.start_list(e.to);
+        if (leftmost && t.has_hits(e.to)) { t.fail(e.to) = kDead; continue; }
+        uint32_t f = fv;
+        while (t.step(f, e.byte) == kFailId) f = t.fail(f);
         f = t.step(f, e.byte);
-        t.fail[e.to] = f;
-        t.hits[e.to].insert(t.hits[e.to].end(), t.hits[f].begin(), t.hits[f].end());
-        if (t.hits[e.to].size() > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;
+        t.fail(e.to) = f;
+        t.append_list(e.to, f);
+        if (t.hlen(e.to) > kMaxIndex || t.hpool.size() > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;
       }
-      if (!leftmost && !t.hits[kRoot].empty())
-        t.hits[v].insert(t.hits[v].end(), t.hits[kRoot].begin(), t.hits[kRoot].end());  // :1368-1371
+      if (root_hits) t.extend_list(v, kRoot);  // :1368-1371
     }
   }
-  t.root_loop_closed = leftmost && !t.hits[kRoot].empty();
+  t.root_loop_closed = leftmost && t.has_hits(kRoot);
   lap("failure links + match lists");
 
   // ---- state permutation: DEAD, FAIL, MATCH.., START_U, START_A, NON-MATCH.. (:1399-1481) ----
@@ -330,7 +489,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   for (size_t i = 0; i < ns; ++i) slot[i] = uint32_t(i);
   uint32_t next_avail = 4;
   for (size_t i = 4; i < ns; ++i) {
-    if (t.hits[slot[i]].empty()) continue;
+    if (!t.has_hits(slot[i])) continue;
     std::swap(slot[i], slot[next_avail]);
     ++next_avail;
   }
@@ -338,7 +497,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   std::swap(slot[3], slot[n_start_a]);
   std::swap(slot[2], slot[n_start_u]);
   uint32_t n_max_match = next_avail - 3;
-  if (!t.hits[kAnchoredRoot].empty()) n_max_match = n_start_a;
+  if (t.has_hits(kAnchoredRoot)) n_max_match = n_start_a;
   for (size_t i = 0; i < ns; ++i) newid[slot[i]] = uint32_t(i);
 
   lap("state permutation");
@@ -358,7 +517,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   if (trans_len - stride > kMaxIndex) return ACG_E_STATE_ID_OVERFLOW;  // :462-478
   d.trans_len = trans_len;
   const size_t n_match_states = both ? size_t(n_max_match - 1) * 2 : size_t(n_max_match - 1);
-  std::vector<std::vector<uint32_t>> mlists(n_match_states);
+  std::vector<uint32_t> mnode(n_match_states, kNone);  // trie node whose list the match state reports
 
   auto rep_class = [&](uint8_t b) { return d.classes[b]; };
 
@@ -373,7 +532,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
       f.inherit_row.push_back(inherit);
       f.fill_id.push_back(fill);
       f.edge_off.push_back(uint32_t(f.edge_to.size()));
-      for (const Edge& e : t.edges[node]) {
+      for (const Edge& e : t.edges_of(node)) {
         f.edge_class.push_back(rep_class(e.byte));
         f.edge_to.push_back(newid[e.to] << s2);
       }
@@ -382,31 +541,37 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     add_row(kRoot, UINT32_MAX, t.root_loop_closed ? kDead : (newid[kRoot] << s2));
     add_row(kAnchoredRoot, UINT32_MAX, kDead);
     uint32_t cur_depth = 0;
-    for (uint32_t v : bfs) {
-      if (depth[v] != cur_depth) {  // BFS order: depths never decrease
-        cur_depth = depth[v];
+    f.edge_class.reserve(t.edges.size());
+    f.edge_to.reserve(t.edges.size());
+    for (size_t qi = 0; qi < bfs.size(); ++qi) {
+      if (qi + 8 < bfs.size()) { __builtin_prefetch(&t.nodes[bfs[qi + 8]]); __builtin_prefetch(&newid[bfs[qi + 8]]); }
+      if (qi + 4 < bfs.size()) __builtin_prefetch(t.edges.data() + t.nodes[bfs[qi + 4]].eoff);
+      if (qi + 2 < bfs.size())
+        for (const Edge& e : t.edges_of(bfs[qi + 2])) __builtin_prefetch(&newid[e.to]);
+      const uint32_t v = bfs[qi];
+      const uint32_t dv = t.nodes[v].depth;
+      if (dv != cur_depth) {  // BFS order: depths never decrease
+        cur_depth = dv;
         f.level_off.push_back(uint32_t(f.row.size()));
       }
-      add_row(v, t.fail[v] != kDead ? newid[t.fail[v]] : UINT32_MAX, kDead);
+      add_row(v, t.fail(v) != kDead ? newid[t.fail(v)] : UINT32_MAX, kDead);
     }
     f.level_off.push_back(uint32_t(f.row.size()));
     f.edge_off.push_back(uint32_t(f.edge_to.size()));
     auto add_shallow = [&](uint32_t node) {
-      for (const Edge& e : t.edges[node])
+      for (const Edge& e : t.edges_of(node))
         f.shallow.push_back(DenseFillPlan::ShallowEdge{newid[node], e.byte, newid[e.to]});
     };
     add_shallow(kRoot);
     for (uint32_t v : bfs) {
-      if (depth[v] >= 5) break;
+      if (t.nodes[v].depth >= 5) break;
       add_shallow(v);
     }
-    for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos) {
-      const auto& h = t.hits[slot[pos]];
-      if (!h.empty()) mlists[pos - 2] = h;
-    }
+    for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos)
+      if (t.has_hits(slot[pos])) mnode[pos - 2] = slot[pos];
     d.row_depth.assign(ns, 0xFFFF);
     d.row_depth[newid[kRoot]] = 0;
-    for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(depth[v], 0xFFFE));
+    for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(t.nodes[v].depth, 0xFFFE));
     d.max_special_id = n_max_special << s2;
     d.max_match_id = n_max_match << s2;
     d.start_unanchored_id = n_start_u << s2;
@@ -417,7 +582,7 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     uint32_t* T = d.trans.data();
     auto row_of = [&](uint32_t node) { return T + (size_t(newid[node]) << s2); };
     auto overlay_edges = [&](uint32_t node, uint32_t* row) {
-      for (const Edge& e : t.edges[node]) row[rep_class(e.byte)] = newid[e.to] << s2;
+      for (const Edge& e : t.edges_of(node)) row[rep_class(e.byte)] = newid[e.to] << s2;
     };
     // root: explicit loop (or DEAD once closed), then edges
     {
@@ -429,18 +594,16 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
     overlay_edges(kAnchoredRoot, row_of(kAnchoredRoot));  // undefined -> DEAD (fail == DEAD)
     for (uint32_t v : bfs) {
       uint32_t* row = row_of(v);
-      if (!anchored && t.fail[v] != kDead)
-        std::memcpy(row, row_of(t.fail[v]), sizeof(uint32_t) * d.alphabet_len);  // inherit delta(fail, .)
+      if (!anchored && t.fail(v) != kDead)
+        std::memcpy(row, row_of(t.fail(v)), sizeof(uint32_t) * d.alphabet_len);  // inherit delta(fail, .)
       overlay_edges(v, row);
     }
-    for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos) {
-      const auto& h = t.hits[slot[pos]];
-      if (!h.empty()) mlists[pos - 2] = h;
-    }
+    for (size_t pos = 2; pos <= n_max_match && pos < ns; ++pos)
+      if (t.has_hits(slot[pos])) mnode[pos - 2] = slot[pos];
     if (!anchored) {
       d.row_depth.assign(ns, 0xFFFF);
       d.row_depth[newid[kRoot]] = 0;
-      for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(depth[v], 0xFFFE));
+      for (size_t v = 4; v < ns; ++v) d.row_depth[newid[v]] = uint16_t(std::min<uint32_t>(t.nodes[v].depth, 0xFFFE));
     }
     d.max_special_id = n_max_special << s2;
     d.max_match_id = n_max_match << s2;
@@ -455,12 +618,12 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
       uint32_t* row = urow(kRoot);
       const uint32_t self = t.root_loop_closed ? kDead : newid[kRoot];
       for (uint32_t c = 0; c < alen; ++c) row[c] = self;
-      for (const Edge& e : t.edges[kRoot]) row[rep_class(e.byte)] = newid[e.to];
+      for (const Edge& e : t.edges_of(kRoot)) row[rep_class(e.byte)] = newid[e.to];
     }
     for (uint32_t v : bfs) {
       uint32_t* row = urow(v);
-      if (t.fail[v] != kDead) std::memcpy(row, urow(t.fail[v]), sizeof(uint32_t) * alen);
-      for (const Edge& e : t.edges[v]) row[rep_class(e.byte)] = newid[e.to];
+      if (t.fail(v) != kDead) std::memcpy(row, urow(t.fail(v)), sizeof(uint32_t) * alen);
+      for (const Edge& e : t.edges_of(v)) row[rep_class(e.byte)] = newid[e.to];
     }
     std::vector<uint32_t> map_u(ns, kDead), map_a(ns, kDead);
     uint32_t next_sid = 0;
@@ -478,12 +641,12 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
         uint32_t* row = T + map_u[pos];
         const uint32_t* src = U.data() + pos * alen;
         for (uint32_t c = 0; c < alen; ++c) row[c] = map_u[src[c]];
-        if (!t.hits[node].empty()) mlists[(map_u[pos] >> s2) - 2] = t.hits[node];
+        if (t.has_hits(node)) mnode[(map_u[pos] >> s2) - 2] = node;
       }
       if (pos != n_start_u) {
         uint32_t* row = T + map_a[pos];
-        for (const Edge& e : t.edges[node]) row[rep_class(e.byte)] = map_a[newid[e.to]];
-        if (!t.hits[node].empty()) mlists[(map_a[pos] >> s2) - 2] = t.hits[node];
+        for (const Edge& e : t.edges_of(node)) row[rep_class(e.byte)] = map_a[newid[e.to]];
+        if (t.has_hits(node)) mnode[(map_a[pos] >> s2) - 2] = node;
       }
     }
     d.max_special_id = map_a[n_max_special];
@@ -496,10 +659,15 @@ int build_dfa(const std::vector<PatternRef>& patterns, const BuildOptions& opts,
   // CSR of `matches: Vec<Vec<PatternID>>` (src/dfa.rs:96-99)
   d.match_offsets.assign(n_match_states + 1, 0);
   size_t total = 0;
-  for (size_t i = 0; i < n_match_states; ++i) { d.match_offsets[i] = uint32_t(total); total += mlists[i].size(); }
+  for (size_t i = 0; i < n_match_states; ++i) {
+    d.match_offsets[i] = uint32_t(total);
+    if (mnode[i] != kNone) total += t.hlen(mnode[i]);
+  }
   d.match_offsets[n_match_states] = uint32_t(total);
-  d.match_pids.reserve(total);
-  for (auto& l : mlists) d.match_pids.insert(d.match_pids.end(), l.begin(), l.end());
+  d.match_pids.resize(total);
+  for (size_t i = 0; i < n_match_states; ++i)
+    if (mnode[i] != kNone)
+      std::memcpy(d.match_pids.data() + d.match_offsets[i], t.list(mnode[i]), size_t(t.hlen(mnode[i])) * sizeof(uint32_t));
   lap("match CSR");
   return 0;
 }

@@ -69,7 +69,8 @@ def one(rng, it):
     if device_fill:
         b.device_fill(True)
     ac = b.build(pats)
-    experiment = rng.choice([0, 0] + list(range(32)))   # ACG_EXP_* kernel variants (acb200_debug.h)
+    # ACG_EXP_* kernel / plan variants (acb200_debug.h): KEY24 8, GLOBAL_TILES 16, STATIC_TILES 32, NO_BYTESCAN 64
+    experiment = rng.choice([0, 0, 0] + [a | b | c for a in (0, 8) for b in (0, 16, 32) for c in (0, 64)])
     assert ab._lib.acg_debug_set_experiment(ac._h, experiment) == 0
     o = O.Oracle(pats, match_kind=kind, ascii_case_insensitive=ci, start_kind=start_kind, byte_classes=bc, kind=O.KIND_DFA)
     if rng.random() < 0.3:
