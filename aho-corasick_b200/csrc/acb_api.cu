@@ -1074,7 +1074,7 @@ int run_prefilter(const acg_dfa* a, const uint8_t* d_hay, uint64_t readable, uin
       uint64_t scanned = span_start;
       // pageable source: the chunk goes through a page-locked ring buffer filled by host threads
       const bool staged = span_end - span_start >= std::min<uint64_t>(8u << 20, chunk) && is_pageable_host(h_hay + span_start);
-      if (staged && (rc = ensure_stage(w, chunk))) return rc;
+      if (staged && (rc = ensure_stage(w, std::min<uint64_t>(chunk, span_end - span_start)))) return rc;
       bool stage_used[2] = {false, false};
       int stage_i = 0;
       CK(cudaEventRecord(w.ev2, w.copy_stream));
