@@ -194,16 +194,17 @@ def test_pipelined_steps_two_in_flight():
             h = batches[-1]
             comm.find_overlapping(ac, h.ctypes.data, h.size, 0, (0, h.size))
             tickets = []
+            comm.mark(0)   # device timestamps around the loop (acg_comm_mark), as bench.py takes them
             for k, h in enumerate(batches):
                 tickets.append(comm.begin(ac, h.ctypes.data, h.size, 0, (0, h.size)))
-                if k == 1 and rank == 0:
-                    pass
                 if k >= 1:
                     n, dptr, st = comm.wait(tickets[k - 1])
                     if rank == 0:
                         got[k - 1] = comm.fetch()
                         assert n == len(got[k - 1])
             n, dptr, st = comm.wait(tickets[-1])
+            comm.mark(1)
+            assert comm.mark_elapsed_ms() >= 0.0
             if rank == 0:
                 got[-1] = comm.fetch()
             comm.close()
@@ -228,4 +229,6 @@ def test_pipelined_steps_two_in_flight():
     assert comm.wait(t0)[0] == len(wants[0]) and comm.wait(t1)[0] == len(wants[0])
     with pytest.raises(ab.DeviceError):
         comm.wait(t1)
+    with pytest.raises(ab.DeviceError):
+        S.Comm(S.unique_id(), 0, 1).mark_elapsed_ms()   # no marks recorded yet
     comm.close()
