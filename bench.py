@@ -336,17 +336,18 @@ def run_workload(rig, args, wl, steps, warmup, want_e2e=True, check=True):
     if world > 1 and not args.blocking_steps:
         # warm-up doubles as calibration: both forms of the step run `warmup` times untimed, the faster
         # (max over ranks) is the one the timed region uses
+        n_cal = max(3, warmup)
         rig.barrier()
         b_ms = 0.0
-        for _ in range(warmup):
+        for _ in range(n_cal):
             _, ms, gms, _ = step()
             b_ms += ms + gms
         rig.barrier()
         stream_of_steps(2)  # first use allocates the staging buffer and the second workspace
         rig.barrier()
-        _, p_ms, _ = stream_of_steps(warmup)
+        _, p_ms, _ = stream_of_steps(n_cal)
         b_s, p_s = rig.max_over_ranks(b_ms / 1e3, p_ms / 1e3)
-        calib = {"blocking_ms_per_step": b_s * 1e3 / warmup, "stream_ms_per_step": p_s * 1e3 / warmup}
+        calib = {"blocking_ms_per_step": b_s * 1e3 / n_cal, "stream_ms_per_step": p_s * 1e3 / n_cal, "steps": n_cal}
         if p_s < b_s:
             mode = "stream"
     rig.barrier()
